@@ -1,0 +1,148 @@
+/* bayeslands_b200.h - C-ABI of the B200-native Bayeslands hot path (libbayeslands_b200.so).
+ *
+ * Drop-in boundary.  The entry points replace what the reference binds through f2py for
+ * this path, batched over B independent (rain, erodibility) proposals:
+ *
+ *   reference interface (file:line under /root/reference)                      replaced by
+ *   ------------------------------------------------------------------------   -----------------------
+ *   PDalgo.pdstack.pitparams / pitfilling   libUtils/PDalgo.f90:271-321        bl_ctx_create, bl_run
+ *   sfd.directions_base / directions        libUtils/sfd.c:55-153  (sfd.pyf)   bl_run (stage SFD)
+ *   FLWnetwork.fstack.build                 libUtils/FLWnetwork.f90:21-71      bl_run (stage STACK)
+ *   FLOWalgo.flowcompute.discharge          libUtils/FLOWalgo.f90:53-81        bl_run (stage DISCHARGE)
+ *     .basinparameters/.basindrainage(all)  FLOWalgo.f90:130-297               bl_run (stage BASINS)
+ *     .flowcfl                              FLOWalgo.f90:299-330               bl_run (stage CFL)
+ *     .streampower/.getid1/.getids          FLOWalgo.f90:583-1180              bl_run (stage SPL)
+ *   sfd.diffusion                           libUtils/sfd.c:155-185             bl_run (stage DIFF)
+ *   buildFlux.streamflow / sediment_flux    simulation/buildFlux.py:21-320     bl_run (device-side step loop)
+ *   Model.run_to_time                       pyBadlands/model.py:218-505        bl_run(stops)
+ *   bl_mcmc.interpolateArray+likelihoodFunc bl_mcmc.py:167-215, :482-513       bl_run (checkpoint outputs)
+ *
+ * Ownership: every device buffer is caller-owned (PyTorch tensors): the caller allocates one workspace
+ * of bl_workspace_bytes() and the output buffers and passes raw device pointers.  Mesh/parameter structs
+ * hold HOST pointers; they are copied into the workspace by bl_ctx_create.  The library keeps no global
+ * state: contexts are independent and re-entrant (the reference's Fortran modules are not:
+ * libUtils/PDclass.f90:15-34, FLOWalgo.f90:15-23).
+ * Errors: every call returns 0 on success or a negative bl_status; bl_last_error() gives the message.
+ * Index convention: 0-based int32, a negative neighbour id terminates a list (libUtils/sfd.c:79-81).
+ */
+#ifndef BAYESLANDS_B200_H
+#define BAYESLANDS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BL_KP 20 /* padded neighbour slots (MAX_NEIGHBOURS, libUtils/sfd.c:14) */
+#define BL_NCKPT_MAX 8
+#define BL_NPTS_MAX 16
+
+typedef enum {
+    BL_OK = 0,
+    BL_ERR_ARG = -1,       /* bad argument / inconsistent mesh */
+    BL_ERR_CUDA = -2,      /* CUDA runtime error */
+    BL_ERR_SPACE = -3,     /* workspace too small */
+    BL_ERR_UNSUPPORTED = -4
+} bl_status;
+
+/* per-proposal status bits written by the device loop (bl_get_status) */
+#define BL_ST_CASCADE_GUARD 1u   /* pit cascade hit the iteration guard (reference would spin) */
+#define BL_ST_MARINE        2u   /* marine deposition reached (etopo path) but CDr/marine kernels disabled */
+#define BL_ST_DRAIN_CYCLE   4u   /* pit-drainage graph had a cycle: sequential fallback was used */
+#define BL_ST_NAN           8u   /* non-finite elevation produced */
+
+typedef struct {
+    int32_t N;                 /* TIN nodes */
+    int32_t bounds;            /* ghost nodes are ids 0..bounds-1 (recGrid.boundsPt) */
+    const int32_t *ngb;        /* [N][BL_KP] FVmesh.neighbours (negative = end) */
+    const double *edge;        /* [N][BL_KP] FVmesh.edge_length */
+    const double *vor;         /* [N][BL_KP] FVmesh.vor_edges */
+    const double *area;        /* [N] FVmesh.control_volumes */
+    const double *xy;          /* [N][2] FVmesh.node_coords */
+    const int32_t *borders;    /* [N] flow.borders  (simulation/buildFlux.py:139-141) */
+    const int32_t *borders2;   /* [N] flow.borders2 (buildFlux.py:149-151) */
+    const int32_t *indomain;   /* [N] flow.domain.contains_points (buildFlux.py:135-138) */
+    const int32_t *parent;     /* [bounds] flow.parentIDs */
+    const double *z0;          /* [N] initial elevation (model.elevation after load_xml) */
+    const double *disp;        /* [N] vertical displacement rate m/a, or NULL (model.disp) */
+    /* TIN -> regular grid table of bl_mcmc.interpolateArray (k = 3 nearest, weights 1/d) */
+    int32_t G;                 /* ny*nx output cells (0: no grid outputs) */
+    const int32_t *grid_idx;   /* [G][3] */
+    const double *grid_w;      /* [G][3] */
+    const int32_t *grid_exact; /* [G] 1 where the nearest node is at distance 0 */
+} bl_mesh;
+
+typedef struct {
+    double spl_m, spl_n;       /* FLOWalgo.eroparams (m, n) */
+    double eps, fill_th;       /* PDalgo.pitparams (epsilon, fillTH) */
+    double CDa, CDm, CDr;      /* creep coefficients */
+    double minDT, maxDT;       /* input.minDT / maxDT */
+    double hill_cfl, ms_cfl;   /* hillslope.CFL / CFLms (diffLinear.py:68, :142-144) */
+    double diffprop;           /* PDalgo.pitparams pyProp */
+    int32_t diffnb;            /* PDalgo.pitparams pyDiff */
+    int32_t depo;              /* flow.depo */
+    int32_t btype;             /* 0 fixed, 1 slope, 2 flat, 3 wall (buildFlux.py:292-302) */
+    int32_t shuffle_mode;      /* 0: bases ascending; 1: counter-hash shuffle (flowNetwork.py:316) */
+    double seapos;             /* force.sea0 */
+    int32_t nsea;              /* sea-level curve length (0: constant seapos) */
+    const double *seat;        /* [nsea] host */
+    const double *seav;        /* [nsea] host */
+    /* likelihood inputs (bl_mcmc.likelihoodFunc) */
+    const double *real_elev;   /* [G] observed final topography, host, or NULL */
+    int32_t npts;              /* erdp points (<= BL_NPTS_MAX) */
+    const int32_t *pts_cell;   /* [npts] flat grid cell index row*nx+col (bl_mcmc.py:156-157) */
+} bl_params;
+
+typedef struct bl_ctx bl_ctx;
+
+const char *bl_last_error(void);
+int bl_version(void);
+
+/* Bytes of device workspace bl_ctx_create needs for B proposals on this mesh. */
+size_t bl_workspace_bytes(const bl_mesh *mesh, const bl_params *par, int B);
+
+/* Build a context: validates the mesh (symmetric adjacency, ghost ids), derives the Gauss-Seidel level
+ * schedule of fillPD, uploads constants into `workspace` (a DEVICE pointer the caller owns). */
+int bl_ctx_create(const bl_mesh *mesh, const bl_params *par, int B, int device, void *workspace,
+                  size_t workspace_bytes, bl_ctx **out);
+int bl_ctx_destroy(bl_ctx *ctx);
+
+/* Model() + load_xml() + blackBox parameter pokes for all B proposals: elevation <- z0, cumdiff <- 0,
+ * tNow <- tStart.  rain/erod/seed are DEVICE pointers [B] (bl_mcmc.py:132-136; seeds replace
+ * model.py:68-74). */
+int bl_reset(bl_ctx *ctx, const double *rain_dev, const double *erod_dev, const uint64_t *seed_dev,
+             double tStart, void *stream);
+
+/* Model.run_to_time for every proposal: step each proposal through the stop times (HOST array, ascending).
+ * ckpt[i] >= 0 marks stops[i] as checkpoint number ckpt[i] (the 5 sim_interval times of blackBox): the
+ * TIN->grid interpolation of elevation / cumdiff is evaluated there.  Outputs are DEVICE pointers, any may
+ * be NULL:
+ *   out_pts  [B][BL_NCKPT_MAX][BL_NPTS_MAX]  cumdiff grid value at the erdp points, per checkpoint
+ *   out_sse  [B]                             sum (pred_elev - real_elev)^2 at the LAST checkpoint marked
+ *   out_elev [B][nck][G], out_erdp [B][nck][G]  full grids (nck = number of marked stops), optional  */
+int bl_run(bl_ctx *ctx, int nstops, const double *stops, const int32_t *ckpt, double *out_pts,
+           double *out_sse, double *out_elev, double *out_erdp, int nck, void *stream);
+
+/* One time step for every proposal (buildFlux.streamflow + sediment_flux with this tStop); leaves every
+ * per-stage product in the workspace for bl_get_field - the per-stage parity entry point. */
+int bl_step(bl_ctx *ctx, double tStop, void *stream);
+
+typedef enum {
+    BL_F_Z = 0, BL_F_CUMDIFF, BL_F_CUMHILL, BL_F_FILLH, BL_F_MAXH, BL_F_Q, BL_F_PITVOL, BL_F_ERO,
+    BL_F_DEPO, BL_F_SEDFLUX,                                    /* double [N] */
+    BL_F_RCV = 32, BL_F_RCV1, BL_F_STACK, BL_F_STACK1, BL_F_PITID, BL_F_PITDRAIN, BL_F_ALLDRAIN /* int32 [N] */
+} bl_field;
+
+/* Copy one per-proposal array to HOST memory (synchronises the stream). */
+int bl_get_field(bl_ctx *ctx, int field, int proposal, void *dst_host, void *stream);
+/* tNow[B], steps[B] (int64), status[B] (uint32), last dt[B] to HOST; any pointer may be NULL. */
+int bl_get_scalars(bl_ctx *ctx, double *tnow, int64_t *steps, uint32_t *status, double *last_dt,
+                   void *stream);
+/* number of kernel launches issued by this context so far (for bench.py's gpu_launches) */
+int64_t bl_launch_count(const bl_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
