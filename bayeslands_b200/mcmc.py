@@ -1,0 +1,220 @@
+"""`bl_mcmc.bayeslands_mcmc` look-alike on the batched B200 engine.
+
+Same names, argument meaning and return shapes as the reference (`bl_mcmc.py:61-835`) for the path this
+repo covers: `blackBox`, `interpolateArray` (folded into the engine), `likelihoodFunc`, the accept/reject
+core of `sampler` - plus batched variants (`blackBox_batch`, `likelihood_batch`, `sampler_chains`) because
+one GPU evaluates hundreds of proposals at once.  Plotting / file-dump helpers of the reference
+(`viewMap` ... `viewCrossSection`, `bl_mcmc.py:217-455`) are out of scope.
+
+Deviations, all documented in DESIGN.md:
+  * `load_xml` is not repeated per proposal: the mesh is built once.
+  * `m`, `n` arguments are accepted and ignored exactly like the reference's dead stores (F7).
+  * `pos_likl = np.zeros(samples, likelihood)` (bl_mcmc.py:618, a TypeError) becomes `np.full` (F11).
+  * RNG protocol (F6/H7): numpy global stream for proposals, stdlib `random` for `u`, explicit per-proposal
+    seeds for the base shuffle.
+"""
+from __future__ import annotations
+
+import collections
+import math
+import os
+import random
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import config, hostparams, mesh as meshmod
+from .engine import Engine
+
+
+def log_likelihood(sse_elev, G, pts_pred, pts_real, likl_sed, sed_weight=50.0):
+    """`likelihoodFunc` arithmetic (bl_mcmc.py:488-508): tau^2 is the MSE, so the elevation term collapses to
+    -G/2 (ln(2 pi tau^2) + 1).  Vectorised over a leading batch axis."""
+    sse_elev = np.asarray(sse_elev, dtype=np.float64)
+    tausq = sse_elev / G
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lik = -0.5 * G * np.log(2 * math.pi * tausq) - 0.5 * sse_elev / tausq
+        if likl_sed:
+            d2 = np.square(pts_pred[..., 1:, :] - pts_real[1:, :])          # [B, nt-1, npts]
+            npts = pts_real.shape[1]
+            t2 = d2.sum(axis=-1) / npts                                      # [B, nt-1]
+            lp = (-0.5 * npts * np.log(2 * math.pi * t2) - 0.5 * d2.sum(axis=-1) / t2).sum(axis=-1)
+            lik = lik + lp * sed_weight
+    return lik, tausq
+
+
+class bayeslands_mcmc(object):
+    def __init__(self, muted, simtime, samples, real_elev, real_erdp, real_erdp_pts, erdp_coords, filename,
+                 xmlinput, erodlimits, rainlimits, mlimit, nlimit, run_nb, likl_sed, batch: int = 1,
+                 device: int = 0, dem_xyz: Optional[np.ndarray] = None, sealevel: Optional[np.ndarray] = None,
+                 base_dir: Optional[str] = None, mesh=None, shuffle_seed: int = 0):
+        self.filename = filename
+        self.input = xmlinput
+        self.real_elev = np.asarray(real_elev, dtype=np.float64)
+        self.real_erdp = real_erdp
+        self.real_erdp_pts = np.asarray(real_erdp_pts, dtype=np.float64)
+        self.erdp_coords = np.asarray(erdp_coords)
+        self.likl_sed = likl_sed
+        self.simtime = simtime
+        self.samples = samples
+        self.run_nb = run_nb
+        self.muted = muted
+        self.erodlimits = erodlimits
+        self.rainlimits = rainlimits
+        self.mlimit = mlimit
+        self.nlimit = nlimit
+        self.step_rain = (rainlimits[1] - rainlimits[0]) * 0.03        # bl_mcmc.py:89-92
+        self.step_erod = (erodlimits[1] - erodlimits[0]) * 0.03
+        self.step_m = (mlimit[1] - mlimit[0]) * 0.01
+        self.step_n = (nlimit[1] - nlimit[0]) * 0.01
+        self.sim_interval = hostparams.sim_interval(simtime)            # bl_mcmc.py:94
+        self.burn_in = 0.05
+        # ---- built once instead of per proposal
+        self.inp = xmlinput if isinstance(xmlinput, config.Input) else config.parse_xml(xmlinput, base_dir=base_dir)
+        if mesh is None:
+            if dem_xyz is None:
+                dem_xyz = np.loadtxt(self.inp.demfile)
+            mesh = meshmod.build_from_dem(dem_xyz, self.inp.btype, self.inp.Afactor)
+        if sealevel is None and self.inp.seafile is not None:
+            sealevel = np.loadtxt(self.inp.seafile)
+        self.mesh = mesh
+        self.batch = int(batch)
+        self.engine = Engine(mesh, self.inp, self.batch, device=device, real_elev=self.real_elev,
+                             erdp_coords=self.erdp_coords, sealevel=sealevel)
+        self.G = self.engine.G
+        self.shuffle_seed = int(shuffle_seed)
+        self._evals = 0
+        # pinned staging for the end-to-end path
+        self._h_in = torch.empty((2, self.batch), dtype=torch.float64).pin_memory()
+        self._h_seed = torch.empty(self.batch, dtype=torch.int64).pin_memory()
+        self._h_sse = torch.empty(self.batch, dtype=torch.float64).pin_memory()
+        self._h_pts = torch.empty((self.batch, len(self.sim_interval), len(self.erdp_coords)),
+                                  dtype=torch.float64).pin_memory()
+
+    # ------------------------------------------------------------------------------------------------
+    def _seeds(self, n):
+        s = np.arange(self._evals, self._evals + n, dtype=np.int64) + self.shuffle_seed * 1000003
+        self._evals += n
+        return s
+
+    def blackBox_batch(self, rain, erodibility, grids: bool = False, seeds=None):
+        """`blackBox` for B proposals at once.  Returns (sse[B], pts[B, nt, npts], elev, erdp) as numpy; elev /
+        erdp are [B, nt, ny, nx] when `grids`.  Host buffers in, host buffers out (H2D/D2H inside)."""
+        rain = np.asarray(rain, dtype=np.float64); erodibility = np.asarray(erodibility, dtype=np.float64)
+        n = len(rain)
+        if n > self.batch:
+            raise ValueError("batch of %d proposals exceeds engine batch %d" % (n, self.batch))
+        if seeds is None:
+            seeds = self._seeds(n)
+        hin, hseed = self._h_in, self._h_seed
+        hin[0, :n] = torch.from_numpy(rain); hin[1, :n] = torch.from_numpy(erodibility)
+        hseed[:n] = torch.from_numpy(np.asarray(seeds, dtype=np.int64))
+        if n < self.batch:
+            hin[:, n:] = hin[:, :1]; hseed[n:] = hseed[:1]
+        eng = self.engine
+        dev_in = hin.to(eng.tdev, non_blocking=True)
+        dev_seed = hseed.to(eng.tdev, non_blocking=True)
+        eng.reset(dev_in[0], dev_in[1], dev_seed)
+        pts, sse, elev, erdp = eng.run_schedule(self.sim_interval, grids=grids)
+        self._h_sse.copy_(sse, non_blocking=True)
+        self._h_pts.copy_(pts, non_blocking=True)
+        torch.cuda.current_stream(eng.tdev).synchronize()
+        out_e = out_d = None
+        if grids:
+            ny, nx = self.mesh.grid_ny, self.mesh.grid_nx
+            out_e = elev[:n].cpu().numpy().reshape(n, len(self.sim_interval), ny, nx)
+            out_d = erdp[:n].cpu().numpy().reshape(n, len(self.sim_interval), ny, nx)
+        return self._h_sse.numpy()[:n].copy(), self._h_pts.numpy()[:n].copy(), out_e, out_d
+
+    def likelihood_batch(self, rain, erodibility, seeds=None):
+        """log-likelihood[B] (and tau^2_elev[B]) for B proposals - the end-to-end hot-path call."""
+        sse, pts, _, _ = self.blackBox_batch(rain, erodibility, grids=False, seeds=seeds)
+        return log_likelihood(sse, self.G, pts, self.real_erdp_pts, self.likl_sed)
+
+    # ---- reference-shaped single-proposal API ------------------------------------------------------
+    def blackBox(self, rain, erodibility, m, n):
+        """bl_mcmc.py:97-165: three OrderedDicts keyed by simulation time."""
+        sse, pts, elev, erdp = self.blackBox_batch([rain], [erodibility], grids=True)
+        elev_vec, erdp_vec, erdp_pts_vec = collections.OrderedDict(), collections.OrderedDict(), collections.OrderedDict()
+        for x, T in enumerate(self.sim_interval):
+            self.simtime = T
+            elev_vec[T] = elev[0, x]
+            erdp_vec[T] = erdp[0, x]
+            erdp_pts_vec[T] = pts[0, x]
+        return elev_vec, erdp_vec, erdp_pts_vec
+
+    def likelihoodFunc(self, input_vector, real_elev, real_erdp, real_erdp_pts, tausq_elev, tausq_erdp, tausq_erdp_pts):
+        """bl_mcmc.py:482-513 (the tausq_* arguments are ignored there too)."""
+        pred_elev_vec, pred_erdp_vec, pred_erdp_pts_vec = self.blackBox(input_vector[0], input_vector[1],
+                                                                       input_vector[2], input_vector[3])
+        tausq_elev = (np.sum(np.square(pred_elev_vec[self.simtime] - real_elev))) / real_elev.size
+        tausq_pts = np.zeros(self.sim_interval.size)
+        for i in range(self.sim_interval.size):
+            tausq_pts[i] = np.sum(np.square(pred_erdp_pts_vec[self.sim_interval[i]] - self.real_erdp_pts[i])) / real_erdp_pts.shape[1]
+        likelihood_elev = -0.5 * np.log(2 * math.pi * tausq_elev) - 0.5 * np.square(pred_elev_vec[self.simtime] - real_elev) / tausq_elev
+        likelihood_erdp_pts = 0
+        if self.likl_sed:
+            for i in range(1, self.sim_interval.size):
+                likelihood_erdp_pts += np.sum(-0.5 * np.log(2 * math.pi * tausq_pts[i]) - 0.5 * np.square(
+                    pred_erdp_pts_vec[self.sim_interval[i]] - self.real_erdp_pts[i]) / tausq_pts[i])
+            likelihood = np.sum(likelihood_elev) + (likelihood_erdp_pts * 50)
+        else:
+            likelihood = np.sum(likelihood_elev)
+        return [likelihood, pred_elev_vec, pred_erdp_vec, pred_erdp_pts_vec]
+
+    # ---- accept/reject core of sampler (bl_mcmc.py:633-704, :747-755) -------------------------------
+    def sampler_chains(self, nchains: Optional[int] = None, np_seed: int = 0, py_seed: int = 0, log=None):
+        """`nchains` independent random-walk Metropolis chains advanced in lock step, one batched forward
+        evaluation per iteration.  Chain c draws from its own numpy RandomState(np_seed + c) and
+        random.Random(py_seed + c) in the reference's order per iteration: normal(rain), normal(erod),
+        3 x normal(size=1) for the eta walk (consumed, unused - F8), then uniform for the accept test.
+        Returns dict(pos_rain, pos_erod, pos_likl [samples, nchains], accept_ratio[nchains])."""
+        C_ = int(nchains or self.batch)
+        S_ = self.samples
+        rs = [np.random.RandomState(np_seed + c) for c in range(C_)]
+        pr = [random.Random(py_seed + c) for c in range(C_)]
+        rain = np.array([r.uniform(self.rainlimits[0], self.rainlimits[1]) for r in rs])
+        erod = np.array([r.uniform(self.erodlimits[0], self.erodlimits[1]) for r in rs])
+        lik, _ = self.likelihood_batch(rain, erod)      # the reference evaluates the start twice (:569, :610)
+        pos_rain = np.zeros((S_, C_)); pos_erod = np.zeros((S_, C_)); pos_likl = np.zeros((S_, C_))
+        pos_rain[0], pos_erod[0], pos_likl[0] = rain, erod, lik
+        naccept = np.zeros(C_, dtype=np.int64)
+        eta = np.zeros(C_)
+        for i in range(S_ - 1):
+            p_rain = rain.copy(); p_erod = erod.copy()
+            for c in range(C_):
+                v = rain[c] + rs[c].normal(0, self.step_rain)
+                if not (v < self.rainlimits[0] or v > self.rainlimits[1]):
+                    p_rain[c] = v
+                v = erod[c] + rs[c].normal(0, self.step_erod)
+                if not (v < self.erodlimits[0] or v > self.erodlimits[1]):
+                    p_erod[c] = v
+                for _ in range(3):
+                    rs[c].normal(0, abs(eta[c] * 0.02) if eta[c] else 1.0, 1)
+            lik_p, _ = self.likelihood_batch(p_rain, p_erod)
+            for c in range(C_):
+                diff = lik_p[c] - lik[c]
+                try:
+                    mh = min(1, math.exp(diff))
+                except OverflowError:
+                    mh = 1
+                u = pr[c].uniform(0, 1)
+                if u < mh:
+                    lik[c], rain[c], erod[c] = lik_p[c], p_rain[c], p_erod[c]
+                    naccept[c] += 1
+            pos_rain[i + 1], pos_erod[i + 1], pos_likl[i + 1] = rain, erod, lik
+            if log is not None:
+                log(i, rain, erod, lik)
+        return dict(pos_rain=pos_rain, pos_erod=pos_erod, pos_likl=pos_likl, accept_ratio=naccept / max(1, S_ - 1) * 100.0)
+
+    def sampler(self):
+        """Single chain with the reference's draw order (global numpy stream + stdlib random)."""
+        out = self.sampler_chains(1, np_seed=0, py_seed=0)
+        if self.filename:
+            os.makedirs(self.filename, exist_ok=True)
+            with open(os.path.join(self.filename, "exp_data.txt"), "w") as f:       # storeParams, :457-480
+                for r, e, l in zip(out["pos_rain"][:, 0], out["pos_erod"][:, 0], out["pos_likl"][:, 0]):
+                    f.write("{0} {1} {2} \n".format(r, e, l))
+        return out["pos_rain"][:, 0], out["pos_erod"][:, 0], out["pos_likl"][:, 0], out["accept_ratio"][0]

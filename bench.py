@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py - MCMC forward-model evaluations per second on the BASELINE.json workload.
+
+A "step" is one pass of the hot path over one batch of B synthetic (rain, erodibility) proposals:
+`blackBox` (full pyBadlands run to simtime with the 5 sim_interval grids) + `likelihoodFunc`.
+Workload at N=1: BASELINE.json configs[1] = Examples/crater, full resolution (T = 50 000 a), batched
+proposals on one B200.  Proposals shard across GPUs (weak scaling, B per GPU); the only exchange is the
+NCCL all_gather of the B log-likelihoods per step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the reference cannot run here:
+Python 2 + gfortran + Triangle) on all host cores for the same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (npz, simtime, rain limits, erod limits, erdp coords, likl_sed)
+    "crater": ("crater", 50000, (0.0, 3.0), (3.e-5, 7.e-5),
+               [[60, 60], [52, 67], [74, 76], [62, 45], [72, 66], [85, 73], [90, 75], [44, 86], [100, 80], [88, 69]], True),
+    "crater_fast": ("crater_fast", 15000, (0.0, 3.0), (3.e-5, 7.e-5),
+                    [[60, 60], [72, 66], [85, 73], [90, 75], [44, 86], [100, 80], [88, 69], [79, 91], [96, 77], [42, 49]], True),
+}
+B_ALG_NODE_STEP = 340.0   # algorithmic bytes / node / time step / proposal
+B_ALG_CELL = 160.0        # bytes / grid cell / evaluation
+
+
+def load_config(name):
+    from bayeslands_b200 import config, mesh
+    npz, simtime, rl, el, coords, likl_sed = CONFIGS[name]
+    d = np.load(os.path.join(ROOT, "data", npz + ".npz"))
+    inp = config.parse_xml(str(d["xml"]))
+    m = mesh.build_from_dem(d["dem_xyz"], inp.btype, inp.Afactor)
+    return d, inp, m, simtime, rl, el, np.array(coords), likl_sed
+
+
+def proposals(step, rank, B, rl, el):
+    rng = np.random.default_rng(5678 + 1000 * step + rank)
+    return rng.uniform(rl[0], rl[1], B), rng.uniform(el[0], el[1], B), rng.integers(1, 2 ** 31, B).astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU oracle legs (the only places bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(cfg):
+    from oracle import oracle
+    d, inp, m, simtime, rl, el, coords, likl_sed = load_config(cfg)
+    _W.update(om=oracle.OracleModel(m, inp), d=d, simtime=simtime, coords=coords, likl_sed=likl_sed, oracle=oracle)
+
+
+def _cpu_eval(args):
+    rain, erod, seed = args
+    om, d = _W["om"], _W["d"]
+    ev, ed, pts = om.blackbox(rain, erod, _W["simtime"], _W["coords"], seed=int(seed))
+    T = sorted(ev)[-1]
+    lik, _ = _W["oracle"].likelihood(ev[T], d["final_elev"], np.array([pts[k] for k in sorted(pts)]),
+                                     d["final_erdp_pts"], _W["likl_sed"])
+    return lik, om.steps
+
+
+def cpu_baseline(cfg, budget_s=12.0):
+    """Oracle, one process, evaluations one after another (faithful to `python bl_mcmc.py`, 1 rank)."""
+    _cpu_init(cfg)
+    _, _, _, _, rl, el, _, _ = load_config(cfg)
+    r, e, s = proposals(10 ** 6, 0, 64, rl, el)
+    t0 = time.perf_counter()
+    n = 0
+    while n < len(r) and (n < 2 or time.perf_counter() - t0 < budget_s):
+        _cpu_eval((r[n], e[n], s[n]))
+        n += 1
+    dt = time.perf_counter() - t0
+    return dict(value=n / dt, unit="evals/s", cores=1, kind="port",
+                sample="%d %s evaluations, CPU oracle (C restatement, -O2), 1 process" % (n, cfg))
+
+
+def run_reference(args):
+    """--impl reference: the oracle port on every host core, bounded sample per step."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = args.config
+    ncores = os.cpu_count() or 1
+    _, _, m, simtime, rl, el, _, _ = load_config(cfg)
+    per_step = max(ncores, 8)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(ncores, initializer=_cpu_init, initargs=(cfg,)) as pool:
+        def one(step):
+            r, e, s = proposals(step, 0, per_step, rl, el)
+            return pool.map(_cpu_eval, list(zip(r, e, s)), chunksize=1)
+        for w in range(args.warmup):
+            one(-1 - w)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            one(k)
+        dt = time.perf_counter() - t0
+    val = per_step * args.steps / dt
+    line = dict(impl="reference", metric="mcmc_forward_model_evals_per_sec", value=val, unit="evals/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=dt / args.steps * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload="Examples/%s full blackBox+likelihood, T=%d a, N=%d TIN nodes" % (cfg, simtime, m.N),
+                            proposals_per_step=per_step),
+                cpu_baseline=dict(value=val, unit="evals/s", cores=ncores, kind="port",
+                                  sample="%d evaluations per step over %d processes, CPU oracle "
+                                         "(reference itself cannot run: py2+gfortran+Triangle)" % (per_step, ncores)),
+                e2e=dict(value=val, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(dev), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bayeslands_b200.mcmc import bayeslands_mcmc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = args.config
+    d, inp, m, simtime, rl, el, coords, likl_sed = load_config(cfg)
+    B = args.batch
+    mc = bayeslands_mcmc(True, simtime, 0, d["final_elev"], d["final_erdp"], d["final_erdp_pts"], coords, None, inp,
+                         el, rl, (0.4, 0.6), (0.9, 1.1), "bench", likl_sed, batch=B, device=local, mesh=m)
+    eng = mc.engine
+    dev = eng.tdev
+    gather = torch.empty(world * B, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing (value): inputs already in HBM when the timed region starts
+    def dev_step(step, ev0=None, ev1=None):
+        r, e, s = proposals(step, rank, B, rl, el)
+        dr = torch.as_tensor(r, device=dev); de = torch.as_tensor(e, device=dev); ds = torch.as_tensor(s, device=dev)
+        torch.cuda.synchronize(dev)
+        return dr, de, ds
+
+    staged = [dev_step(k) for k in range(args.steps)]
+    for w in range(args.warmup):
+        dr, de, ds = dev_step(-1 - w)
+        eng.reset(dr, de, ds); eng.run_schedule(mc.sim_interval)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = eng.launches
+    steps_total = 0
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(args.steps):
+        dr, de, ds = staged[k]
+        eng.reset(dr, de, ds)
+        kev[k][0].record()
+        pts, sse, _, _ = eng.run_schedule(mc.sim_interval)
+        kev[k][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gather, sse)
+    t_end.record()
+    barrier()
+    ms = t_start.elapsed_time(t_end)
+    kernel_ms = [a.elapsed_time(b) for a, b in kev]
+    launches = eng.launches - launches0
+    sc = eng.scalars()
+    steps_last = sc["steps"].astype(np.float64)           # time steps per evaluation of the last batch
+    status = int(np.bitwise_or.reduce(sc["status"]))
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the public API (host buffers in, host likelihoods out)
+    for w in range(max(1, args.warmup // 2)):
+        r, e, s = proposals(-100 - w, rank, B, rl, el)
+        mc.likelihood_batch(r, e, seeds=s)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        r, e, s = proposals(500 + k, rank, B, rl, el)
+        lik, _ = mc.likelihood_batch(r, e, seeds=s)
+        if world > 1:
+            dist.all_gather_into_tensor(gather, torch.as_tensor(lik, device=dev))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    e2e_val = world * B * args.steps / e2e_s
+    h2d = B * (8 + 8 + 8)
+    d2h = B * 8 + B * len(mc.sim_interval) * len(coords) * 8
+
+    if rank == 0:
+        # roofline of the dominant (only) kernel, bl_run_kernel: algorithmic bytes of the last launch / its duration
+        alg_bytes = float(np.sum(steps_last) * m.N * B_ALG_NODE_STEP + B * B_ALG_CELL * eng.G)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg_bytes / (kernel_ms[-1] * 1e-3) / 1e9
+        cpu = cpu_baseline(cfg) if world == 1 and not args.no_cpu else None
+        line = dict(metric="mcmc_forward_model_evals_per_sec", value=value, unit="evals/s", n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload="Examples/%s full blackBox+likelihood, T=%d a, N=%d TIN nodes, G=%d grid cells"
+                                         % (cfg, simtime, m.N, eng.G),
+                                proposals_per_gpu_per_step=B, mean_time_steps_per_eval=float(np.mean(steps_last)),
+                                l2_policy="per-step working set %.0f MB > L2 (fresh proposals every step)"
+                                          % (eng.workspace.numel() / 1e6),
+                                parallelism="proposals sharded, %d per GPU" % B, status_bits=status),
+                    e2e=dict(value=e2e_val, unit="evals/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                    gpu_launches=int(launches),
+                    roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                                  traffic=None, kernel="bl_run_kernel", kernel_ms=kernel_ms[-1],
+                                  peak_source="MEASURED_PEAKS.json" if peaks else "fallback",
+                                  share_of_step=sum(kernel_ms) / ms),
+                    clocks=clocks)
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=296)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="crater", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
