@@ -17,6 +17,9 @@ c_ip = C.POINTER(C.c_int32)
 BL_KP = 20
 BL_NCKPT_MAX = 8
 BL_NPTS_MAX = 16
+BL_NPHASE = 16
+PHASES = ["fill", "sfd", "stack1", "basins", "stack", "drainage", "discharge", "cfl", "streampower",
+          "newdt", "erodep", "apply"]
 
 # bl_field
 F_Z, F_CUMDIFF, F_CUMHILL, F_FILLH, F_MAXH, F_Q, F_PITVOL, F_ERO, F_DEPO, F_SEDFLUX = range(10)
@@ -45,7 +48,7 @@ class BlParams(C.Structure):
 
 
 EXPORTS = ("bl_last_error", "bl_version", "bl_workspace_bytes", "bl_ctx_create", "bl_ctx_destroy", "bl_reset",
-           "bl_run", "bl_step", "bl_get_field", "bl_get_scalars", "bl_launch_count")
+           "bl_run", "bl_step", "bl_get_field", "bl_get_scalars", "bl_get_phase_cycles", "bl_launch_count")
 
 _lib = None
 
@@ -79,6 +82,7 @@ def load():
     L.bl_step.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
     L.bl_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.bl_get_scalars.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bl_get_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bl_launch_count.restype = C.c_int64
     L.bl_launch_count.argtypes = [C.c_void_p]
     _lib = L

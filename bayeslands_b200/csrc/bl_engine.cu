@@ -28,6 +28,7 @@ constexpr int NWARP = TPB / 32;
 constexpr int NONE_I = -1;
 constexpr unsigned END_U = 0xFFFFFFFFu;
 constexpr int TERM_BIT = 0x40000000;
+constexpr int NPHASE = 16;
 
 thread_local std::string g_err;
 
@@ -58,6 +59,7 @@ struct DevConst {
     double *tnow, *lastdt;
     long long *steps;
     unsigned *status;
+    long long *phase_cyc; // [B][BL_NPHASE] clock64 cycles per phase (thread 0), diagnostics
 };
 
 enum { F_Z, F_CUMDIFF, F_CUMHILL, F_FILLH, F_MAXH, F_Q, F_SEDIN, F_QS, F_DEPO, F_ERO, F_PITVOL, F_PITVOLW,
@@ -982,21 +984,31 @@ __device__ void time_step(const DevConst &c, Smem &S, double &tNow, long long &s
 {
     const int tid = threadIdx.x;
     const double sea = sea_level(c, tNow);
+    long long *pc = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
+    long long t0 = clock64();
+#define TICK(i) do { if (tid == 0) { long long t1_ = clock64(); pc[i] += t1_ - t0; t0 = t1_; } } while (0)
     phase_fill(c, S, sea);
+    TICK(0);
     phase_sfd(c, S);
+    TICK(1);
     // real-surface stack (bases ascending), then filled-surface stack (bases shuffled)
     int nbase1, nbase;
     tree_links(c, S.P.i[I_RCV1], S.P.i[I_FC], S.P.i[I_NS], nullptr, nullptr, nullptr);
     phase_stack(c, S, S.P.i[I_RCV1], S.P.i[I_FC], S.P.i[I_NS], S.P.i[I_STACK1], S.P.i[I_POS1], S.P.i[I_LA], nbase1,
                 false, 0ull);
+    TICK(2);
     phase_basins(c, S, S.P.i[I_LA], nbase1);
+    TICK(3);
     // the filled tree reuses fc; its sibling links go to I_SUCC2 temporarily? no: keep I_NS for the real tree
     // (basin segments are needed later), filled-tree links live in I_LC/I_PS (+ I_SUCC as next-sibling).
     tree_links(c, S.P.i[I_RCV], S.P.i[I_FC], S.P.i[I_SUCC], S.P.i[I_LC], S.P.i[I_PS], S.P.i[I_CNT]);
     phase_stack(c, S, S.P.i[I_RCV], S.P.i[I_FC], S.P.i[I_SUCC], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase,
                 c.shuffle != 0, mix64(seed + (unsigned long long)step));
+    TICK(4);
     phase_drainage(c, S, S.P.i[I_LA], nbase1, sea);
+    TICK(5);
     phase_discharge(c, S, rain);
+    TICK(6);
     // CFL and time step (buildFlux.py:169-177)
     const double flowcfl = phase_cfl(c, S, erod);
     double cfl = fmin(flowcfl, c.hill);
@@ -1006,7 +1018,9 @@ __device__ void time_step(const DevConst &c, Smem &S, double &tNow, long long &s
     cfl = fmin(c.maxDT, cfl);
     // flowNetwork.compute_sedflux (flowNetwork.py:579-719)
     double newdt = cfl;
+    TICK(7);
     phase_streampower(c, S, erod, sea, newdt);
+    TICK(8);
     {
         const int N = c.N;
         const double *cdepo = S.P.f[F_DEPO], *cero = S.P.f[F_ERO], *pitVol = S.P.f[F_PITVOL];
@@ -1026,8 +1040,12 @@ __device__ void time_step(const DevConst &c, Smem &S, double &tNow, long long &s
         newdt = fmax(c.minDT, newdt);
         if (newdt < cfl) phase_streampower(c, S, erod, sea, newdt);
     }
+    TICK(9);
     phase_erodep(c, S, sea);
+    TICK(10);
     phase_apply(c, S, sea, newdt);
+    TICK(11);
+#undef TICK
     tNow += newdt;
     last_dt = newdt;
     ++step;
@@ -1110,6 +1128,7 @@ __global__ void bl_reset_kernel(const DevConst c, const double *rain, const doub
         c.steps[b] = 0;
         c.status[b] = 0u;
         c.lastdt[b] = 0.;
+        for (int i = 0; i < NPHASE; ++i) c.phase_cyc[(size_t)b * NPHASE + i] = 0;
     }
 }
 
@@ -1146,7 +1165,7 @@ namespace {
 struct Layout {
     size_t off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
         off_levo, off_gidx, off_gw, off_gex, off_real, off_pts, off_seat, off_seav, off_rain, off_erod, off_seed,
-        off_tnow, off_lastdt, off_steps, off_status, off_stops, off_ckpt, off_prop, total;
+        off_tnow, off_lastdt, off_steps, off_status, off_phase, off_stops, off_ckpt, off_prop, total;
     int KD, nlev;
 };
 
@@ -1194,6 +1213,7 @@ Layout make_layout(const bl_mesh *m, const bl_params *p, int B, int KD, int nlev
     L.off_lastdt = take((size_t)B * 8);
     L.off_steps = take((size_t)B * 8);
     L.off_status = take((size_t)B * 4);
+    L.off_phase = take((size_t)B * NPHASE * 8);
     L.off_stops = take((size_t)STOPS_CAP * 8);
     L.off_ckpt = take((size_t)STOPS_CAP * 4);
     L.off_prop = take((size_t)B * prop_bytes(m->N));
@@ -1338,6 +1358,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     c.lastdt = (double *)(ws + L.off_lastdt);
     c.steps = (long long *)(ws + L.off_steps);
     c.status = (unsigned *)(ws + L.off_status);
+    c.phase_cyc = (long long *)(ws + L.off_phase);
     ctx->device = device; ctx->B = B; ctx->ws = ws; ctx->ws_bytes = L.total;
     ctx->d_stops = (double *)(ws + L.off_stops);
     ctx->d_ckpt = (int *)(ws + L.off_ckpt);
@@ -1451,6 +1472,16 @@ extern "C" int bl_get_scalars(bl_ctx *ctx, double *tnow, int64_t *steps, uint32_
     if (status) CUDA_OK(cudaMemcpyAsync(status, ctx->c.status, B * 4, cudaMemcpyDeviceToHost, st));
     if (last_dt) CUDA_OK(cudaMemcpyAsync(last_dt, ctx->c.lastdt, B * 8, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
+    return BL_OK;
+}
+
+extern "C" int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst, void *stream)
+{
+    if (!ctx || !dst) { g_err = "bl_get_phase_cycles: null argument"; return BL_ERR_ARG; }
+    CUDA_OK(cudaSetDevice(ctx->device));
+    CUDA_OK(cudaMemcpyAsync(dst, ctx->c.phase_cyc, (size_t)ctx->B * NPHASE * 8, cudaMemcpyDeviceToHost,
+                            (cudaStream_t)stream));
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
     return BL_OK;
 }
 

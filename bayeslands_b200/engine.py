@@ -193,6 +193,12 @@ class Engine:
                                          self._stream()))
         return dict(tNow=tnow, steps=steps, status=status, last_dt=ldt)
 
+    def phase_cycles(self) -> np.ndarray:
+        """[B, BL_NPHASE] SM cycles per phase (see _lib.PHASES), accumulated since reset."""
+        out = np.zeros((self.B, _lib.BL_NPHASE), dtype=np.int64)
+        _lib.check(self.L.bl_get_phase_cycles(self.ctx, out.ctypes.data_as(C.c_void_p), self._stream()))
+        return out
+
     @property
     def launches(self) -> int:
         return int(self.L.bl_launch_count(self.ctx))

@@ -48,7 +48,7 @@ def load_config(name):
 
 
 def proposals(step, rank, B, rl, el):
-    rng = np.random.default_rng(5678 + 1000 * step + rank)
+    rng = np.random.default_rng(5678 + 1000 * (step + 100000) + rank)
     return rng.uniform(rl[0], rl[1], B), rng.uniform(el[0], el[1], B), rng.integers(1, 2 ** 31, B).astype(np.int64)
 
 

@@ -139,6 +139,11 @@ int bl_get_field(bl_ctx *ctx, int field, int proposal, void *dst_host, void *str
 /* tNow[B], steps[B] (int64), status[B] (uint32), last dt[B] to HOST; any pointer may be NULL. */
 int bl_get_scalars(bl_ctx *ctx, double *tnow, int64_t *steps, uint32_t *status, double *last_dt,
                    void *stream);
+/* diagnostics: SM clock cycles spent per phase of the time step, [B][BL_NPHASE] int64 to HOST.
+ * Phase order: fill, sfd, stack1, basins, stack, drainage, discharge, cfl, streampower, newdt(+rerun),
+ * erodep, apply. */
+#define BL_NPHASE 16
+int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst_host, void *stream);
 /* number of kernel launches issued by this context so far (for bench.py's gpu_launches) */
 int64_t bl_launch_count(const bl_ctx *ctx);
 

@@ -1,0 +1,31 @@
+"""Per-phase cycle breakdown of the device time step (diagnostics; run on the GPU box)."""
+import sys, os, json
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from bayeslands_b200 import _lib
+from bayeslands_b200.engine import Engine
+import torch
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "crater_fast"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 148
+d, inp, m, simtime, rl, el, coords, likl_sed = bench.load_config(cfg)
+eng = Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=coords)
+r, e, s = bench.proposals(0, 0, B, rl, el)
+from bayeslands_b200 import hostparams
+for it in range(2):
+    eng.reset(r, e, s)
+    torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    eng.run_schedule(hostparams.sim_interval(simtime))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+pc = eng.phase_cycles().astype(np.float64)
+steps = eng.scalars()["steps"]
+tot = pc.sum(1)
+print("config", cfg, "B", B, "wall ms", dt * 1e3, "mean steps", steps.mean())
+print("mean cycles/step per phase:")
+for i, nm in enumerate(_lib.PHASES):
+    print("  %-12s %10.0f cyc  %5.1f%%" % (nm, (pc[:, i] / steps).mean(), 100 * pc[:, i].sum() / tot.sum()))
+print("  total        %10.0f cyc/step  (%.1f us at 1.965 GHz)" % ((tot / steps).mean(), (tot / steps).mean() / 1965.0))
