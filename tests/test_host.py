@@ -1,0 +1,89 @@
+"""Host-side logic: XML subset, stop-time schedule, mesh contract, C-ABI symbols (no GPU compute)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_xml_defaults_and_values(crater_fast):
+    d, inp, m = crater_fast
+    assert inp.btype == "fixed" and inp.tEnd == 15000.0 and inp.tDisplay == 5000.0 and inp.maxDT == 5000.0
+    assert inp.fillmax == 15.0 and inp.SPLm == 0.5 and inp.SPLn == 1.0 and inp.SPLero == 9e-5
+    assert inp.CDa == 0.02 and inp.CDm == 0.05 and inp.CDr == 0.0 and inp.depo == 1 and inp.seapos == -1000.0
+    from bayeslands_b200 import config
+    e = config.parse_xml(str(np.load(os.path.join(ROOT, "data", "etopo_fast.npz"))["xml"]))
+    assert e.btype == "slope" and e.Afactor == 4 and e.diffnb == 10 and e.diffprop == 0.05 and e.CDr == 10.0
+    assert e.fillmax == 200.0 and e.seafile.endswith("sealevel.csv")
+    with pytest.raises(ValueError):
+        config.parse_xml("<badlands><time><start>0</start><end>1</end><display>1</display></time></badlands>")
+    with pytest.raises(ValueError):
+        config.parse_xml(str(d["xml"]).replace("<display>5000.</display>", "<display>4000.</display>"))
+
+
+def test_schedule_reproduces_run_to_time_stops():
+    """model.py:246-259, :447-486, :529-533: next_display is bumped inside the loop AND after every call."""
+    from bayeslands_b200 import config, hostparams
+    x = str(np.load(os.path.join(ROOT, "data", "crater.npz"))["xml"])
+    inp = config.parse_xml(x)
+    s = hostparams.Schedule(inp)
+    t, out = 0.0, []
+    for T in hostparams.sim_interval(50000):
+        tEnd, segs = s.stops_for(t, float(T))
+        out.append([g[0] for g in segs]); t = tEnd
+    assert out == [[], [5000.0, 10000.0, 12500.0], [20000.0, 25000.0], [30000.0, 35000.0, 37500.0], [45000.0, 50000.0]]
+    assert hostparams.sim_interval(15000).tolist() == [0, 3750, 7500, 11250, 15000]
+    # clamp to the XML end time (model.py:240-243)
+    s2 = hostparams.Schedule(inp)
+    tEnd, segs = s2.stops_for(0.0, 1e9)
+    assert tEnd == 50000.0 and segs[-1][0] == 50000.0
+
+
+def test_mesh_contract(crater_fast):
+    d, inp, m = crater_fast
+    fv = m.FVmesh
+    N = m.N
+    assert m.boundsPt == 488 and fv.neighbours.shape == (N, 20) and fv.neighbours.dtype == np.int32
+    assert (fv.neighbours[fv.neighbours < 0] == -2).all()
+    # symmetric adjacency, ghost cells have zero area, total area = (2400 + 20)^2
+    for i in range(0, N, 53):
+        for j in fv.neighbours[i][fv.neighbours[i] >= 0]:
+            assert i in fv.neighbours[j]
+    assert (fv.control_volumes[:m.boundsPt] == 0).all() and (fv.control_volumes[m.boundsPt:] > 0).all()
+    assert abs(fv.control_volumes.sum() - 2420.0 ** 2) < 1.0
+    # float32 round trip (FVmethod.py:152) and output grid (bl_mcmc.py:186-194)
+    assert np.array_equal(fv.control_volumes, fv.control_volumes.astype(np.float32).astype(np.float64))
+    assert (m.grid_ny, m.grid_nx) == (123, 123) == d["final_elev"].shape
+    # colour-ordered numbering: the Gauss-Seidel dependency depth of fillPD is the number of colours
+    lev = np.zeros(N, dtype=int)
+    for k in range(m.boundsPt, N):
+        nb = fv.neighbours[k]; nb = nb[(nb >= m.boundsPt) & (nb < k)]
+        lev[k] = 1 + (lev[nb].max() if len(nb) else 0)
+    assert lev.max() <= 6
+    # ghost elevations: 'fixed' copies the nearest interior neighbour (elevationTIN.py:52-75)
+    assert np.array_equal(m.elevation[:m.boundsPt], m.elevation[m.parentIDs])
+
+
+def test_cabi_exports_every_declared_symbol():
+    from bayeslands_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "bayeslands_b200.h")).read()
+    declared = set(re.findall(r"\b(bl_[a-z_]+)\s*\(", hdr)) - {"bl_get_status"}
+    assert declared, "no declarations parsed"
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert set(_lib.EXPORTS) <= declared
+    assert _lib.load().bl_version() >= 100
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from bayeslands_b200 import _lib
+    from bayeslands_b200.engine import Engine
+    with pytest.raises(_lib.BlError):
+        Engine(None, None, 1)

@@ -1,0 +1,190 @@
+"""CPU tests of the oracle (C restatement) - pinned against the reference where the reference can be had.
+
+* sfd.c is the one reference source that compiles here: oracle/_ref/libsfd_ref.so (built from
+  /root/reference by oracle/Makefile) pins or_directions_base / or_directions / or_diffusion bit for bit.
+* The Fortran routines have no reference tests: checked through hand cases and invariants.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+def _grid_mesh(nx, ny, z, dx=1.0):
+    """Small regular mesh with the D8 stencil through the product mesh builder."""
+    from bayeslands_b200 import mesh
+    return mesh.build_regular(nx, ny, dx, z, btype="fixed")
+
+
+class _Inp:
+    SPLm, SPLn, CDa, CDm, CDr, minDT, maxDT = 0.5, 1.0, 0.02, 0.05, 0.0, 1.0, 5000.0
+    diffprop, diffnb, depo, btype, fillmax, SPLero = 0.9, 5, 1, "fixed", 15.0, 5e-5
+    Hillslope, tStart, tEnd, tDisplay, seapos, seafile = True, 0.0, 15000.0, 5000.0, -1000.0, None
+    rainVal = np.array([1.0]); rainTime = np.array([[0.0, 15000.0]]); tectTime = np.array([[1e9, 2e9]])
+
+
+def test_sfd_3x3_hand_case():
+    # 3x3 grid probe of sfd.c (SURVEY.md section 4 idea): lowest-elevation neighbour wins
+    L = oracle.lib()
+    z = np.array([9., 8., 7., 9.5, 6.5, 6., 10., 9., 5.])
+    # 4-neighbour lists on a 3x3 grid, order: E, N, W, S (any fixed order)
+    ngb = np.full((9, 20), -2, dtype=np.int32)
+    for j in range(3):
+        for i in range(3):
+            k, q = j * 3 + i, 0
+            for dj, di in ((0, 1), (1, 0), (0, -1), (-1, 0)):
+                jj, ii = j + dj, i + di
+                if 0 <= jj < 3 and 0 <= ii < 3:
+                    ngb[k, q] = jj * 3 + ii; q += 1
+    m = oracle._Mesh(); m.N = 9; m.bounds = 0; m.ngb = ngb.ctypes.data_as(c_ip)
+    base = np.zeros(9, dtype=np.int32); rcv = np.zeros(9, dtype=np.int32)
+    L.or_directions_base(C.byref(m), z.ctypes.data_as(c_dp), base.ctypes.data_as(c_ip), rcv.ctypes.data_as(c_ip))
+    assert rcv.tolist() == [1, 4, 5, 4, 5, 8, 7, 8, 8]  # lowest neighbour, not steepest
+    assert (base >= 0).sum() == 1 and base[8] == 8
+    ref = oracle.ref_sfd()
+    if ref is not None:
+        b2 = np.zeros(9, dtype=np.int32); r2 = np.zeros(9, dtype=np.int32)
+        gids = np.arange(9, dtype=np.int32)
+        ed = np.zeros((9, 20))
+        ref.directions_base(z.ctypes.data_as(c_dp), ngb.ctypes.data_as(c_ip), ed.ctypes.data_as(c_dp),
+                            ed.ctypes.data_as(c_dp), gids.ctypes.data_as(c_ip), b2.ctypes.data_as(c_ip),
+                            r2.ctypes.data_as(c_ip), 9, 9)
+        assert np.array_equal(r2, rcv) and np.array_equal(b2, base)
+
+
+@pytest.mark.skipif(oracle.ref_sfd() is None, reason="oracle/_ref not built (reference absent)")
+def test_sfd_routines_match_reference_sfd_c(crater_fast):
+    """or_directions_base / or_directions / or_diffusion == the reference's own sfd.c, bit for bit, on the
+    crater mesh with perturbed (tie-rich and random) surfaces."""
+    d, inp, m = crater_fast
+    L, ref = oracle.lib(), oracle.ref_sfd()
+    om = oracle.OracleModel(m, inp)
+    N = m.N
+    rng = np.random.default_rng(0)
+    gids = np.arange(N, dtype=np.int32)
+    ngb, ed, di = om._keep["ngb"], om._keep["vor"], om._keep["edge"]
+    for trial in range(4):
+        z = m.elevation + (rng.normal(0, 2.0, N) if trial else 0.0)
+        if trial == 2:
+            z = np.round(z)                     # many exact ties: first-in-list must win
+        z = np.ascontiguousarray(z)
+        fill = np.ascontiguousarray(np.maximum(z, z.mean()))
+        for use_fill in (False, True):
+            b = np.zeros(N, dtype=np.int32); r = np.zeros(N, dtype=np.int32)
+            b2 = np.zeros(N, dtype=np.int32); r2 = np.zeros(N, dtype=np.int32)
+            if not use_fill:
+                L.or_directions_base(C.byref(om.cm), z.ctypes.data_as(c_dp), b.ctypes.data_as(c_ip), r.ctypes.data_as(c_ip))
+                ref.directions_base(z.ctypes.data_as(c_dp), ngb.ctypes.data_as(c_ip), ed.ctypes.data_as(c_dp),
+                                    di.ctypes.data_as(c_dp), gids.ctypes.data_as(c_ip), b2.ctypes.data_as(c_ip),
+                                    r2.ctypes.data_as(c_ip), N, N)
+            else:
+                mh = np.zeros(N); md = np.zeros(N); mh2 = np.zeros(N); md2 = np.zeros(N)
+                L.or_directions(C.byref(om.cm), fill.ctypes.data_as(c_dp), z.ctypes.data_as(c_dp), b.ctypes.data_as(c_ip),
+                                r.ctypes.data_as(c_ip), mh.ctypes.data_as(c_dp), md.ctypes.data_as(c_dp))
+                ref.directions(fill.ctypes.data_as(c_dp), z.ctypes.data_as(c_dp), ngb.ctypes.data_as(c_ip),
+                               ed.ctypes.data_as(c_dp), di.ctypes.data_as(c_dp), gids.ctypes.data_as(c_ip),
+                               b2.ctypes.data_as(c_ip), r2.ctypes.data_as(c_ip), mh2.ctypes.data_as(c_dp),
+                               md2.ctypes.data_as(c_dp), N, N)
+                assert np.array_equal(mh, mh2) and np.array_equal(md, md2)
+            assert np.array_equal(r, r2) and np.array_equal(b, b2)
+        df = np.zeros(N); df2 = np.zeros(N)
+        L.or_diffusion(C.byref(om.cm), z.ctypes.data_as(c_dp), df.ctypes.data_as(c_dp))
+        bord2 = om._keep["borders2"]
+        ref.diffusion(z.ctypes.data_as(c_dp), bord2.ctypes.data_as(c_ip), ngb.ctypes.data_as(c_ip), ed.ctypes.data_as(c_dp),
+                      di.ctypes.data_as(c_dp), gids.ctypes.data_as(c_ip), df2.ctypes.data_as(c_dp), N, N)
+        assert np.array_equal(df, df2)
+
+
+def test_pairwise_sum_is_numpy_sum():
+    L = oracle.lib()
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 7, 8, 9, 127, 128, 129, 1000, 4097, 15129):
+        a = np.ascontiguousarray(rng.normal(0, 1e3, n) ** 3)
+        assert L.or_pairwise_sum(a.ctypes.data_as(c_dp), n) == (np.sum(a) if n else 0.0)
+
+
+def test_interp_matches_numpy_average(crater_fast):
+    d, inp, m = crater_fast
+    om = oracle.OracleModel(m, inp)
+    rng = np.random.default_rng(1)
+    v = rng.normal(50, 20, m.N)
+    got = om.interpolate(v).ravel()
+    idx, w = m.grid_idx, m.grid_w
+    with np.errstate(invalid="ignore"):
+        want = np.average(v[idx], weights=w, axis=1)
+    on = m.grid_exact == 1
+    want[on] = v[idx[on, 0]]
+    assert np.array_equal(got, want)
+
+
+def test_step_invariants(crater_fast):
+    """Invariants SURVEY.md section 4 asks for: stack is a permutation with every node after its receiver,
+    sum of Q at the bases = sum(area*rain), fillH >= z, pit volumes consistent."""
+    d, inp, m = crater_fast
+    om = oracle.OracleModel(m, inp, seed=5)
+    om.reset(1.5, 5e-5, seed=5)
+    area = m.FVmesh.control_volumes
+    for step in range(4):
+        om.streamflow()
+        for stack, rcv in ((om.stack, om.rcv), (om.stack1, om.rcv1)):
+            assert np.array_equal(np.sort(stack), np.arange(m.N))
+            pos = np.empty(m.N, dtype=np.int64); pos[stack] = np.arange(m.N)
+            nb = rcv != np.arange(m.N)
+            assert (pos[rcv[nb]] < pos[nb]).all()
+        assert (om.fillH >= om.z).all()
+        bases = om.rcv == np.arange(m.N)
+        rain = np.where(np.arange(m.N) >= m.boundsPt, 1.5, 0.0)
+        assert np.isclose(om.Q[bases].sum(), (area * rain).sum(), rtol=1e-12)
+        wet = om.fillH > om.z
+        pits = np.flatnonzero(om.pitVol >= 0)
+        for p in pits[:20]:
+            mem = (om.pitID == p) & wet
+            assert np.isclose(om.pitVol[p], -1 + ((om.fillH - om.z) * area)[mem].sum(), rtol=1e-9, atol=1e-9)
+        om.sediment_flux(15000.0)
+    assert om.tNow > 0 and np.isfinite(om.z).all()
+
+
+def test_fill_fixed_point_residual(crater_fast):
+    """fill_mode=1 (run to convergence) is the greatest fixed point of W = max(z, min(min_nb W + eps, cap))."""
+    d, inp, m = crater_fast
+    om = oracle.OracleModel(m, inp, fill_mode=1)
+    om.streamflow()
+    W, z = om.fillH.copy(), om.z.copy()
+    ngb = m.FVmesh.neighbours
+    Wn = np.where(ngb >= 0, W[np.maximum(ngb, 0)], np.inf).min(1)
+    F = np.maximum(z, np.minimum(Wn + 0.01, np.maximum(z, -1000.0) + inp.fillmax))
+    inner = np.arange(m.N) >= m.boundsPt
+    assert np.array_equal(W[inner], F[inner]) and np.array_equal(W[~inner], z[~inner])
+
+
+def test_shuffle_is_permutation_and_seeded():
+    L = oracle.lib()
+    base = np.arange(100, 400, 3, dtype=np.int32)
+    keys = np.zeros(len(base), dtype=np.uint64)
+    outs = []
+    for seed, step in ((1, 0), (1, 1), (2, 0), (1, 0)):
+        b = base.copy()
+        L.or_shuffle_base(b.ctypes.data_as(c_ip), len(b), C.c_uint64(seed), C.c_uint64(step), keys.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(np.sort(b), base)
+        outs.append(b)
+    assert np.array_equal(outs[0], outs[3]) and not np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[0], outs[2])
+
+
+def test_sea_level_matches_scipy_interp1d():
+    from scipy import interpolate
+    import os
+    from conftest import ROOT
+    sl = np.load(os.path.join(ROOT, "data", "etopo_fast.npz"))["sealevel"]
+    f = interpolate.interp1d(sl[:, 0], sl[:, 1], kind="linear")
+    p = oracle._Params(); t = np.ascontiguousarray(sl[:, 0]); v = np.ascontiguousarray(sl[:, 1])
+    p.nsea = len(t); p.seat = t.ctypes.data_as(c_dp); p.seav = v.ctypes.data_as(c_dp)
+    L = oracle.lib()
+    rng = np.random.default_rng(0)
+    for x in list(rng.uniform(0, 5e5, 200)) + [0.0, 100.0, 5e5, 250.0, 499999.0]:
+        assert L.or_sea(C.byref(p), float(x)) == float(f(x))
+    assert L.or_sea(C.byref(p), -5.0) == sl[0, 1] and L.or_sea(C.byref(p), 9e9) == sl[-1, 1]
