@@ -23,12 +23,16 @@
 
 namespace {
 
-constexpr int TPB = 1024;
+#ifndef BL_TPB
+#define BL_TPB 1024
+#endif
+constexpr int TPB = BL_TPB;
 constexpr int NWARP = TPB / 32;
 constexpr int NONE_I = -1;
 constexpr unsigned END_U = 0xFFFFFFFFu;
 constexpr int TERM_BIT = 0x40000000;
 constexpr int NPHASE = 16;
+constexpr int DYN_SMEM = 229376; // dynamic shared memory of the fast kernel (224 KB)
 
 thread_local std::string g_err;
 
@@ -38,6 +42,10 @@ thread_local std::string g_err;
 struct DevConst {
     int N, bounds, KD, nlev, G, npts, nsea, B;
     const int *ngb;             // [KD][N]
+    const unsigned short *ngb16; // [N][KDT] node-major u16 copy for the shared-memory path (0xFFFF = none)
+    int Nq, KDT;                // N rounded up to 64; rows of ngb16
+    int lev_contig;             // lev_nodes[i] == bounds + i (colour-major numbering)
+    int dbg;                    // BL_DEBUG experiments (timing only)
     const double *vor, *edge;   // [KD][N]
     const double *area, *xy;    // [N], [N][2]
     const unsigned char *flags; // bit0 borders, bit1 borders2, bit2 indomain
@@ -103,8 +111,12 @@ __device__ inline void prop_init(Prop &P, char *base, int N)
 // ------------------------------------------------------------------------------------------------
 // block primitives
 // ------------------------------------------------------------------------------------------------
+constexpr int LEVMAX = 63;
 struct Smem {
+    DevConst c;                // kernel-parameter copy: device functions take it by reference, and a
+                               // reference to a by-value kernel parameter would live in (L2-latency) local memory
     Prop P;
+    int lev_off[LEVMAX + 1];   // copy of c.lev_off: every CTA reads it every pass (one hot L2 line otherwise)
     int scan[NWARP + 1];
     double red[NWARP];
     int ibuf[8];
@@ -123,14 +135,14 @@ __device__ inline int blk_exscan(int v, int &total, Smem &S)
     if (lane == 31) S.scan[w] = inc;
     __syncthreads();
     if (w == 0) {
-        int x = S.scan[lane];
+        int x = (lane < NWARP) ? S.scan[lane] : 0;
         int xi = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, xi, o);
             if (lane >= o) xi += t;
         }
-        S.scan[lane] = xi - x;
+        if (lane < NWARP) S.scan[lane] = xi - x;
         if (lane == 31) S.scan[NWARP] = xi;
     }
     __syncthreads();
@@ -147,7 +159,7 @@ __device__ inline double blk_min(double v, Smem &S)
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0) S.red[w] = v;
     __syncthreads();
-    double r = S.red[lane];
+    double r = (lane < NWARP) ? S.red[lane] : 1.e300;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r = fmin(r, __shfl_xor_sync(0xffffffffu, r, o));
     __syncthreads();
@@ -161,7 +173,7 @@ __device__ inline double blk_sum(double v, Smem &S)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) S.red[w] = v;
     __syncthreads();
-    double r = S.red[lane];
+    double r = (lane < NWARP) ? S.red[lane] : 0.;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
     __syncthreads();
@@ -242,8 +254,9 @@ __device__ void phase_fill(const DevConst &c, Smem &S, double sea)
     while (change) {
         int loc = 0;
         for (int l = 0; l < c.nlev; ++l) {
-            const int e = c.lev_off[l + 1];
-            for (int idx = c.lev_off[l] + tid; idx < e; idx += TPB) {
+            const int e = (c.nlev <= LEVMAX) ? S.lev_off[l + 1] : c.lev_off[l + 1];
+            const int b0 = (c.nlev <= LEVMAX) ? S.lev_off[l] : c.lev_off[l];
+            for (int idx = b0 + tid; idx < e; idx += TPB) {
                 const int k = c.lev_nodes[idx];
                 const double w = W[k], zk = z[k];
                 if (w > zk) {
@@ -575,7 +588,7 @@ __device__ void phase_drainage(const DevConst &c, Smem &S, const int *base1, int
     }
     __syncthreads();
     if (tid == 0) drain_sequential(c, S, pids, np, order, drain, chain, true, sea);
-    if (tid == 32) drain_sequential(c, S, pids, np, order, alld, chain2, false, sea);
+    if (tid == 32 % TPB) drain_sequential(c, S, pids, np, order, alld, chain2, false, sea);
     __syncthreads();
 }
 
@@ -1051,6 +1064,8 @@ __device__ void time_step(const DevConst &c, Smem &S, double &tNow, long long &s
     ++step;
 }
 
+#include "bl_fast.cuh"
+
 // bl_mcmc.interpolateArray (bl_mcmc.py:198-213) on the mesh-constant k=3 table
 __device__ inline double interp_cell(const DevConst &c, const double *v, int g)
 {
@@ -1062,13 +1077,18 @@ __device__ inline double interp_cell(const DevConst &c, const double *v, int g)
     return num / den;
 }
 
+template <int KDT>
 __global__ void __launch_bounds__(TPB, 1)
-bl_run_kernel(const DevConst c, int nstops, const double *__restrict__ stops, const int *__restrict__ ckpt,
+bl_run_kernel(const DevConst cpar, int nstops, const double *__restrict__ stops, const int *__restrict__ ckpt,
               double *out_pts, double *out_sse, double *out_elev, double *out_erdp, int nck, int single_step)
 {
     __shared__ Smem S;
+    extern __shared__ __align__(16) unsigned char dsm[];
     const int b = blockIdx.x, tid = threadIdx.x;
-    if (tid == 0) prop_init(S.P, c.prop_base + (size_t)b * c.prop_stride, c.N);
+    if (tid == 0) { S.c = cpar; prop_init(S.P, cpar.prop_base + (size_t)b * cpar.prop_stride, cpar.N); }
+    __syncthreads();
+    const DevConst &c = S.c;
+    for (int i = tid; i <= c.nlev && i <= LEVMAX; i += TPB) S.lev_off[i] = c.lev_off[i];
     __syncthreads();
     double tNow = c.tnow[b];
     long long step = c.steps[b];
@@ -1079,7 +1099,8 @@ bl_run_kernel(const DevConst c, int nstops, const double *__restrict__ stops, co
     for (int s = 0; s < nstops; ++s) {
         const double tStop = stops[s];
         while (tNow < tStop) {
-            time_step(c, S, tNow, step, tStop, rain, erod, seed, last_dt);
+            if (KDT > 0) fast::time_step<(KDT > 0 ? KDT : 8)>(c, S, dsm, tNow, step, tStop, rain, erod, seed, last_dt);
+            else time_step(c, S, tNow, step, tStop, rain, erod, seed, last_dt);
             if (single_step) break;
         }
         const int ck = ckpt ? ckpt[s] : -1;
@@ -1163,7 +1184,7 @@ extern "C" int bl_version(void) { return 100; }
 
 namespace {
 struct Layout {
-    size_t off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
+    size_t off_ngb16, off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
         off_levo, off_gidx, off_gw, off_gex, off_real, off_pts, off_seat, off_seav, off_rain, off_erod, off_seed,
         off_tnow, off_lastdt, off_steps, off_status, off_phase, off_stops, off_ckpt, off_prop, total;
     int KD, nlev;
@@ -1189,6 +1210,7 @@ Layout make_layout(const bl_mesh *m, const bl_params *p, int B, int KD, int nlev
     const size_t N = m->N;
     auto take = [&](size_t bytes) { size_t r = o; o = rup(o + bytes, 256); return r; };
     L.off_ngb = take((size_t)KD * N * 4);
+    L.off_ngb16 = take((size_t)BL_KP * rup(N, 64) * 2);
     L.off_vor = take((size_t)KD * N * 8);
     L.off_edge = take((size_t)KD * N * 8);
     L.off_area = take(N * 8);
@@ -1291,6 +1313,18 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
             vorT[(size_t)q * N + i] = m->vor[(size_t)i * BL_KP + q];
             edgeT[(size_t)q * N + i] = m->edge[(size_t)i * BL_KP + q];
         }
+    const int Nq = (int)rup((size_t)N, 64);
+    int KDT = 0;
+    if (N < 32760 && (size_t)17 * Nq + 256 <= (size_t)DYN_SMEM) KDT = (KD <= 8) ? 8 : (KD <= 12 ? 12 : 20);
+    if (getenv("BL_FORCE_GENERIC")) KDT = 0;
+    const int KDrow = KDT ? KDT : BL_KP;
+    std::vector<unsigned short> ngb16((size_t)BL_KP * Nq, 0xFFFFu);
+    for (int i = 0; i < N; ++i)
+        for (int q = 0; q < KD; ++q) {
+            int j = m->ngb[(size_t)i * BL_KP + q];
+            if (j < 0) break;
+            ngb16[(size_t)i * KDrow + q] = (unsigned short)j;
+        }
     std::vector<unsigned char> flags(N);
     for (int i = 0; i < N; ++i)
         flags[i] = (unsigned char)((m->borders[i] ? 1 : 0) | (m->borders2[i] ? 2 : 0) | (m->indomain[i] ? 4 : 0));
@@ -1305,6 +1339,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     }
 #define UP(off, src, bytes) CUDA_OK(cudaMemcpy(ws + (off), (src), (bytes), cudaMemcpyHostToDevice))
     UP(L.off_ngb, ngbT.data(), ngbT.size() * 4);
+    UP(L.off_ngb16, ngb16.data(), ngb16.size() * 2);
     UP(L.off_vor, vorT.data(), vorT.size() * 8);
     UP(L.off_edge, edgeT.data(), edgeT.size() * 8);
     UP(L.off_area, m->area, (size_t)N * 8);
@@ -1329,6 +1364,12 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     memset(&c, 0, sizeof(c));
     c.N = N; c.bounds = m->bounds; c.KD = KD; c.nlev = nlev; c.G = m->G; c.npts = p->npts; c.nsea = p->nsea; c.B = B;
     c.ngb = (const int *)(ws + L.off_ngb);
+    c.ngb16 = (const unsigned short *)(ws + L.off_ngb16);
+    c.Nq = Nq; c.KDT = KDT;
+    c.lev_contig = 1;
+    c.dbg = getenv("BL_DEBUG") ? atoi(getenv("BL_DEBUG")) : 0;
+    for (size_t i = 0; i < levn.size() && (int)i < N - m->bounds; ++i)
+        if (levn[i] != m->bounds + (int)i) { c.lev_contig = 0; break; }
     c.vor = (const double *)(ws + L.off_vor);
     c.edge = (const double *)(ws + L.off_edge);
     c.area = (const double *)(ws + L.off_area);
@@ -1402,8 +1443,19 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
     CUDA_OK(cudaMemcpyAsync(ctx->d_stops, stops, (size_t)nstops * 8, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(ctx->d_ckpt, ck.data(), (size_t)nstops * 4, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaStreamSynchronize(st)); // ck is a stack vector
-    bl_run_kernel<<<ctx->B, TPB, 0, st>>>(ctx->c, nstops, ctx->d_stops, ctx->d_ckpt, out_pts, out_sse, out_elev,
-                                          out_erdp, nck, single);
+#define LAUNCH(K, DYN)                                                                                          \
+    do {                                                                                                        \
+        if (DYN) CUDA_OK(cudaFuncSetAttribute(bl_run_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN)); \
+        bl_run_kernel<K><<<ctx->B, TPB, DYN, st>>>(ctx->c, nstops, ctx->d_stops, ctx->d_ckpt, out_pts, out_sse,   \
+                                                   out_elev, out_erdp, nck, single);                            \
+    } while (0)
+    switch (ctx->c.KDT) {
+        case 8: LAUNCH(8, DYN_SMEM); break;
+        case 12: LAUNCH(12, DYN_SMEM); break;
+        case 20: LAUNCH(20, DYN_SMEM); break;
+        default: LAUNCH(0, 0); break;
+    }
+#undef LAUNCH
     ctx->launches++;
     CUDA_OK(cudaGetLastError());
     return BL_OK;

@@ -1,0 +1,770 @@
+// bl_fast.cuh - shared-memory resident time step (included by bl_engine.cu).
+//
+// Same algorithms and the same fp64 operation order as the generic phases in bl_engine.cu (so results stay
+// bit-identical to the CPU oracle), but every iterative / pointer-chasing phase runs on arrays held in the
+// CTA's 227 KB of shared memory instead of L2:
+//   fill + receivers : W (fillH) and z as fp64 + per-node dirty flags        2*8N + N  bytes
+//   stack order      : Euler tour as packed (next:16 | rank:16) words          8N + 2N
+//   basins           : root ids (u16) + stack-ordered volume terms (fp64)      2N + 8N
+//   discharge / SPL  : node values fp64 + donor links (u16) + counters (u8)    8N + 6N + 3N
+// Neighbour ids come from a u16 slot-major table (coalesced).  Requires N < 32768 and 17*Nq <= 225 KB.
+#pragma once
+
+namespace fast {
+
+constexpr unsigned short NONE16 = 0xFFFFu;
+constexpr unsigned END16 = 0xFFFFu;
+
+// Neighbour ids of node k: node-major u16 table [N][KDT], fetched as KDT/4 8-byte words (one or two coalesced
+// transactions per node) and kept packed in registers - an indexable u16 array would live in local memory, which
+// with the L1 carved out for shared memory costs an L2 round trip per access.
+template <int KDT>
+struct Ids {
+    unsigned w[KDT / 2];
+    __device__ __forceinline__ unsigned get(int p) const { return (w[p >> 1] >> (16 * (p & 1))) & 0xFFFFu; }
+};
+template <int KDT>
+__device__ __forceinline__ void load_ids(const DevConst &c, int k, Ids<KDT> &ids)
+{
+    const uint2 *src = reinterpret_cast<const uint2 *>(c.ngb16 + (size_t)k * KDT);
+#pragma unroll
+    for (int q = 0; q < KDT / 4; ++q) {
+        const uint2 v = __ldg(src + q);
+        ids.w[2 * q] = v.x;
+        ids.w[2 * q + 1] = v.y;
+    }
+}
+template <int KDT>
+__device__ __forceinline__ void none_ids(Ids<KDT> &ids)
+{
+#pragma unroll
+    for (int q = 0; q < KDT / 2; ++q) ids.w[q] = 0xFFFFFFFFu;
+}
+
+// ---- depression filling + receivers ---------------------------------------------------------------
+// PDalgo.f90:19-91 with the literal sweep semantics of phase_fill; a node is re-evaluated only when one of
+// its neighbours changed since its last evaluation (re-evaluating it otherwise is a no-op: after an
+// evaluation W(k) <= min_nb W + eps, or W(k) = z(k) for good), so the values and the `change` flag of every
+// sweep - and hence the reference's early stop - are unchanged.  sfd.c:55-153 follows on the same arrays.
+template <int KDT>
+__device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double sea, int &any_marine)
+{
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    double *W = (double *)dsm, *zs = W + Nq;
+    unsigned char *dirty = (unsigned char *)(zs + Nq);
+    const double *z = S.P.f[F_Z];
+    for (int i = tid; i < N; i += TPB) {
+        const double zi = z[i];
+        zs[i] = zi;
+        W[i] = (i < c.bounds) ? zi : 1.e6;
+        dirty[i] = (i >= c.bounds);
+    }
+    __syncthreads();
+    const double eps = c.eps, TH = c.TH;
+    int change = 1;
+    long long *pcd = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
+    int nevald = 0, nsweepd = 0;
+    while (change) {
+        int loc = 0;
+        ++nsweepd;
+        for (int l = 0; l < c.nlev; ++l) {
+            const int e = (c.nlev <= LEVMAX) ? S.lev_off[l + 1] : c.lev_off[l + 1];
+            const int b0 = (c.nlev <= LEVMAX) ? S.lev_off[l] : c.lev_off[l];
+            // up to 4 candidates per thread are collected first so that their neighbour-id loads (L2) overlap
+            for (int base = b0; base < e; base += 4 * TPB) {
+                int ks[4];
+                int nk = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {           // node ids first (independent loads when not contiguous)
+                    const int idx = base + u * TPB + tid;
+                    ks[u] = (idx < e) ? (c.lev_contig ? (c.bounds + idx) : __ldg(c.lev_nodes + idx)) : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = ks[u];
+                    ks[u] = -1;
+                    if (k >= 0 && dirty[k]) {
+                        dirty[k] = 0;
+                        if (W[k] > zs[k]) { ks[u] = k; ++nk; }
+                    }
+                }
+                if (nk == 0) continue;
+                nevald += nk;
+                Ids<KDT> ids[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ks[u] >= 0) load_ids<KDT>(c, ks[u], ids[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (ks[u] < 0) continue;
+                    const int k = ks[u];
+                    const double w = W[k], zk = zs[k];
+                    double hmin = 2.e6;
+#pragma unroll
+                    for (int p = 0; p < KDT; ++p)
+                        if (ids[u].get(p) != NONE16) hmin = fmin(hmin, W[ids[u].get(p)]);
+                    const double he = hmin + eps;
+                    double nw = w;
+                    if (zk >= he) nw = zk;
+                    else if (w > he) {
+                        nw = he;
+                        if (zk >= sea) { if (nw - zk > TH) nw = zk + TH; else loc = 1; }
+                        else           { if (nw - sea > TH) nw = sea + TH; else loc = 1; }
+                    }
+                    if (nw != w) {
+                        W[k] = nw;
+#pragma unroll
+                        for (int p = 0; p < KDT; ++p)
+                            if (ids[u].get(p) != NONE16 && (int)ids[u].get(p) >= c.bounds) dirty[ids[u].get(p)] = 1;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        change = __syncthreads_or(loc);
+    }
+    if (tid == 0) pcd[12] += nsweepd;                                   // diagnostics: sweeps
+    if (nevald) atomicAdd((unsigned long long *)&pcd[13], (unsigned long long)nevald);   // and node evaluations
+    // receivers on both surfaces
+    int *rcv = S.P.i[I_RCV], *rcv1 = S.P.i[I_RCV1];
+    double *maxh = S.P.f[F_MAXH], *fillH = S.P.f[F_FILLH];
+    int mar = 0;
+    for (int g = tid; g < N; g += TPB) {
+        Ids<KDT> ids;
+        load_ids<KDT>(c, g, ids);
+        const double zg = zs[g], wg = W[g];
+        int low1 = g, low = g;
+        double zl = zg, wl = wg, dH = 1.e6;
+#pragma unroll
+        for (int p = 0; p < KDT; ++p) {
+            if (ids.get(p) == NONE16) continue;
+            const int j = ids.get(p);
+            const double zj = zs[j], wj = W[j];
+            if (zj < zl) { low1 = j; zl = zj; }
+            if (wj < wl) { low = j; wl = wj; }
+            const double dh = zj - zg;
+            if (dh >= 0. && dh < dH) dH = dh;
+        }
+        rcv1[g] = low1;
+        rcv[g] = low;
+        if (dH > 9.99e5) dH = 0.;
+        maxh[g] = dH;
+        fillH[g] = wg;
+        mar |= (wg < sea);
+    }
+    any_marine = __syncthreads_or(mar);
+}
+
+// ---- stack order ----------------------------------------------------------------------------------
+// Same Euler-tour ranking as phase_stack, with the tour held in shared memory as (next:16 | rank:16) words
+// updated in place: a word is read and written as one 32-bit access, so any interleaving keeps the
+// invariant "rank = number of enter events from this element up to (excluding) next".
+template <int KDT>
+__device__ void links_stack(const DevConst &c, Smem &S, unsigned char *dsm, const int *rcvg, int *stack, int *pos,
+                            int *baselist, int &nbase, bool filled, bool shuffle, unsigned long long seedstep)
+{
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    unsigned *eu = (unsigned *)dsm;                                  // [2*Nq]
+    unsigned short *r16 = (unsigned short *)(dsm + (size_t)8 * Nq);  // [Nq]
+    unsigned long long *K = (unsigned long long *)(dsm + (size_t)10 * Nq + 64 - ((size_t)10 * Nq) % 8);
+    const int kcap = (int)(((size_t)DYN_SMEM - (size_t)10 * Nq - 128) / 8);
+    for (int v = tid; v < N; v += TPB) r16[v] = (unsigned short)rcvg[v];
+    __syncthreads();
+    unsigned short *lc16 = (unsigned short *)S.P.i[I_LC], *ps16 = (unsigned short *)S.P.i[I_PS];
+    unsigned char *cnt8 = (unsigned char *)S.P.i[I_CNT];
+    for (int v = tid; v < N; v += TPB) {
+        Ids<KDT> ids;
+        load_ids<KDT>(c, v, ids);
+        const int r = r16[v];
+        int f = NONE16, l = -1, n = 0;
+#pragma unroll
+        for (int p = 0; p < KDT; ++p) {
+            if (ids.get(p) == NONE16) continue;
+            const int w = ids.get(p);
+            if (r16[w] == v) { ++n; if (w < f) f = w; if (w > l) l = w; }
+        }
+        int nx = NONE16, pv = -1;
+        if (r != v) {
+            Ids<KDT> jds;
+            load_ids<KDT>(c, r, jds);
+#pragma unroll
+            for (int p = 0; p < KDT; ++p) {
+                if (jds.get(p) == NONE16) continue;
+                const int w = jds.get(p);
+                if (w != v && r16[w] == r) {
+                    if (w > v && w < nx) nx = w;
+                    if (w < v && w > pv) pv = w;
+                }
+            }
+        }
+        eu[2 * v] = ((unsigned)((f != NONE16) ? 2 * f : 2 * v + 1) << 16) | 1u;
+        if (r != v) eu[2 * v + 1] = ((unsigned)((nx != NONE16) ? 2 * nx : 2 * r + 1) << 16);
+        if (filled) {
+            lc16[v] = (l >= 0) ? (unsigned short)l : NONE16;
+            ps16[v] = (pv >= 0) ? (unsigned short)pv : NONE16;
+            cnt8[v] = (unsigned char)n;
+        }
+    }
+    nbase = blk_compact(N, baselist, [&](int i) { return r16[i] == i; }, S);
+    if (shuffle && nbase > 1) {
+        int n2 = 1;
+        while (n2 < nbase) n2 <<= 1;
+        unsigned long long *KK = (n2 <= kcap) ? K : S.P.keys;
+        for (int i = tid; i < n2; i += TPB)
+            KK[i] = (i < nbase) ? (((mix64(seedstep ^ (unsigned long long)(unsigned)baselist[i]) >> 32) << 32) |
+                                   (unsigned)baselist[i])
+                                : ~0ull;
+        __syncthreads();
+        blk_bitonic(KK, n2);
+        for (int i = tid; i < nbase; i += TPB) baselist[i] = (int)(unsigned)(KK[i] & 0xFFFFFFFFull);
+        __syncthreads();
+    }
+    int *nsroot = S.P.i[I_NS];
+    for (int i = tid; i < nbase; i += TPB) {
+        const int root = baselist[i];
+        const int nxt = (i + 1 < nbase) ? baselist[i + 1] : NONE_I;
+        eu[2 * root + 1] = ((nxt != NONE_I) ? (unsigned)(2 * nxt) : END16) << 16;
+        if (!filled) nsroot[root] = nxt;
+    }
+    __syncthreads();
+    const int M = 2 * N;
+    int active = 1;
+    while (active) {
+        int loc = 0;
+        for (int e = tid; e < M; e += TPB) {
+            const unsigned w = eu[e];
+            const unsigned nx = w >> 16;
+            if (nx != END16) {
+                const unsigned w2 = eu[nx];
+                eu[e] = (w2 & 0xFFFF0000u) | ((w + w2) & 0xFFFFu);
+                loc = 1;
+            }
+        }
+        active = __syncthreads_or(loc);
+    }
+    for (int v = tid; v < N; v += TPB) {
+        const int p = N - (int)(eu[2 * v] & 0xFFFFu);
+        pos[v] = p;
+        stack[p] = v;
+    }
+    __syncthreads();
+}
+
+// ---- pit ids and volumes (FLOWalgo.f90:130-165) ------------------------------------------------------
+__device__ void basins(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1)
+{
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    unsigned short *root16 = (unsigned short *)dsm;          // [Nq]
+    double *val = (double *)(dsm + (size_t)8 * Nq);          // [Nq]
+    const double *z = S.P.f[F_Z], *W = S.P.f[F_FILLH];
+    const int *rcv1 = S.P.i[I_RCV1], *pos1 = S.P.i[I_POS1], *ns1 = S.P.i[I_NS];
+    int *pitID = S.P.i[I_PITID];
+    double *pitVol = S.P.f[F_PITVOL];
+    for (int v = tid; v < N; v += TPB) root16[v] = (unsigned short)rcv1[v];
+    __syncthreads();
+    int ch = 1;
+    while (ch) {
+        int loc = 0;
+        for (int v = tid; v < N; v += TPB) {
+            const unsigned short r = root16[v], rr = root16[r];
+            if (rr != r) { root16[v] = rr; loc = 1; }
+        }
+        ch = __syncthreads_or(loc);
+    }
+    for (int v = tid; v < N; v += TPB) {
+        const double wv = W[v], zv = z[v];
+        const bool wet = wv > zv;
+        const int root = root16[v];
+        pitID[v] = (wet || root == v) ? root : -1;
+        val[pos1[v]] = wet ? (wv - zv) * c.area[v] : 0.0;
+        pitVol[v] = -1.0;
+    }
+    __syncthreads();
+    for (int i = tid; i < nbase1; i += TPB) {
+        const int root = base1[i];
+        const int lo = pos1[root];
+        const int nr = ns1[root];
+        const int hi = (nr != NONE_I) ? pos1[nr] : N;
+        double s = -1.0;
+        for (int k = lo; k < hi; ++k) s = s + val[k];
+        pitVol[root] = s;
+    }
+    __syncthreads();
+}
+
+// ---- pit drainage (FLOWalgo.f90:167-297), see phase_drainage -------------------------------------------
+__device__ inline int pit_walk16(const unsigned short *r16, const unsigned short *pid16, const double *W, int root,
+                                 bool use_sea, double sea)
+{
+    if (use_sea && W[root] < sea) return root | TERM_BIT;
+    int donor = root;
+    for (;;) {
+        const int r = r16[donor];
+        if (r == donor) return r | TERM_BIT;
+        if (use_sea && W[r] < sea) return r | TERM_BIT;
+        const int pid = pid16[r];
+        if (pid == NONE16 || pid == root) donor = r;
+        else if (use_sea && W[pid] < sea) donor = r;
+        else return pid;
+    }
+}
+
+__device__ void drainage(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1, double sea,
+                         int any_marine)
+{
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    unsigned short *r16 = (unsigned short *)dsm, *pid16 = r16 + Nq;
+    const int *rcv = S.P.i[I_RCV], *pitID = S.P.i[I_PITID];
+    const double *W = S.P.f[F_FILLH], *pitVol = S.P.f[F_PITVOL];
+    int *succ = S.P.i[I_SUCC], *succ2 = S.P.i[I_SUCC2], *drain = S.P.i[I_PITDRAIN], *alld = S.P.i[I_ALLDRAIN];
+    int *mark = S.P.i[I_MARK];
+    for (int v = tid; v < N; v += TPB) {
+        r16[v] = (unsigned short)rcv[v];
+        const int p = pitID[v];
+        pid16[v] = (p < 0) ? NONE16 : (unsigned short)p;
+        drain[v] = -1; alld[v] = -1; mark[v] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < nbase1; i += TPB) {
+        const int root = base1[i];
+        const int s2 = pit_walk16(r16, pid16, W, root, false, sea);
+        succ2[root] = s2;
+        succ[root] = any_marine ? pit_walk16(r16, pid16, W, root, true, sea) : s2;
+    }
+    __syncthreads();
+    int cyc = 0;
+    for (int i = tid; i < nbase1; i += TPB) {
+        const int p = base1[i];
+        if (pitVol[p] >= 0.) {
+            int q = p, steps = 0;
+            while (!(succ[q] & TERM_BIT)) { q = succ[q]; if (++steps > nbase1) { cyc |= 1; break; } }
+            q = p; steps = 0;
+            while (!(succ2[q] & TERM_BIT)) { q = succ2[q]; if (++steps > nbase1) { cyc |= 2; break; } }
+        }
+    }
+    cyc = __syncthreads_or(cyc);
+    if (!cyc) {
+        for (int i = tid; i < nbase1; i += TPB) {
+            const int p = base1[i];
+            if (pitVol[p] >= 0.) {
+                int q = p;
+                for (;;) {
+                    if (atomicOr(&mark[q], 1) & 1) break;
+                    const int s = succ[q];
+                    drain[q] = s & ~TERM_BIT;
+                    if (s & TERM_BIT) break;
+                    q = s;
+                }
+                q = p;
+                for (;;) {
+                    if (atomicOr(&mark[q], 2) & 2) break;
+                    const int s = succ2[q];
+                    alld[q] = s & ~TERM_BIT;
+                    if (s & TERM_BIT) break;
+                    q = s;
+                }
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    __syncthreads();
+    phase_drainage(c, S, base1, nbase1, sea);   // generic path handles the cyclic case literally
+}
+
+// ---- shared-memory layout of the discharge / stream-power scans -------------------------------------------
+struct ScanSm {
+    double *vals;
+    unsigned short *lc, *ps, *r16;
+    unsigned *cntw;           // working donor counters, 4 per word
+    unsigned char *cnt0, *kind;
+};
+__device__ inline ScanSm scan_layout(unsigned char *dsm, int Nq)
+{
+    ScanSm s;
+    s.vals = (double *)dsm;
+    s.lc = (unsigned short *)(dsm + (size_t)8 * Nq);
+    s.ps = s.lc + Nq;
+    s.r16 = s.ps + Nq;
+    s.cntw = (unsigned *)(dsm + (size_t)14 * Nq);
+    s.cnt0 = dsm + (size_t)15 * Nq;
+    s.kind = dsm + (size_t)16 * Nq;
+    return s;
+}
+__device__ inline unsigned cnt_dec(unsigned *cntw, int v)   // returns the previous byte value
+{
+    const unsigned sh = 8u * (v & 3);
+    const unsigned old = atomicSub(&cntw[v >> 2], 1u << sh);
+    return (old >> sh) & 0xFFu;
+}
+
+// FLOWalgo.f90:53-81 (see phase_discharge); leaves Q in sm.vals and in global F_Q
+__device__ void discharge(const DevConst &c, Smem &S, unsigned char *dsm, double rain)
+{
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    ScanSm sm = scan_layout(dsm, Nq);
+    const unsigned short *lc16 = (const unsigned short *)S.P.i[I_LC], *ps16 = (const unsigned short *)S.P.i[I_PS];
+    const unsigned char *cnt8 = (const unsigned char *)S.P.i[I_CNT];
+    const int *rcv = S.P.i[I_RCV];
+    for (int v = tid; v < N; v += TPB) {
+        sm.lc[v] = lc16[v]; sm.ps[v] = ps16[v]; sm.r16[v] = (unsigned short)rcv[v];
+        sm.cnt0[v] = cnt8[v];
+        sm.vals[v] = c.area[v] * ((v >= c.bounds) ? rain : 0.);
+    }
+    for (int v = tid; v < Nq / 4; v += TPB) sm.cntw[v] = ((const unsigned *)cnt8)[v];
+    __syncthreads();
+    volatile double *vals = sm.vals;
+    for (int v = tid; v < N; v += TPB) {
+        if (sm.cnt0[v] != 0) continue;
+        int cur = v;
+        double acc = vals[cur];                 // leaf: own value only
+        for (;;) {
+            const int r = sm.r16[cur];
+            if (r == cur) break;
+            if (sm.cnt0[r] == 1) {              // single donor: no counter, no fence - this thread owns the chain
+                acc = vals[r] + acc;
+                vals[r] = acc;
+                cur = r;
+                continue;
+            }
+            __threadfence_block();
+            if (cnt_dec(sm.cntw, r) != 1u) break;
+            cur = r;
+            acc = vals[cur];
+            for (unsigned d = sm.lc[cur]; d != NONE16; d = sm.ps[d]) acc = acc + vals[d];
+            vals[cur] = acc;
+        }
+    }
+    __syncthreads();
+    double *Q = S.P.f[F_Q];
+    for (int v = tid; v < N; v += TPB) Q[v] = sm.vals[v];
+}
+
+__device__ double flow_cfl(const DevConst &c, Smem &S, unsigned char *dsm, double erod)
+{
+    const int N = c.N, Nq = c.Nq;
+    ScanSm sm = scan_layout(dsm, Nq);
+    const double *W = S.P.f[F_FILLH];
+    double cfl = 1.e6;
+    for (int d = threadIdx.x; d < N; d += TPB) {
+        const int r = sm.r16[d];
+        const double q = sm.vals[d];
+        if (d == r || !(q > 0.)) continue;
+        const double dz = W[d] - W[r];
+        if (dz > 0.) {
+            const double dx = c.xy[2 * d] - c.xy[2 * r], dy = c.xy[2 * d + 1] - c.xy[2 * r + 1];
+            const double dist = sqrt(dx * dx + dy * dy);
+            const double tmp = dist / (erod * powx(q, c.m) * powx(dz / dist, c.n - 1.));
+            cfl = fmin(tmp, cfl);
+        }
+    }
+    return blk_min(cfl, S);
+}
+
+// FLOWalgo.f90:583-1044 (see phase_streampower).  `first`: Q is still in sm.vals (straight after discharge).
+__device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, double erod, double sea, double dt,
+                            bool first, const int *base1, int nbase1)
+{
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    ScanSm sm = scan_layout(dsm, Nq);
+    const int *pitID = S.P.i[I_PITID], *stack = S.P.i[I_STACK], *pitDrain = S.P.i[I_PITDRAIN];
+    int *events = S.P.i[I_EVENTS];
+    const double *z = S.P.f[F_Z], *W = S.P.f[F_FILLH], *Qg = S.P.f[F_Q], *maxhA = S.P.f[F_MAXH];
+    const double *pitVol1 = S.P.f[F_PITVOL];
+    double *depo = S.P.f[F_DEPO], *ero = S.P.f[F_ERO], *pdep = S.P.f[F_PDEP], *pitVol = S.P.f[F_PITVOLW];
+    // (1) per-node pre-pass
+    for (int d = tid; d < N; d += TPB) {
+        const int r = sm.r16[d];
+        const double zd = z[d], zr = z[r], fh = W[d], area = c.area[d];
+        const double q = first ? sm.vals[d] : Qg[d];
+        double dh = 0.95 * (zd - zr);
+        if (zd > sea && zr < sea) dh = 0.99 * (zd - sea);
+        if (dh < 0.001) dh = 0.;
+        const double waterH = fh - zd;
+        double SPL = 0., totspl = 0.;
+        if (r != d && dh > 0. && waterH == 0. && fh >= sea) {
+            const double dx = c.xy[2 * d] - c.xy[2 * r], dy = c.xy[2 * d + 1] - c.xy[2 * r + 1];
+            const double dist = sqrt(dx * dx + dy * dy);
+            if (dist > 0.) {
+                const double slp = dh / dist;
+                SPL = -erod * 1. * 1. * powx(q, c.m) * powx(slp, c.n);
+                totspl = totspl + SPL;
+                if (-totspl * dt > dh) {
+                    const double frac = dh / (-totspl * dt);
+                    SPL = SPL * frac;
+                    totspl = -dh;
+                }
+            }
+        }
+        double maxh = maxhA[d];
+        if (waterH > 0.) maxh = waterH;
+        else if (zd < sea) maxh = sea - zd;
+        maxh = 0.95 * maxh;
+        int k;
+        double e = 0.;
+        if (totspl < 0.) { k = 0; e = SPL * dt * area; }
+        else if (totspl >= 0. && area > 0.) {
+            if (waterH > 0. && fh > sea) k = 1;
+            else if (zd <= sea) k = 2;
+            else if (maxh > 0. && waterH == 0. && d != r && zd > sea) { k = 3; e = maxh; }
+            else if (d == r) k = 2;
+            else k = 4;
+        } else k = 5;
+        sm.kind[d] = (unsigned char)k;
+        sm.vals[d] = e;
+        depo[d] = 0.;
+        ero[d] = 0.;
+    }
+    for (int v = tid; v < Nq / 4; v += TPB) sm.cntw[v] = ((const unsigned *)sm.cnt0)[v];
+    __syncthreads();
+    // (2) ordered sediment routing
+    volatile double *vals = sm.vals;
+    for (int v = tid; v < N; v += TPB) {
+        if (sm.cnt0[v] != 0) continue;
+        int cur = v;
+        double acc = 0. * dt;                   // a leaf receives nothing
+        for (;;) {
+            const int k = sm.kind[cur];
+            const double own = vals[cur];
+            double Qs = 0., erodep = 0.;
+            if (k == 0) { erodep = own; Qs = -erodep + acc; }
+            else if (k == 1) { if (acc != 0.) { pdep[cur] = acc; sm.kind[cur] = 6; } }
+            else if (k == 2) { erodep = acc; }
+            else if (k == 3) {
+                const double area = c.area[cur];
+                const double totflx = 0. + acc, maxh = own;
+                if (totflx / area < maxh) erodep = acc;
+                else { const double frac = acc / totflx; erodep = frac * maxh * area; Qs = acc - erodep; }
+            } else if (k == 4) Qs = acc;
+            if (!(k == 1 && acc != 0.)) {
+                if (erodep < 0.) ero[cur] = 0. + erodep;
+                else if (erodep != 0.) depo[cur] = 0. + erodep;
+            }
+            vals[cur] = Qs;
+            const int r = sm.r16[cur];
+            if (r == cur) break;
+            if (sm.cnt0[r] == 1) {              // single donor: this thread carries the flux down the chain
+                acc = 0. * dt + Qs;
+                cur = r;
+                continue;
+            }
+            __threadfence_block();
+            if (cnt_dec(sm.cntw, r) != 1u) break;
+            cur = r;
+            acc = 0. * dt;
+            for (unsigned d = sm.lc[cur]; d != NONE16; d = sm.ps[d]) acc = acc + vals[d];
+        }
+    }
+    __syncthreads();
+    // (3) lake-entry events in reverse stack order
+    const int nev = blk_compact(N, events, [&](int i) { const int v = stack[N - 1 - i]; return sm.kind[v] == 6 && pdep[v] > 0.; }, S);
+    if (nev == 0) return;
+    // parallel replay: when no event overflows its own pit (the usual case) events of different pits are
+    // independent and events of one pit are applied in order by one thread -> same sums as the serial loop
+    int over = 0;
+    int *evpit = S.P.i[I_MEMB];
+    for (int e = tid; e < nev; e += TPB) {
+        const int donor = stack[N - 1 - events[e]];
+        const int pit = pitID[donor];
+        const bool ok = (pit >= 0 && c.area[pit] > 0.);
+        evpit[e] = ok ? pit : -1;
+        if (ok && W[pit] < sea) over = 1;
+    }
+    __syncthreads();
+    for (int i = tid; i < nbase1; i += TPB) {
+        const int pit = base1[i];
+        double dp = depo[pit];
+        const double vol = pitVol1[pit];
+        bool touched = false;
+        for (int e = 0; e < nev; ++e) {
+            if (evpit[e] != pit) continue;
+            const double pitDep = pdep[stack[N - 1 - events[e]]];
+            const double totdist = 0. + pitDep, tmpdist = 0. + dp;
+            if (tmpdist + totdist <= vol || pitDrain[pit] == pit) { dp = dp + pitDep; touched = true; }
+            else { over = 1; break; }
+        }
+        S.P.f[F_VAL][pit] = dp;   // staged, committed below when no event overflowed
+        (void)touched;
+    }
+    over = __syncthreads_or(over);
+    if (!over) {
+        for (int i = tid; i < nbase1; i += TPB) { const int pit = base1[i]; depo[pit] = S.P.f[F_VAL][pit]; }
+        __syncthreads();
+        return;
+    }
+    // serial replay, literal (FLOWalgo.f90:967-1034)
+    for (int k = tid; k < N; k += TPB) pitVol[k] = pitVol1[k];
+    __syncthreads();
+    if (tid == 0) {
+        unsigned st = 0;
+        for (int e = 0; e < nev; ++e) {
+            const int donor = stack[N - 1 - events[e]];
+            const int recvr = sm.r16[donor];
+            double pitDep = pdep[donor];
+            double totdist = 0. + pitDep;
+            if (!(pitID[donor] >= 0 && c.area[pitID[donor]] > 0.)) continue;
+            int tmpID = pitID[donor], nID = tmpID;
+            long guard = 0;
+            while (totdist > 0.) {
+                if (++guard > 1000000 || tmpID < 0) { st |= BL_ST_CASCADE_GUARD; break; }
+                const double tmpdist = 0. + depo[tmpID];
+                const double pv = pitVol[tmpID];
+                if (W[tmpID] < sea) {
+                    st |= BL_ST_MARINE;
+                    if (z[donor] < sea) depo[donor] = depo[donor] + pitDep;
+                    totdist = 0.;
+                    nID = recvr;
+                } else if (tmpdist + totdist <= pv) {
+                    depo[tmpID] = depo[tmpID] + pitDep; totdist = 0.; nID = tmpID;
+                } else if (pitDrain[tmpID] == tmpID) {
+                    depo[tmpID] = depo[tmpID] + pitDep; totdist = 0.; nID = tmpID;
+                } else {
+                    if (!(c.flags[tmpID] & 1)) { totdist = 0.; nID = tmpID; }
+                    else if (tmpdist == pv) nID = tmpID;
+                    else {
+                        const double frac = pitDep / totdist;
+                        depo[tmpID] = depo[tmpID] + (pv - tmpdist) * frac;
+                        pitDep = (totdist - (pv - tmpdist)) * frac;
+                        const double newdist = 0. + pitDep;
+                        const double totflx = 0. + depo[tmpID];
+                        totdist = newdist;
+                        pitVol[tmpID] = totflx;
+                        nID = tmpID;
+                    }
+                }
+                tmpID = pitDrain[nID];
+            }
+        }
+        if (st) atomicOr(&c.status[blockIdx.x], st);
+    }
+    __syncthreads();
+}
+
+// buildFlux.py:193-195, :252-272, :292-315 (see phase_apply) with z staged in shared memory for the gather
+template <int KDT>
+__device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea, double timestep)
+{
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    double *zs = (double *)dsm, *cd = zs + Nq;
+    double *z = S.P.f[F_Z], *cumdiff = S.P.f[F_CUMDIFF], *cumhill = S.P.f[F_CUMHILL];
+    const double *sedflux = S.P.f[F_SEDFLUX];
+    for (int k = tid; k < N; k += TPB) {
+        const double sf = sedflux[k];
+        zs[k] = z[k] + sf;
+        cumdiff[k] += sf;
+    }
+    __syncthreads();
+    for (int g = tid; g < N; g += TPB) {
+        double acc = 0.;
+        const unsigned char fg = c.flags[g];
+        const double zg = zs[g];
+        if (fg & 2) {
+            Ids<KDT> ids;
+            load_ids<KDT>(c, g, ids);
+#pragma unroll
+            for (int p = 0; p < KDT; ++p) {
+                if (ids.get(p) == NONE16) continue;
+                const int j = ids.get(p);
+                const double di = c.edge[(size_t)p * N + g], ed = c.vor[(size_t)p * N + g], zj = zs[j];
+                const bool bj = c.flags[j] & 2;
+                if (bj && di > 0.) acc += ed * (zj - zg) / di;
+                if (!bj) { if (zj < zg && di > 0.) acc += ed * (zj - zg) / di; }
+            }
+        }
+        const double area = c.area[g];
+        const double ac = (area > 0.) ? 1. / area : 0.;
+        double coeff = ac * ((zg >= sea) ? c.CDa : c.CDm);
+        if (!(fg & 2)) { coeff = 0.; acc = 0.; }
+        cd[g] = coeff * acc * timestep;
+    }
+    __syncthreads();
+    for (int k = tid; k < N; k += TPB) {
+        double zn = zs[k];
+        if (c.flags[k] & 1) { const double d = cd[k]; zn += d; cumdiff[k] += d; cumhill[k] += d; }
+        zs[k] = zn;
+    }
+    __syncthreads();
+    if (c.btype != 0) {
+        const double add = (c.btype == 1) ? -0.1 : (c.btype == 2 ? 0. : 100.);
+        for (int k = tid; k < c.bounds; k += TPB) {
+            const double zp = zs[c.parent[k]];
+            cd[k] = (c.btype == 2) ? zp : zp + add;
+        }
+        __syncthreads();
+        for (int k = tid; k < c.bounds; k += TPB) zs[k] = cd[k];
+        __syncthreads();
+    }
+    for (int k = tid; k < N; k += TPB) {
+        double zn = zs[k];
+        if (c.disp) zn += c.disp[k] * timestep;
+        z[k] = zn;
+    }
+    __syncthreads();
+}
+
+template <int KDT>
+__device__ void time_step(const DevConst &c, Smem &S, unsigned char *dsm, double &tNow, long long &step, double tStop,
+                          double rain, double erod, unsigned long long seed, double &last_dt)
+{
+    const int tid = threadIdx.x;
+    const double sea = sea_level(c, tNow);
+    long long *pc = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
+    long long t0 = clock64();
+#define TICK(i) do { if (tid == 0) { long long t1_ = clock64(); pc[i] += t1_ - t0; t0 = t1_; } } while (0)
+    int any_marine;
+    fill_sfd<KDT>(c, S, dsm, sea, any_marine);
+    TICK(0);
+    int nbase1, nbase;
+    links_stack<KDT>(c, S, dsm, S.P.i[I_RCV1], S.P.i[I_STACK1], S.P.i[I_POS1], S.P.i[I_LA], nbase1, false, false, 0ull);
+    TICK(2);
+    basins(c, S, dsm, S.P.i[I_LA], nbase1);
+    TICK(3);
+    links_stack<KDT>(c, S, dsm, S.P.i[I_RCV], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase, true, c.shuffle != 0,
+                     mix64(seed + (unsigned long long)step));
+    TICK(4);
+    drainage(c, S, dsm, S.P.i[I_LA], nbase1, sea, any_marine);
+    TICK(5);
+    discharge(c, S, dsm, rain);
+    TICK(6);
+    const double flowcfl = flow_cfl(c, S, dsm, erod);
+    double cfl = fmin(flowcfl, c.hill);
+    cfl = py2_floorish(cfl);
+    cfl = fmin(cfl, tStop - tNow);
+    cfl = fmax(c.minDT, cfl);
+    cfl = fmin(c.maxDT, cfl);
+    double newdt = cfl;
+    TICK(7);
+    streampower(c, S, dsm, erod, sea, newdt, true, S.P.i[I_LA], nbase1);
+    TICK(8);
+    {
+        // getid1 (FLOWalgo.f90:1047-1086): pitVol > 0 only at basin roots, so only those can qualify
+        const double *cdepo = S.P.f[F_DEPO], *cero = S.P.f[F_ERO], *pitVol = S.P.f[F_PITVOL];
+        const int *pitID = S.P.i[I_PITID], *alld = S.P.i[I_ALLDRAIN], *base1 = S.P.i[I_LA];
+        int nb = 0;
+        double minperc = 1.e300;
+        for (int i = tid; i < nbase1; i += TPB) {
+            const int k = base1[i];
+            const double vc = (c.depo == 0) ? cero[k] : cdepo[k] + cero[k];
+            const double sumvol = 0. + vc;
+            const bool in1 = (sumvol > pitVol[k] && pitVol[k] > 0.);
+            const bool in2 = (pitID[k] >= 0 && alld[k] == pitID[k]);
+            if (in1 && in2 && (c.flags[k] & 4)) { nb = 1; minperc = fmin(minperc, pitVol[k] / sumvol); }
+        }
+        nb = __syncthreads_or(nb);
+        if (nb) { minperc = blk_min(minperc, S); newdt = cfl * minperc; }
+        newdt = py2_floorish(newdt);
+        newdt = fmax(c.minDT, newdt);
+        if (newdt < cfl) streampower(c, S, dsm, erod, sea, newdt, false, S.P.i[I_LA], nbase1);
+    }
+    TICK(9);
+    phase_erodep(c, S, sea);
+    TICK(10);
+    apply<KDT>(c, S, dsm, sea, newdt);
+    TICK(11);
+#undef TICK
+    tNow += newdt;
+    last_dt = newdt;
+    ++step;
+}
+
+} // namespace fast
