@@ -117,6 +117,7 @@ struct Smem {
                                // reference to a by-value kernel parameter would live in (L2-latency) local memory
     Prop P;
     int lev_off[LEVMAX + 1];   // copy of c.lev_off: every CTA reads it every pass (one hot L2 line otherwise)
+    int fl_head[LEVMAX + 1], fl_tail[LEVMAX + 1];   // per-level worklist rings of the fill
     int scan[NWARP + 1];
     double red[NWARP];
     int ibuf[8];
@@ -1315,7 +1316,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
         }
     const int Nq = (int)rup((size_t)N, 64);
     int KDT = 0;
-    if (N < 32760 && (size_t)17 * Nq + 256 <= (size_t)DYN_SMEM) KDT = (KD <= 8) ? 8 : (KD <= 12 ? 12 : 20);
+    if (N < 32760 && nlev <= LEVMAX && (size_t)17 * Nq + 256 <= (size_t)DYN_SMEM) KDT = (KD <= 8) ? 8 : (KD <= 12 ? 12 : 20);
     if (getenv("BL_FORCE_GENERIC")) KDT = 0;
     const int KDrow = KDT ? KDT : BL_KP;
     std::vector<unsigned short> ngb16((size_t)BL_KP * Nq, 0xFFFFu);
@@ -1443,6 +1444,8 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
     CUDA_OK(cudaMemcpyAsync(ctx->d_stops, stops, (size_t)nstops * 8, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(ctx->d_ckpt, ck.data(), (size_t)nstops * 4, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaStreamSynchronize(st)); // ck is a stack vector
+    // the fast path needs 17 bytes of shared memory per node: small meshes leave room for several CTAs per SM
+    const int dyn = (int)std::min((size_t)DYN_SMEM, rup((size_t)17 * ctx->c.Nq + 256, 1024));
 #define LAUNCH(K, DYN)                                                                                          \
     do {                                                                                                        \
         if (DYN) CUDA_OK(cudaFuncSetAttribute(bl_run_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN)); \
@@ -1450,9 +1453,9 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
                                                    out_elev, out_erdp, nck, single);                            \
     } while (0)
     switch (ctx->c.KDT) {
-        case 8: LAUNCH(8, DYN_SMEM); break;
-        case 12: LAUNCH(12, DYN_SMEM); break;
-        case 20: LAUNCH(20, DYN_SMEM); break;
+        case 8: LAUNCH(8, dyn); break;
+        case 12: LAUNCH(12, dyn); break;
+        case 20: LAUNCH(20, dyn); break;
         default: LAUNCH(0, 0); break;
     }
 #undef LAUNCH

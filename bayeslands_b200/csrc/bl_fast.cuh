@@ -42,67 +42,63 @@ __device__ __forceinline__ void none_ids(Ids<KDT> &ids)
 }
 
 // ---- depression filling + receivers ---------------------------------------------------------------
-// PDalgo.f90:19-91 with the literal sweep semantics of phase_fill; a node is re-evaluated only when one of
+// PDalgo.f90:19-91 with the literal sweep semantics of phase_fill.  A node is re-evaluated only when one of
 // its neighbours changed since its last evaluation (re-evaluating it otherwise is a no-op: after an
 // evaluation W(k) <= min_nb W + eps, or W(k) = z(k) for good), so the values and the `change` flag of every
-// sweep - and hence the reference's early stop - are unchanged.  sfd.c:55-153 follows on the same arrays.
+// sweep - and hence the reference's early stop - are unchanged.  Pending nodes are kept in one dense
+// worklist per Gauss-Seidel level (a changed node appends its not-yet-pending neighbours to the list of THEIR
+// level, which is consumed at that level's next turn - later in this sweep or in the next one), so a level
+// pass costs a few full warps instead of every warp running the predicated evaluation code.
+// sfd.c:55-153 follows on the same arrays.
 template <int KDT>
 __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double sea, int &any_marine)
 {
-    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
-    double *W = (double *)dsm, *zs = W + Nq;
-    unsigned char *dirty = (unsigned char *)(zs + Nq);
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x, nb = c.bounds;
+    double *W = (double *)dsm;                                          // [Nq]
+    unsigned short *pend = (unsigned short *)(dsm + (size_t)8 * Nq);    // [Nq] ring per level, slot = lev_off + i
+    unsigned char *lev8 = dsm + (size_t)10 * Nq;                        // [Nq] level of each node
+    unsigned *bits = (unsigned *)(dsm + (size_t)11 * Nq);               // [Nq/32] "is pending"
     const double *z = S.P.f[F_Z];
-    for (int i = tid; i < N; i += TPB) {
-        const double zi = z[i];
-        zs[i] = zi;
-        W[i] = (i < c.bounds) ? zi : 1.e6;
-        dirty[i] = (i >= c.bounds);
+    const bool smlev = (c.nlev <= LEVMAX);
+    for (int i = tid; i < N; i += TPB) W[i] = (i < nb) ? z[i] : 1.e6;
+    for (int i = tid; i < Nq / 32; i += TPB) bits[i] = 0u;
+    for (int l = 0; l < c.nlev; ++l) {
+        const int b0 = smlev ? S.lev_off[l] : c.lev_off[l], e = smlev ? S.lev_off[l + 1] : c.lev_off[l + 1];
+        for (int idx = b0 + tid; idx < e; idx += TPB) {
+            const int k = c.lev_contig ? (nb + idx) : c.lev_nodes[idx];
+            lev8[k] = (unsigned char)l;
+            pend[idx] = (unsigned short)k;
+        }
+        if (tid == 0 && l <= LEVMAX) { S.fl_head[l] = 0; S.fl_tail[l] = e - b0; }
     }
     __syncthreads();
+    for (int i = nb + tid; i < N; i += TPB) atomicOr(&bits[i >> 5], 1u << (i & 31));
+    __syncthreads();
     const double eps = c.eps, TH = c.TH;
-    int change = 1;
     long long *pcd = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
     int nevald = 0, nsweepd = 0;
+    int change = 1;
     while (change) {
         int loc = 0;
         ++nsweepd;
         for (int l = 0; l < c.nlev; ++l) {
-            const int e = (c.nlev <= LEVMAX) ? S.lev_off[l + 1] : c.lev_off[l + 1];
-            const int b0 = (c.nlev <= LEVMAX) ? S.lev_off[l] : c.lev_off[l];
-            // up to 4 candidates per thread are collected first so that their neighbour-id loads (L2) overlap
-            for (int base = b0; base < e; base += 4 * TPB) {
-                int ks[4];
-                int nk = 0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {           // node ids first (independent loads when not contiguous)
-                    const int idx = base + u * TPB + tid;
-                    ks[u] = (idx < e) ? (c.lev_contig ? (c.bounds + idx) : __ldg(c.lev_nodes + idx)) : -1;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int k = ks[u];
-                    ks[u] = -1;
-                    if (k >= 0 && dirty[k]) {
-                        dirty[k] = 0;
-                        if (W[k] > zs[k]) { ks[u] = k; ++nk; }
-                    }
-                }
-                if (nk == 0) continue;
-                nevald += nk;
-                Ids<KDT> ids[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (ks[u] >= 0) load_ids<KDT>(c, ks[u], ids[u]);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (ks[u] < 0) continue;
-                    const int k = ks[u];
-                    const double w = W[k], zk = zs[k];
+            const int b0 = S.lev_off[l], cap = S.lev_off[l + 1] - b0;
+            const int head = S.fl_head[l], n = S.fl_tail[l] - head;
+            for (int i = tid; i < n; i += TPB) {
+                int slot = head + i;
+                slot = (slot >= cap) ? slot % cap : slot;
+                const int k = pend[b0 + slot];
+                atomicAnd(&bits[k >> 5], ~(1u << (k & 31)));
+                const double w = W[k];
+                Ids<KDT> ids;
+                load_ids<KDT>(c, k, ids);
+                const double zk = __ldg(z + k);
+                ++nevald;
+                if (w > zk) {
                     double hmin = 2.e6;
 #pragma unroll
                     for (int p = 0; p < KDT; ++p)
-                        if (ids[u].get(p) != NONE16) hmin = fmin(hmin, W[ids[u].get(p)]);
+                        if (ids.get(p) != NONE16) hmin = fmin(hmin, W[ids.get(p)]);
                     const double he = hmin + eps;
                     double nw = w;
                     if (zk >= he) nw = zk;
@@ -113,18 +109,41 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
                     }
                     if (nw != w) {
                         W[k] = nw;
+                        // mark every interior neighbour pending (independent shared-memory atomics, issued back to
+                        // back), then append those that were not pending yet to the worklist of their level
+                        unsigned fresh = 0;
 #pragma unroll
-                        for (int p = 0; p < KDT; ++p)
-                            if (ids[u].get(p) != NONE16 && (int)ids[u].get(p) >= c.bounds) dirty[ids[u].get(p)] = 1;
+                        for (int p = 0; p < KDT; ++p) {
+                            const unsigned j = ids.get(p);
+                            if (j == NONE16 || (int)j < nb) continue;
+                            const unsigned bit = 1u << (j & 31);
+                            if (!(atomicOr(&bits[j >> 5], bit) & bit)) fresh |= 1u << p;
+                        }
+#pragma unroll
+                        for (int p = 0; p < KDT; ++p) {
+                            if (!(fresh & (1u << p))) continue;
+                            const unsigned j = ids.get(p);
+                            const int lj = lev8[j];
+                            const int bj = S.lev_off[lj], cj = S.lev_off[lj + 1] - bj;
+                            int t = atomicAdd(&S.fl_tail[lj], 1);
+                            t = (t >= cj) ? t % cj : t;
+                            pend[bj + t] = (unsigned short)j;
+                        }
                     }
                 }
             }
             __syncthreads();
+            if (tid == 0) S.fl_head[l] = head + n;   // consumed; nobody reads head[l] before its next turn
         }
         change = __syncthreads_or(loc);
     }
     if (tid == 0) pcd[12] += nsweepd;                                   // diagnostics: sweeps
     if (nevald) atomicAdd((unsigned long long *)&pcd[13], (unsigned long long)nevald);   // and node evaluations
+    // stage z next to W for the receiver search
+    double *zs = W + Nq;
+    __syncthreads();
+    for (int i = tid; i < N; i += TPB) zs[i] = z[i];
+    __syncthreads();
     // receivers on both surfaces
     int *rcv = S.P.i[I_RCV], *rcv1 = S.P.i[I_RCV1];
     double *maxh = S.P.f[F_MAXH], *fillH = S.P.f[F_FILLH];
@@ -167,7 +186,7 @@ __device__ void links_stack(const DevConst &c, Smem &S, unsigned char *dsm, cons
     unsigned *eu = (unsigned *)dsm;                                  // [2*Nq]
     unsigned short *r16 = (unsigned short *)(dsm + (size_t)8 * Nq);  // [Nq]
     unsigned long long *K = (unsigned long long *)(dsm + (size_t)10 * Nq + 64 - ((size_t)10 * Nq) % 8);
-    const int kcap = (int)(((size_t)DYN_SMEM - (size_t)10 * Nq - 128) / 8);
+    const int kcap = (int)(((size_t)17 * Nq - (size_t)10 * Nq - 128) / 8);
     for (int v = tid; v < N; v += TPB) r16[v] = (unsigned short)rcvg[v];
     __syncthreads();
     unsigned short *lc16 = (unsigned short *)S.P.i[I_LC], *ps16 = (unsigned short *)S.P.i[I_PS];
