@@ -181,7 +181,6 @@ class bayeslands_mcmc(object):
         pos_rain = np.zeros((S_, C_)); pos_erod = np.zeros((S_, C_)); pos_likl = np.zeros((S_, C_))
         pos_rain[0], pos_erod[0], pos_likl[0] = rain, erod, lik
         naccept = np.zeros(C_, dtype=np.int64)
-        eta = np.zeros(C_)
         for i in range(S_ - 1):
             p_rain = rain.copy(); p_erod = erod.copy()
             for c in range(C_):
@@ -191,8 +190,8 @@ class bayeslands_mcmc(object):
                 v = erod[c] + rs[c].normal(0, self.step_erod)
                 if not (v < self.erodlimits[0] or v > self.erodlimits[1]):
                     p_erod[c] = v
-                for _ in range(3):
-                    rs[c].normal(0, abs(eta[c] * 0.02) if eta[c] else 1.0, 1)
+                for _ in range(3):          # eta random walk draws (bl_mcmc.py:670-677): consumed, never used (F8)
+                    rs[c].normal(0, 1.0, 1)
             lik_p, _ = self.likelihood_batch(p_rain, p_erod)
             for c in range(C_):
                 diff = lik_p[c] - lik[c]

@@ -1,0 +1,113 @@
+"""GPU tests of the reference-shaped host API (bayeslands_mcmc / Model mirrors) against the oracle."""
+import math
+import random
+
+import numpy as np
+import pytest
+
+from conftest import CRATER_FAST_COORDS
+
+pytestmark = pytest.mark.gpu
+
+
+def _mc(crater_fast, batch, likl_sed=True, samples=6):
+    from bayeslands_b200.mcmc import bayeslands_mcmc
+    d, inp, m = crater_fast
+    return bayeslands_mcmc(True, 15000, samples, d["final_elev"], d["final_erdp"], d["final_erdp_pts"],
+                           np.array(CRATER_FAST_COORDS), None, inp, [3.e-5, 7.e-5], [0.0, 3.0], [0.4, 0.6], [0.9, 1.1],
+                           "t", likl_sed, batch=batch, mesh=m)
+
+
+def _oracle_lik(crater_fast, om, rain, erod, seed, likl_sed):
+    from oracle import oracle
+    d, inp, m = crater_fast
+    ev, ed, pts = om.blackbox(rain, erod, 15000, CRATER_FAST_COORDS, seed=int(seed))
+    return oracle.likelihood(ev[15000], d["final_elev"], np.array([pts[k] for k in sorted(pts)]), d["final_erdp_pts"],
+                             likl_sed)[0], ev, ed, pts
+
+
+def test_blackbox_and_likelihoodfunc_match_reference_shapes_and_oracle(crater_fast):
+    from oracle import oracle
+    d, inp, m = crater_fast
+    mc = _mc(crater_fast, 4)
+    mc._evals = 0
+    ev, ed, pts = mc.blackBox(1.5, 5e-5, 0.5, 1.0)
+    assert list(ev.keys()) == [0, 3750, 7500, 11250, 15000] and ev[15000].shape == (123, 123) and pts[0].shape == (10,)
+    om = oracle.OracleModel(m, inp)
+    _, oev, oed, opts = _oracle_lik(crater_fast, om, 1.5, 5e-5, 0, True)
+    for T in ev:
+        assert np.array_equal(ev[T], oev[T]) and np.array_equal(ed[T], oed[T]) and np.array_equal(pts[T], opts[T])
+    mc._evals = 0
+    out = mc.likelihoodFunc([1.5, 5e-5, 0.5, 1.0], d["final_elev"], d["final_erdp"], d["final_erdp_pts"], 1.0, 1.0, 1.0)
+    want = _oracle_lik(crater_fast, om, 1.5, 5e-5, 0, True)[0]
+    assert abs(out[0] - want) <= 1e-9 * abs(want)
+
+
+def test_likelihood_batch_matches_oracle(crater_fast):
+    from oracle import oracle
+    d, inp, m = crater_fast
+    for sed in (False, True):
+        mc = _mc(crater_fast, 5, likl_sed=sed)
+        rain = np.array([1.5, 0.2, 2.8, 1.0, 0.0]); erod = np.array([5e-5, 6.5e-5, 3.2e-5, 4e-5, 5e-5])
+        seeds = np.array([11, 12, 13, 14, 15], dtype=np.int64)
+        lik, tau = mc.likelihood_batch(rain, erod, seeds=seeds)
+        om = oracle.OracleModel(m, inp)
+        for b in range(5):
+            want = _oracle_lik(crater_fast, om, rain[b], erod[b], seeds[b], sed)[0]
+            assert abs(lik[b] - want) <= 1e-9 * abs(want)
+
+
+def test_sampler_chains_accept_reject_equal_oracle_chain(crater_fast):
+    """Same RNG protocol driven by the oracle must take identical accept/reject decisions."""
+    from oracle import oracle
+    d, inp, m = crater_fast
+    S, Cn = 5, 2
+    mc = _mc(crater_fast, Cn, samples=S)
+    mc._evals = 0
+    out = mc.sampler_chains(Cn, np_seed=3, py_seed=9)
+    om = oracle.OracleModel(m, inp)
+    evals = 0
+    # replay on the CPU: seeds are handed out in evaluation order, batch by batch (mcmc._seeds)
+    rs = [np.random.RandomState(3 + c) for c in range(Cn)]
+    pr = [random.Random(9 + c) for c in range(Cn)]
+    rain = np.array([r.uniform(0.0, 3.0) for r in rs]); erod = np.array([r.uniform(3e-5, 7e-5) for r in rs])
+    lik = np.array([_oracle_lik(crater_fast, om, rain[c], erod[c], evals + c, True)[0] for c in range(Cn)]); evals += Cn
+    pos = [(rain.copy(), erod.copy())]
+    for i in range(S - 1):
+        p_r, p_e = rain.copy(), erod.copy()
+        for c in range(Cn):
+            v = rain[c] + rs[c].normal(0, mc.step_rain)
+            if not (v < 0.0 or v > 3.0): p_r[c] = v
+            v = erod[c] + rs[c].normal(0, mc.step_erod)
+            if not (v < 3e-5 or v > 7e-5): p_e[c] = v
+            for _ in range(3): rs[c].normal(0, 1.0, 1)
+        lp = np.array([_oracle_lik(crater_fast, om, p_r[c], p_e[c], evals + c, True)[0] for c in range(Cn)]); evals += Cn
+        for c in range(Cn):
+            try: mh = min(1, math.exp(lp[c] - lik[c]))
+            except OverflowError: mh = 1
+            if pr[c].uniform(0, 1) < mh: lik[c], rain[c], erod[c] = lp[c], p_r[c], p_e[c]
+        pos.append((rain.copy(), erod.copy()))
+    for i in range(S):
+        assert np.array_equal(out["pos_rain"][i], pos[i][0]) and np.array_equal(out["pos_erod"][i], pos[i][1])
+
+
+def test_model_mirror_load_xml_run_to_time(crater_fast):
+    from bayeslands_b200.model import Model
+    from oracle import oracle
+    d, inp, m = crater_fast
+    model = Model()
+    ie, ir = model.load_xml("0", str(d["xml"]), muted=True, mesh=m, seed=5)
+    assert ie == [] and ir == []
+    model.input.SPLero = 4e-5
+    model.flow.erodibility.fill(4e-5)
+    model.force.rainVal[:] = 2.0
+    om = oracle.OracleModel(m, inp, seed=5)
+    om.reset(2.0, 4e-5, seed=5)
+    for T in (0, 3750, 7500):
+        model.run_to_time(T, muted=True)
+        om.run_to_time(float(T))
+        assert model.tNow == om.tNow
+        assert np.array_equal(model.elevation, om.z) and np.array_equal(model.cumdiff, om.cumdiff)
+    model.run_to_time(1e9, muted=True)          # clamped to the XML end (model.py:240-243)
+    assert model.tNow == 15000.0
+    assert model.FVmesh.node_coords.shape == (m.N, 2) and model.flow.receivers.shape == (m.N,)
