@@ -645,6 +645,8 @@ __device__ double phase_cfl(const DevConst &c, Smem &S, double erod)
 
 __device__ inline double py2_floorish(double x) { return (x > 1.) ? round(x - 0.5) : x; }
 
+__device__ void phase_streampower_serial(const DevConst &c, Smem &S, double erod, double sea, double dt);
+
 // phase: stream power law.  FLOWalgo.f90:583-1044, single rock, detachment-limited.
 //  (1) per-node pre-pass: incision rate and the deposition rule that applies (parallel);
 //  (2) sediment routing  sedFluxes(recvr) += Qs  as the same ordered dataflow pass as the discharge;
@@ -688,7 +690,13 @@ __device__ void phase_streampower(const DevConst &c, Smem &S, double erod, doubl
         double e = 0.;
         if (totspl < 0.) { k = 0; e = SPL * dt * area; }
         else if (totspl >= 0. && area > 0.) {
-            if (waterH > 0. && fh > sea) k = 1;
+            if (waterH > 0. && fh > sea) {
+                k = 1;
+                // first cascade iteration is static when the node's pit lies under the sea (:979-991): the load
+                // settles on the node if it is under water itself, else it is passed on to the receiver
+                const int pp = pitID[d];
+                if (pp >= 0 && c.area[pp] > 0. && W[pp] < sea) k = (zd < sea) ? 2 : 4;
+            }
             else if (zd <= sea) k = 2;
             else if (maxh > 0. && waterH == 0. && d != r && zd > sea) k = 3;
             else if (d == r) k = 2;
@@ -738,6 +746,8 @@ __device__ void phase_streampower(const DevConst &c, Smem &S, double erod, doubl
     __syncthreads();
     // (3) lake-entry events in reverse stack order
     const int nev = blk_compact(N, events, [&](int i) { const int v = stack[N - 1 - i]; return kind[v] == 1 && pdep[v] > 0.; }, S);
+    if (tid == 0) S.ibuf[0] = 0;
+    __syncthreads();
     if (tid == 0 && nev > 0) {
         unsigned st = 0;
         for (int e = 0; e < nev; ++e) {
@@ -752,9 +762,10 @@ __device__ void phase_streampower(const DevConst &c, Smem &S, double erod, doubl
                 if (++guard > 1000000 || tmpID < 0) { st |= BL_ST_CASCADE_GUARD; break; }
                 const double tmpdist = 0. + depo[tmpID];
                 if (W[tmpID] < sea) {
-                    // marine branch feeds sedFluxes(recvr): needs the sequential marine path (etopo)
-                    st |= BL_ST_MARINE;
+                    // an overflow reaching the sea is handed back to the routing (sedFluxes(recvr) += pitDep):
+                    // redo the whole pass with the literal serial loop
                     if (z[donor] < sea) depo[donor] = depo[donor] + pitDep;
+                    else { S.ibuf[0] = 1; e = nev; }
                     totdist = 0.;
                     nID = recvr;
                 } else if (tmpdist + totdist <= pitVol[tmpID]) {
@@ -781,6 +792,7 @@ __device__ void phase_streampower(const DevConst &c, Smem &S, double erod, doubl
         if (st) atomicOr(&c.status[blockIdx.x], st);
     }
     __syncthreads();
+    if (S.ibuf[0]) phase_streampower_serial(c, S, erod, sea, dt);
 }
 
 // numpy pairwise summation order (numpy/_core/src/umath/loops_utils.h.src) for flowNetwork.py:759
@@ -828,6 +840,237 @@ __device__ double pairwise_sum(const double *a, int n)
     return vstk[0];
 }
 
+// PDalgo.f90:136-269 marine_distribution (single rock): a strictly sequential "drop the sediment, spill what does
+// not fit to the lowest neighbour" walk over the marine deposit nodes, diffnb passes, elevation updated in
+// place.  Kept literal on one thread per proposal (parallelism is across proposals); the per-pass reset of the
+// sediment array is done by the whole block.  Adds the resulting thickness to dth[].
+__device__ void phase_marine_distribution(const DevConst &c, Smem &S, double sea)
+{
+    const int N = c.N, tid = threadIdx.x;
+    const double *z = S.P.f[F_Z];
+    double *dep = S.P.f[F_SEDIN], *dth = S.P.f[F_DTHICK];
+    double *elev = S.P.f[F_VAL], *seadep = S.P.f[F_E];
+    int *seaid = S.P.i[I_MEMB];
+    const int *isl = S.P.i[I_KIND];
+    const int nsea = blk_compact(N, seaid, [&](int i) { return isl[i] == 2; }, S);
+    for (int k = tid; k < N; k += TPB) elev[k] = z[k];
+    __syncthreads();
+    const double diff_res = 1.e-2;
+    const int max_it_cyc = 500000;
+    for (int mm = 0; mm < c.diffnb; ++mm) {
+        for (int k = tid; k < N; k += TPB) seadep[k] = ((isl[k] == 2) ? dep[k] : 0.) / (double)(float)c.diffnb;
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 0; k < nsea; ++k) {
+                int id = seaid[k];
+                int it = 0;
+                for (;;) {
+                    if (!(c.flags[id] & 1)) { seadep[id] = 0.; break; }
+                    const double area = c.area[id];
+                    double maxz = -1.e8;
+                    for (int q = 0; q < c.KD; ++q) {
+                        const int j = c.ngb[(size_t)q * N + id];
+                        if (j < 0) break;
+                        if (maxz < elev[j]) maxz = elev[j];
+                    }
+                    if (maxz > sea) maxz = sea;
+                    if (maxz < elev[id]) maxz = elev[id];
+                    const double vol = fmax(0., c.diffprop * (maxz - elev[id]) * area);
+                    if (it > max_it_cyc) { elev[id] = elev[id] + seadep[id] / area; seadep[id] = 0.; break; }
+                    if (seadep[id] / area < diff_res) { elev[id] = elev[id] + seadep[id] / area; seadep[id] = 0.; break; }
+                    it = it + 1;
+                    if (seadep[id] < vol) { elev[id] = elev[id] + seadep[id] / area; seadep[id] = 0.; break; }
+                    else { seadep[id] = seadep[id] - vol; elev[id] = elev[id] + vol / area; }
+                    if (seadep[id] > 0.) {
+                        double minz = elev[id];
+                        int nid = -1;
+                        maxz = -1.e8;
+                        for (int q = 0; q < c.KD; ++q) {
+                            const int j = c.ngb[(size_t)q * N + id];
+                            if (j < 0) break;
+                            if (minz > elev[j]) { nid = j; minz = elev[nid]; }
+                            if (maxz < elev[j]) maxz = elev[j];
+                        }
+                        if (nid == -1) {
+                            const double dh = maxz - elev[id] + 0.1;
+                            if (seadep[id] > dh * area) {
+                                elev[id] = elev[id] + dh;
+                                seadep[id] = seadep[id] - dh * area;
+                                nid = seaid[k];
+                                it = 0;
+                                if (nid == id) seadep[nid] = seadep[id];
+                                else { seadep[nid] = seadep[nid] + seadep[id]; seadep[id] = 0.; }
+                                id = seaid[k];
+                            } else { elev[id] = elev[id] + seadep[id] / area; seadep[id] = 0.; break; }
+                        } else {
+                            seadep[nid] = seadep[nid] + seadep[id];
+                            seadep[id] = 0.;
+                            id = nid;
+                        }
+                    } else { seadep[id] = 0.; break; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int k = tid; k < N; k += TPB) {
+        dth[k] += elev[k] - z[k];
+        if (isl[k] == 2) dep[k] = 0.;
+    }
+    __syncthreads();
+}
+
+// FLOWalgo.f90:332-388 diffmarine + the sub-stepping loop of buildFlux.py:198-247 (river-borne marine sediment
+// diffusion, criver > 0).  z / cumdiff are updated in place; `sumdep` starts as the step's deposition thickness.
+__device__ void phase_marine_diffusion(const DevConst &c, Smem &S, double sea, double timestep)
+{
+    const int N = c.N, tid = threadIdx.x;
+    double *z = S.P.f[F_Z], *cumdiff = S.P.f[F_CUMDIFF];
+    double *sumdep = S.P.f[F_DTHICK], *coeff = S.P.f[F_E], *dm = S.P.f[F_CAPH];
+    const double maxth = 0.1;
+    for (int k = tid; k < N; k += TPB) {                       // diffLinear.sedfluxmarine (diffLinear.py:184-213)
+        const double area = c.area[k];
+        const double ac = (area > 0.) ? 1. / area : 0.;
+        coeff[k] = ac * ((z[k] >= sea) ? 0. : c.CDr);
+    }
+    __syncthreads();
+    double diffstep = timestep;
+    int it = 0;
+    while (diffstep > 0. && it < 1000) {
+        double maxstep = fmin(c.ms, diffstep);
+        double mind = maxstep;
+        for (int g = tid; g < N; g += TPB) {
+            double acc = 0.;
+            if ((c.flags[g] & 1) && z[g] < sea) {
+                const double zg = z[g], dg = sumdep[g], cg = coeff[g];
+                for (int q = 0; q < c.KD; ++q) {
+                    const int j = c.ngb[(size_t)q * N + g];
+                    if (j < 0) break;
+                    const double zj = z[j];
+                    if (c.flags[j] & 1) {
+                        const double flx = c.vor[(size_t)q * N + g] * (zj - zg) / c.edge[(size_t)q * N + g];
+                        if (dg > maxth && zg > zj) acc = acc + cg * flx;
+                        else if (sumdep[j] > maxth && zg < zj && zj < sea) acc = acc + cg * flx;
+                    } else {
+                        if (dg > maxth && zg > zj) {
+                            const double flx = c.vor[(size_t)q * N + g] * (zj - zg) / c.edge[(size_t)q * N + g];
+                            acc = acc + cg * flx;
+                        }
+                    }
+                }
+                if (acc < 0. && acc * maxstep < -dg) mind = fmin(-dg / acc, mind);
+            }
+            dm[g] = (c.flags[g] & 1) ? acc : 0.;
+        }
+        mind = blk_min(mind, S);
+        maxstep = fmin(mind, maxstep);
+        diffstep -= maxstep;
+        for (int k = tid; k < N; k += TPB) {
+            const double d = dm[k] * maxstep;
+            sumdep[k] += d; z[k] += d; cumdiff[k] += d;
+        }
+        __syncthreads();
+        ++it;
+    }
+}
+
+// FLOWalgo.f90:583-1044, literal reverse-stack loop on one thread.  Used only when the pit cascade hands sediment
+// back to the routing (an overflowing lake draining into the sea: sedFluxes(recvr) += pitDep, :986-989), which
+// couples the cascade state to the ordered routing and leaves no parallel shortcut.
+__device__ void streampower_serial(const DevConst &c, Smem &S, const int *rcv, double erod, double sea, double dt,
+                                   unsigned &st)
+{
+    const int N = c.N;
+    const int *stack = S.P.i[I_STACK], *pitID = S.P.i[I_PITID], *pitDrain = S.P.i[I_PITDRAIN];
+    const double *z = S.P.f[F_Z], *W = S.P.f[F_FILLH], *Q = S.P.f[F_Q], *maxhA = S.P.f[F_MAXH];
+    double *depo = S.P.f[F_DEPO], *ero = S.P.f[F_ERO], *sedfl = S.P.f[F_SEDIN], *pitVol = S.P.f[F_PITVOLW];
+    for (int i = N - 1; i >= 0; --i) {
+        const int donor = stack[i], recvr = rcv[donor];
+        const double zd = z[donor], zr = z[recvr], fh = W[donor], area = c.area[donor];
+        double SPL = 0., totspl = 0.;
+        double dh = 0.95 * (zd - zr);
+        if (zd > sea && zr < sea) dh = 0.99 * (zd - sea);
+        if (dh < 0.001) dh = 0.;
+        const double waterH = fh - zd;
+        double totdist = 0.;
+        if (recvr != donor && dh > 0. && waterH == 0. && fh >= sea) {
+            const double dx = c.xy[2 * donor] - c.xy[2 * recvr], dy = c.xy[2 * donor + 1] - c.xy[2 * recvr + 1];
+            const double dist = sqrt(dx * dx + dy * dy);
+            if (dist > 0.) {
+                const double slp = dh / dist;
+                SPL = -erod * 1. * 1. * powx(Q[donor], c.m) * powx(slp, c.n);
+                totspl = totspl + SPL;
+                if (-totspl * dt > dh) { const double frac = dh / (-totspl * dt); SPL = SPL * frac; totspl = -dh; }
+            }
+        }
+        double maxh = maxhA[donor];
+        if (waterH > 0.) maxh = waterH;
+        else if (zd < sea) maxh = sea - zd;
+        maxh = 0.95 * maxh;
+        double Qs = 0., erodep = 0., pitDep = 0.;
+        if (totspl < 0.) { erodep = SPL * dt * area; Qs = -erodep + sedfl[donor]; }
+        else if (totspl >= 0. && area > 0.) {
+            if (waterH > 0. && fh > sea) { pitDep = sedfl[donor]; totdist = totdist + pitDep; }
+            else if (zd <= sea) erodep = sedfl[donor];
+            else if (maxh > 0. && waterH == 0. && donor != recvr && zd > sea) {
+                const double totflx = 0. + sedfl[donor];
+                if (totflx / area < maxh) erodep = sedfl[donor];
+                else { const double frac = sedfl[donor] / totflx; erodep = frac * maxh * area; Qs = sedfl[donor] - erodep; }
+            } else if (donor == recvr) erodep = sedfl[donor];
+            else Qs = sedfl[donor];
+        }
+        if (pitDep == 0.) {
+            sedfl[recvr] = sedfl[recvr] + Qs;
+            if (erodep < 0.) ero[donor] = ero[donor] + erodep;
+            else depo[donor] = depo[donor] + erodep;
+        } else if (pitDep > 0. && pitID[donor] >= 0 && c.area[pitID[donor]] > 0.) {
+            int tmpID = pitID[donor], nID = tmpID;
+            long guard = 0;
+            while (totdist > 0.) {
+                if (++guard > 1000000 || tmpID < 0) { st |= BL_ST_CASCADE_GUARD; break; }
+                const double tmpdist = 0. + depo[tmpID];
+                if (W[tmpID] < sea) {
+                    if (zd < sea) depo[donor] = depo[donor] + pitDep;
+                    else sedfl[recvr] = sedfl[recvr] + pitDep;
+                    totdist = 0.; nID = recvr;
+                } else if (tmpdist + totdist <= pitVol[tmpID]) { depo[tmpID] = depo[tmpID] + pitDep; totdist = 0.; nID = tmpID; }
+                else if (pitDrain[tmpID] == tmpID) { depo[tmpID] = depo[tmpID] + pitDep; totdist = 0.; nID = tmpID; }
+                else {
+                    if (!(c.flags[tmpID] & 1)) { totdist = 0.; nID = tmpID; }
+                    else if (tmpdist == pitVol[tmpID]) nID = tmpID;
+                    else {
+                        const double frac = pitDep / totdist;
+                        depo[tmpID] = depo[tmpID] + (pitVol[tmpID] - tmpdist) * frac;
+                        pitDep = (totdist - (pitVol[tmpID] - tmpdist)) * frac;
+                        const double newdist = 0. + pitDep;
+                        const double totflx = 0. + depo[tmpID];
+                        totdist = newdist;
+                        pitVol[tmpID] = totflx;
+                        nID = tmpID;
+                    }
+                }
+                tmpID = pitDrain[nID];
+            }
+        }
+    }
+}
+
+// block wrapper: reset the outputs, then run the literal loop on thread 0
+__device__ void phase_streampower_serial(const DevConst &c, Smem &S, double erod, double sea, double dt)
+{
+    const int N = c.N, tid = threadIdx.x;
+    double *depo = S.P.f[F_DEPO], *ero = S.P.f[F_ERO], *sedfl = S.P.f[F_SEDIN], *pitVol = S.P.f[F_PITVOLW];
+    const double *pitVol1 = S.P.f[F_PITVOL];
+    for (int k = tid; k < N; k += TPB) { depo[k] = 0.; ero[k] = 0.; sedfl[k] = 0. * dt; pitVol[k] = pitVol1[k]; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned st = 0;
+        streampower_serial(c, S, S.P.i[I_RCV], erod, sea, dt, st);
+        if (st) atomicOr(&c.status[blockIdx.x], st);
+    }
+    __syncthreads();
+}
+
 // phase: erosion / deposition thickness.  flowNetwork.compute_sedflux (flowNetwork.py:721-793) with getids
 // (FLOWalgo.f90:1089-1180) fused.  Result sedflux[] (= ed) in metres.
 __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
@@ -856,7 +1099,7 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
                     else d = 0.;
                 }
             }
-            if (zk <= sea) { sumdep = sumdep + d; if (sumdep > 0.) marine = 1; }
+            if (zk <= sea) { sumdep = sumdep + d; if (sumdep > 0.) { marine = 1; island = 2; } }
             if (plain) { th = d / c.area[k]; d = 0.; }
         }
         dep[k] = d;
@@ -864,10 +1107,9 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
         S.P.i[I_KIND][k] = island;
     }
     marine = __syncthreads_or(marine);
-    if (marine && tid == 0) atomicOr(&c.status[blockIdx.x], BL_ST_MARINE);
     if (c.depo != 0) {
         const int *isl = S.P.i[I_KIND];
-        const int nland = blk_compact(N, land, [&](int i) { return isl[i] != 0; }, S);
+        const int nland = blk_compact(N, land, [&](int i) { return isl[i] == 1; }, S);
         // land pits (flowNetwork.py:750-763): members = where(pitID == p) in ascending id; the basin's nodes
         // are a contiguous segment of the real-surface stack.  Small basins: one thread gathers + sorts its
         // members; large basins: the block compacts them in id order.
@@ -922,6 +1164,7 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
         }
         for (int q = tid; q < nland; q += TPB) dep[land[q]] = 0.;
         __syncthreads();
+        if (marine) phase_marine_distribution(c, S, sea);     // flowNetwork.py:769-776
         // forced deposition of anything left (flowNetwork.py:782-785)
         int any = 0;
         for (int k = tid; k < N; k += TPB) any |= (dep[k] != 0.);
@@ -952,6 +1195,7 @@ __device__ void phase_apply(const DevConst &c, Smem &S, double sea, double times
     double *cd = S.P.f[F_VAL];
     for (int k = tid; k < N; k += TPB) { z[k] += sedflux[k]; cumdiff[k] += sedflux[k]; }
     __syncthreads();
+    if (c.CDr > 0.) phase_marine_diffusion(c, S, sea, timestep);
     for (int g = tid; g < N; g += TPB) {
         double acc = 0.;
         const unsigned char fg = c.flags[g];
@@ -1295,7 +1539,6 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
             }
             if (!ok) { g_err = "bl_ctx_create: neighbour lists are not symmetric"; return BL_ERR_ARG; }
         }
-    if (p->CDr > 0.) { g_err = "bl_ctx_create: criver > 0 (marine sediment diffusion) not built yet"; return BL_ERR_UNSUPPORTED; }
     std::vector<int> level;
     const int nlev = std::max(1, gs_levels(m, level));
     const int KD = std::max(1, max_degree(m));

@@ -523,7 +523,11 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
         double e = 0.;
         if (totspl < 0.) { k = 0; e = SPL * dt * area; }
         else if (totspl >= 0. && area > 0.) {
-            if (waterH > 0. && fh > sea) k = 1;
+            if (waterH > 0. && fh > sea) {
+                k = 1;
+                const int pp = pitID[d];          // pit under the sea: static first cascade step (:979-991)
+                if (pp >= 0 && c.area[pp] > 0. && W[pp] < sea) k = (zd < sea) ? 2 : 4;
+            }
             else if (zd <= sea) k = 2;
             else if (maxh > 0. && waterH == 0. && d != r && zd > sea) { k = 3; e = maxh; }
             else if (d == r) k = 2;
@@ -613,6 +617,7 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
     }
     // serial replay, literal (FLOWalgo.f90:967-1034)
     for (int k = tid; k < N; k += TPB) pitVol[k] = pitVol1[k];
+    if (tid == 0) S.ibuf[0] = 0;
     __syncthreads();
     if (tid == 0) {
         unsigned st = 0;
@@ -629,8 +634,8 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
                 const double tmpdist = 0. + depo[tmpID];
                 const double pv = pitVol[tmpID];
                 if (W[tmpID] < sea) {
-                    st |= BL_ST_MARINE;
                     if (z[donor] < sea) depo[donor] = depo[donor] + pitDep;
+                    else { S.ibuf[0] = 1; e = nev; }     // handed back to the routing: literal serial pass below
                     totdist = 0.;
                     nID = recvr;
                 } else if (tmpdist + totdist <= pv) {
@@ -657,6 +662,7 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
         if (st) atomicOr(&c.status[blockIdx.x], st);
     }
     __syncthreads();
+    if (S.ibuf[0]) phase_streampower_serial(c, S, erod, sea, dt);
 }
 
 // buildFlux.py:193-195, :252-272, :292-315 (see phase_apply) with z staged in shared memory for the gather
@@ -667,10 +673,17 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
     double *zs = (double *)dsm, *cd = zs + Nq;
     double *z = S.P.f[F_Z], *cumdiff = S.P.f[F_CUMDIFF], *cumhill = S.P.f[F_CUMHILL];
     const double *sedflux = S.P.f[F_SEDFLUX];
-    for (int k = tid; k < N; k += TPB) {
-        const double sf = sedflux[k];
-        zs[k] = z[k] + sf;
-        cumdiff[k] += sf;
+    if (c.CDr > 0.) {            // river-borne marine sediment diffusion works on the global arrays
+        for (int k = tid; k < N; k += TPB) { const double sf = sedflux[k]; z[k] += sf; cumdiff[k] += sf; }
+        __syncthreads();
+        phase_marine_diffusion(c, S, sea, timestep);
+        for (int k = tid; k < N; k += TPB) zs[k] = z[k];
+    } else {
+        for (int k = tid; k < N; k += TPB) {
+            const double sf = sedflux[k];
+            zs[k] = z[k] + sf;
+            cumdiff[k] += sf;
+        }
     }
     __syncthreads();
     for (int g = tid; g < N; g += TPB) {

@@ -33,6 +33,10 @@ CONFIGS = {
                [[60, 60], [52, 67], [74, 76], [62, 45], [72, 66], [85, 73], [90, 75], [44, 86], [100, 80], [88, 69]], True),
     "crater_fast": ("crater_fast", 15000, (0.0, 3.0), (3.e-5, 7.e-5),
                     [[60, 60], [72, 66], [85, 73], [90, 75], [44, 86], [100, 80], [88, 69], [79, 91], [96, 77], [42, 49]], True),
+    "etopo_fast": ("etopo_fast", 500000, (0.0, 3.0), (3.e-6, 7.e-6),
+                   [[42, 10], [39, 8], [75, 51], [59, 13], [40, 5], [6, 20], [14, 66], [4, 40], [68, 40], [72, 44]], True),
+    "etopo": ("etopo", 1000000, (0.0, 3.0), (3.e-6, 7.e-6),
+              [[42, 10], [39, 8], [75, 51], [59, 13], [40, 5], [6, 20], [14, 66], [4, 40], [72, 73], [46, 64]], True),
 }
 B_ALG_NODE_STEP = 340.0   # algorithmic bytes / node / time step / proposal
 B_ALG_CELL = 160.0        # bytes / grid cell / evaluation
@@ -61,7 +65,7 @@ _W = {}
 def _cpu_init(cfg):
     from oracle import oracle
     d, inp, m, simtime, rl, el, coords, likl_sed = load_config(cfg)
-    _W.update(om=oracle.OracleModel(m, inp), d=d, simtime=simtime, coords=coords, likl_sed=likl_sed, oracle=oracle)
+    _W.update(om=oracle.OracleModel(m, inp, sealevel=d["sealevel"] if "sealevel" in d else None), d=d, simtime=simtime, coords=coords, likl_sed=likl_sed, oracle=oracle)
 
 
 def _cpu_eval(args):
@@ -178,7 +182,8 @@ def run_ours(args):
     d, inp, m, simtime, rl, el, coords, likl_sed = load_config(cfg)
     B = args.batch
     mc = bayeslands_mcmc(True, simtime, 0, d["final_elev"], d["final_erdp"], d["final_erdp_pts"], coords, None, inp,
-                         el, rl, (0.4, 0.6), (0.9, 1.1), "bench", likl_sed, batch=B, device=local, mesh=m)
+                         el, rl, (0.4, 0.6), (0.9, 1.1), "bench", likl_sed, batch=B, device=local, mesh=m,
+                         sealevel=d["sealevel"] if "sealevel" in d else None)
     eng = mc.engine
     dev = eng.tdev
     gather = torch.empty(world * B, dtype=torch.float64, device=dev) if world > 1 else None

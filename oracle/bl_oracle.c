@@ -14,7 +14,8 @@
 #include <string.h>
 
 /* diagnostics (not part of the algorithm): pit-cascade event / iteration counters */
-long or_diag_cascade_events = 0, or_diag_cascade_iters = 0;
+long or_diag_cascade_events = 0, or_diag_cascade_iters = 0, or_diag_marine_iters = 0, or_diag_marine_calls = 0,
+     or_diag_marine_nodes = 0, or_diag_msub = 0, or_diag_cascade_marine_pass = 0;
 
 /* ------------------------------------------------------------------------------------------ */
 /* libUtils/sfd.c                                                                              */
@@ -407,7 +408,7 @@ int or_streampower(const or_mesh *m, const or_params *p, int n, const int *stack
                 double tmpdist = 0. + depo[tmpID];
                 if (fillH[tmpID] < sea) {
                     if (z[donor] < sea) depo[donor] = depo[donor] + pitDep;
-                    else sedfl[recvr] = sedfl[recvr] + pitDep;
+                    else { sedfl[recvr] = sedfl[recvr] + pitDep; if (tmpID != pitID[donor]) ++or_diag_cascade_marine_pass; }
                     totdist = 0.;
                     nID = recvr;
                 } else if (tmpdist + totdist <= pitVol[tmpID]) {
@@ -483,12 +484,14 @@ void or_marine_distribution(const or_mesh *m, const or_params *p, const double *
     const double diff_res = 1.e-2;
     const int max_it_cyc = 500000;
     memcpy(elev, elevation, (size_t)N * sizeof(double));
+    ++or_diag_marine_calls; or_diag_marine_nodes += nIDs;
     for (int mm = 0; mm < p->diffnb; ++mm) {
         for (int k = 0; k < N; ++k) seadep[k] = seavol[k] / (double)(float)p->diffnb;
         for (int k = 0; k < nIDs; ++k) {
             int id = depIDs[k];
             int it = 0;
             for (;;) {
+                ++or_diag_marine_iters;
                 if (m->borders[id] < 1) { seadep[id] = 0.; break; }
                 const int *nb = m->ngb + (size_t)id * OR_KP;
                 double maxz = -1.e8;
@@ -830,6 +833,7 @@ int or_sediment_flux(const or_mesh *m, const or_params *p, or_state *s, double t
             for (int k = 0; k < N; ++k) if (!m->borders[k]) dm[k] = 0.;
             maxstep = fmin(mindt, maxstep);
             diffstep -= maxstep;
+            ++or_diag_msub;
             for (int k = 0; k < N; ++k) {
                 double d = dm[k] * maxstep;
                 sumdep[k] += d; s->z[k] += d; s->cumdiff[k] += d;

@@ -24,3 +24,17 @@ def crater_fast():
 
 
 CRATER_FAST_COORDS = [[60, 60], [72, 66], [85, 73], [90, 75], [44, 86], [100, 80], [88, 69], [79, 91], [96, 77], [42, 49]]
+
+
+@pytest.fixture(scope="session")
+def etopo_fast():
+    """(data, Input, MeshArrays) of Examples/etopo_fast (sea-level curve, slope boundary, marine deposition)."""
+    import numpy as np
+    from bayeslands_b200 import config, mesh
+    d = np.load(os.path.join(ROOT, "data", "etopo_fast.npz"))
+    inp = config.parse_xml(str(d["xml"]))
+    m = mesh.build_from_dem(d["dem_xyz"], inp.btype, inp.Afactor)
+    return d, inp, m
+
+
+ETOPO_FAST_COORDS = [[42, 10], [39, 8], [75, 51], [59, 13], [40, 5], [6, 20], [14, 66], [4, 40], [68, 40], [72, 44]]

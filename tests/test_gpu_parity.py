@@ -6,7 +6,7 @@ array, because the kernels keep the oracle's operation order and are compiled wi
 import numpy as np
 import pytest
 
-from conftest import CRATER_FAST_COORDS
+from conftest import CRATER_FAST_COORDS, ETOPO_FAST_COORDS
 
 pytestmark = pytest.mark.gpu
 
@@ -77,3 +77,82 @@ def test_full_run_blackbox_bit_exact(crater_fast):
             assert np.array_equal(pts[b, ci], pv[T])
         ref = np.sum(np.square(ev[times[-1]] - d["final_elev"]))
         assert abs(sse[b] - ref) <= 1e-11 * ref
+
+
+ETOPO_PROPOSALS = [(1.5, 5e-6), (2.9, 6.9e-6), (0.5, 3e-6), (0.0, 5e-6)]
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+def test_etopo_stepwise_bit_exact(etopo_fast, generic, monkeypatch):
+    """etopo path: sea-level curve, 'slope' boundary, marine deposition (marine_distribution), river-borne marine
+    diffusion sub-steps, overflow-to-sea fallback - every stage array against the oracle, both device paths."""
+    from bayeslands_b200.engine import Engine
+    from oracle import oracle
+    d, inp, m = etopo_fast
+    if generic:
+        monkeypatch.setenv("BL_FORCE_GENERIC", "1")
+    B = len(ETOPO_PROPOSALS)
+    eng = Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=ETOPO_FAST_COORDS, sealevel=d["sealevel"])
+    rain = np.array([p[0] for p in ETOPO_PROPOSALS]); erod = np.array([p[1] for p in ETOPO_PROPOSALS])
+    seeds = np.arange(B, dtype=np.int64) + 5
+    eng.reset(rain, erod, seeds)
+    oms = []
+    for b in range(B):
+        om = oracle.OracleModel(m, inp, seed=int(seeds[b]), sealevel=d["sealevel"])
+        om.reset(rain[b], erod[b], seed=int(seeds[b]))
+        oms.append(om)
+    for step in range(25):
+        eng.step(500000.0)
+        sc = eng.scalars()
+        for b, om in enumerate(oms):
+            om.streamflow(); om.sediment_flux(500000.0)
+            for f in INT_FIELDS:
+                g = eng.field(f, b); o = getattr(om, f)
+                assert np.array_equal(g, o), "step %d proposal %d %s: %d mismatches" % (step, b, f, (g != o).sum())
+            for f in FP_FIELDS:
+                g = eng.field(f, b); o = getattr(om, f)
+                assert np.array_equal(g, o), "step %d proposal %d %s: max abs diff %g" % (step, b, f, np.abs(g - o).max())
+            assert sc["tNow"][b] == om.tNow and sc["last_dt"][b] == om.last_dt and sc["status"][b] == 0
+
+
+def test_etopo_full_run_bit_exact(etopo_fast):
+    from bayeslands_b200.engine import Engine
+    from bayeslands_b200 import hostparams
+    from oracle import oracle
+    d, inp, m = etopo_fast
+    B = len(ETOPO_PROPOSALS)
+    eng = Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=ETOPO_FAST_COORDS, sealevel=d["sealevel"])
+    rain = np.array([p[0] for p in ETOPO_PROPOSALS]); erod = np.array([p[1] for p in ETOPO_PROPOSALS])
+    seeds = np.arange(B, dtype=np.int64) + 50
+    eng.reset(rain, erod, seeds)
+    times = hostparams.sim_interval(500000)
+    pts, sse, elev, erdp = eng.run_schedule(times, grids=True)
+    pts, elev = pts.cpu().numpy(), elev.cpu().numpy()
+    sc = eng.scalars()
+    assert (sc["status"] == 0).all()
+    for b in range(B):
+        om = oracle.OracleModel(m, inp, seed=int(seeds[b]), sealevel=d["sealevel"])
+        ev, ed, pv = om.blackbox(rain[b], erod[b], 500000, ETOPO_FAST_COORDS, seed=int(seeds[b]))
+        assert sc["steps"][b] == om.steps
+        assert np.array_equal(eng.field("z", b), om.z) and np.array_equal(eng.field("cumdiff", b), om.cumdiff)
+        for ci, T in enumerate(times):
+            assert np.array_equal(elev[b, ci].reshape(ev[T].shape), ev[T]) and np.array_equal(pts[b, ci], pv[T])
+
+
+def test_crater_generic_path_bit_exact(crater_fast, monkeypatch):
+    """The generic (L2-resident) device path stays bit-exact too: it serves meshes too large for shared memory."""
+    from oracle import oracle
+    monkeypatch.setenv("BL_FORCE_GENERIC", "1")
+    d, inp, m = crater_fast
+    eng = _engine(crater_fast, 2)
+    rain = np.array([1.5, 2.7]); erod = np.array([5e-5, 3.3e-5]); seeds = np.array([3, 4], dtype=np.int64)
+    eng.reset(rain, erod, seeds)
+    oms = [oracle.OracleModel(m, inp, seed=int(s)) for s in seeds]
+    for b, om in enumerate(oms):
+        om.reset(rain[b], erod[b], seed=int(seeds[b]))
+    for step in range(6):
+        eng.step(15000.0)
+        for b, om in enumerate(oms):
+            om.streamflow(); om.sediment_flux(15000.0)
+            for f in INT_FIELDS + FP_FIELDS:
+                assert np.array_equal(eng.field(f, b), getattr(om, f)), (step, b, f)

@@ -10,7 +10,7 @@ import torch
 cfg = sys.argv[1] if len(sys.argv) > 1 else "crater_fast"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 148
 d, inp, m, simtime, rl, el, coords, likl_sed = bench.load_config(cfg)
-eng = Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=coords)
+eng = Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=coords, sealevel=d["sealevel"] if "sealevel" in d else None)
 r, e, s = bench.proposals(0, 0, B, rl, el)
 from bayeslands_b200 import hostparams
 for it in range(2):
