@@ -8,7 +8,7 @@
 //   basins           : root ids (u16) + stack-ordered volume terms (fp64)      2N + 8N
 //   discharge / SPL  : node values fp64 + donor links (u16) + counters (u8)    8N + 6N + 3N
 // Neighbour ids come from a u16 slot-major table (coalesced).  Requires N < 32768 and 17*Nq <= 225 KB.
-#pragma once
+
 
 namespace fast {
 
