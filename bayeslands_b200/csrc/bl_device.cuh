@@ -9,7 +9,7 @@ struct Smem {
                                // reference to a by-value kernel parameter would live in (L2-latency) local memory
     Prop P;
     int lev_off[LEVMAX + 1];   // copy of c.lev_off: every CTA reads it every pass (one hot L2 line otherwise)
-    int fl_head[LEVMAX + 1], fl_tail[LEVMAX + 1];   // per-level worklist rings of the fill
+    int fl_head[LEVMAX + 1], fl_tail[LEVMAX + 1], fl_base[LEVMAX + 1], fl_mask[LEVMAX + 1];   // per-level worklist rings of the fill
     unsigned char *dsm;        // dynamic shared memory of the fast kernel (nullptr on the generic path)
     int dsm_bytes;
     int scan[NWARP + 1];

@@ -55,21 +55,26 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
 {
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x, nb = c.bounds;
     double *W = (double *)dsm;                                          // [Nq]
-    unsigned short *pend = (unsigned short *)(dsm + (size_t)8 * Nq);    // [Nq] ring per level, slot = lev_off + i
-    unsigned char *lev8 = dsm + (size_t)10 * Nq;                        // [Nq] level of each node
-    unsigned *bits = (unsigned *)(dsm + (size_t)11 * Nq);               // [Nq/32] "is pending"
+    unsigned short *pend = (unsigned short *)(dsm + (size_t)8 * Nq);    // [<2Nq] one power-of-two ring per level
+    unsigned char *lev8 = dsm + (size_t)12 * Nq + 128;                  // [Nq] level of each node
+    unsigned *bits = (unsigned *)(dsm + (size_t)13 * Nq + 256);         // [Nq/32] "is pending"
     const double *z = S.P.f[F_Z];
-    const bool smlev = (c.nlev <= LEVMAX);
     for (int i = tid; i < N; i += TPB) W[i] = (i < nb) ? z[i] : 1.e6;
     for (int i = tid; i < Nq / 32; i += TPB) bits[i] = 0u;
-    for (int l = 0; l < c.nlev; ++l) {
-        const int b0 = smlev ? S.lev_off[l] : c.lev_off[l], e = smlev ? S.lev_off[l + 1] : c.lev_off[l + 1];
-        for (int idx = b0 + tid; idx < e; idx += TPB) {
-            const int k = c.lev_contig ? (nb + idx) : c.lev_nodes[idx];
-            lev8[k] = (unsigned char)l;
-            pend[idx] = (unsigned short)k;
+    {   // ring i of level l lives at pend[fl_base[l] + (i & fl_mask[l])], capacity = level size rounded up to 2^k
+        int base = 0;
+        for (int l = 0; l < c.nlev; ++l) {
+            const int b0 = S.lev_off[l], e = S.lev_off[l + 1];
+            int cap = 1;
+            while (cap < e - b0) cap <<= 1;
+            for (int idx = b0 + tid; idx < e; idx += TPB) {
+                const int k = c.lev_contig ? (nb + idx) : c.lev_nodes[idx];
+                lev8[k] = (unsigned char)l;
+                pend[base + (idx - b0)] = (unsigned short)k;
+            }
+            if (tid == 0) { S.fl_head[l] = 0; S.fl_tail[l] = e - b0; S.fl_base[l] = base; S.fl_mask[l] = cap - 1; }
+            base += cap;
         }
-        if (tid == 0 && l <= LEVMAX) { S.fl_head[l] = 0; S.fl_tail[l] = e - b0; }
     }
     __syncthreads();
     for (int i = nb + tid; i < N; i += TPB) atomicOr(&bits[i >> 5], 1u << (i & 31));
@@ -82,12 +87,11 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
         int loc = 0;
         ++nsweepd;
         for (int l = 0; l < c.nlev; ++l) {
-            const int b0 = S.lev_off[l], cap = S.lev_off[l + 1] - b0;
             const int head = S.fl_head[l], n = S.fl_tail[l] - head;
+            if (n == 0) continue;                               // uniform: nothing pending at this level
+            const int b0 = S.fl_base[l], msk = S.fl_mask[l];
             for (int i = tid; i < n; i += TPB) {
-                int slot = head + i;
-                slot = (slot >= cap) ? slot % cap : slot;
-                const int k = pend[b0 + slot];
+                const int k = pend[b0 + ((head + i) & msk)];
                 atomicAnd(&bits[k >> 5], ~(1u << (k & 31)));
                 const double w = W[k];
                 Ids<KDT> ids;
@@ -95,10 +99,18 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
                 const double zk = __ldg(z + k);
                 ++nevald;
                 if (w > zk) {
-                    double hmin = 2.e6;
+                    double hm[KDT];
 #pragma unroll
-                    for (int p = 0; p < KDT; ++p)
-                        if (ids.get(p) != NONE16) hmin = fmin(hmin, W[ids.get(p)]);
+                    for (int p = 0; p < KDT; ++p) hm[p] = (ids.get(p) != NONE16) ? W[ids.get(p)] : 2.e6;
+                    double hmin;
+                    if (KDT == 8) {      // min is exact: any association gives the same bits
+                        hmin = fmin(fmin(fmin(hm[0], hm[1]), fmin(hm[2], hm[3])), fmin(fmin(hm[4], hm[5]), fmin(hm[6], hm[7])));
+                    } else {
+                        hmin = 2.e6;
+#pragma unroll
+                        for (int p = 0; p < KDT; ++p) hmin = fmin(hmin, hm[p]);
+                    }
+                    hmin = fmin(hmin, 2.e6);
                     const double he = hmin + eps;
                     double nw = w;
                     if (zk >= he) nw = zk;
@@ -109,8 +121,6 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
                     }
                     if (nw != w) {
                         W[k] = nw;
-                        // mark every interior neighbour pending (independent shared-memory atomics, issued back to
-                        // back), then append those that were not pending yet to the worklist of their level
                         unsigned fresh = 0;
 #pragma unroll
                         for (int p = 0; p < KDT; ++p) {
@@ -124,10 +134,8 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
                             if (!(fresh & (1u << p))) continue;
                             const unsigned j = ids.get(p);
                             const int lj = lev8[j];
-                            const int bj = S.lev_off[lj], cj = S.lev_off[lj + 1] - bj;
-                            int t = atomicAdd(&S.fl_tail[lj], 1);
-                            t = (t >= cj) ? t % cj : t;
-                            pend[bj + t] = (unsigned short)j;
+                            const int t = atomicAdd(&S.fl_tail[lj], 1);
+                            pend[S.fl_base[lj] + (t & S.fl_mask[lj])] = (unsigned short)j;
                         }
                     }
                 }
@@ -250,14 +258,17 @@ __device__ void links_stack(const DevConst &c, Smem &S, unsigned char *dsm, cons
     int active = 1;
     while (active) {
         int loc = 0;
-        for (int e = tid; e < M; e += TPB) {
-            const unsigned w = eu[e];
-            const unsigned nx = w >> 16;
-            if (nx != END16) {
-                const unsigned w2 = eu[nx];
-                eu[e] = (w2 & 0xFFFF0000u) | ((w + w2) & 0xFFFFu);
-                loc = 1;
-            }
+        // four elements per thread in flight: the loads of a group are issued before its stores (any interleaving
+        // of word updates is valid, see above), which hides the shared-memory latency of the dependent lookup
+        for (int e0 = tid; e0 < M; e0 += 4 * TPB) {
+            unsigned w[4], nx[4], w2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int e = e0 + u * TPB; w[u] = (e < M) ? eu[e] : 0xFFFF0000u; nx[u] = w[u] >> 16; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) w2[u] = (nx[u] != END16) ? eu[nx[u]] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (nx[u] != END16) { eu[e0 + u * TPB] = (w2[u] & 0xFFFF0000u) | ((w[u] + w2[u]) & 0xFFFFu); loc = 1; }
         }
         active = __syncthreads_or(loc);
     }

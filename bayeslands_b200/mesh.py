@@ -388,3 +388,70 @@ def _colour_order(points: np.ndarray, nb: int) -> np.ndarray:
         level[v] = 1 + (level[lower].max() if len(lower) else 0)
     inner2 = order[nb:]
     return np.concatenate((np.arange(nb), inner2[np.lexsort((rank[inner2], level[inner2]))]))
+
+
+def build_regular(nx: int, ny: int, dx: float, z: np.ndarray, btype: str = "fixed") -> MeshArrays:
+    """Synthetic regular-grid landscape (BASELINE config 5): D8 stencil as the neighbour list.
+
+    Documented deviation: the reference has no regular-grid mode.  Node order: ghost
+    ring first (same order as raster2TIN), then the nx*ny grid row-major (x fastest).  FV arrays are
+    analytic: area dx^2, Voronoi edge dx for the 4 axis neighbours and 0 for the diagonals.
+    """
+    z = np.asarray(z, dtype=np.float64).reshape(ny, nx)
+    xs = dx * np.arange(nx)
+    ys = dx * np.arange(ny)
+    b_x = dx * np.arange(-1, nx + 1)
+    bsouth = np.column_stack((b_x, np.full(nx + 2, -dx)))
+    bnorth = np.column_stack((b_x, np.full(nx + 2, ny * dx)))
+    beast = np.column_stack((np.full(ny, -dx), ys))
+    bwest = np.column_stack((np.full(ny, nx * dx), ys))
+    bounds = np.vstack((bsouth, beast, bnorth, bwest))
+    nb = len(bounds)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    pts = np.vstack((bounds, np.column_stack((X.ravel(), Y.ravel()))))
+    N = len(pts)
+    # id lookup on the (ny+2, nx+2) extended lattice
+    ext = np.full((ny + 2, nx + 2), -1, dtype=np.int64)
+    ext[0, :] = np.arange(nx + 2)
+    ext[1:-1, 0] = nx + 2 + np.arange(ny)
+    ext[-1, :] = nx + 2 + ny + np.arange(nx + 2)
+    ext[1:-1, -1] = 2 * (nx + 2) + ny + np.arange(ny)
+    ext[1:-1, 1:-1] = nb + np.arange(nx * ny).reshape(ny, nx)
+    ngb = np.full((N, KP), -2, dtype=np.int32)
+    elen = np.zeros((N, KP)); vor = np.zeros((N, KP))
+    offs = [(0, 1, dx, dx), (1, 1, dx * np.sqrt(2.0), 0.0), (1, 0, dx, dx), (1, -1, dx * np.sqrt(2.0), 0.0),
+            (0, -1, dx, dx), (-1, -1, dx * np.sqrt(2.0), 0.0), (-1, 0, dx, dx), (-1, 1, dx * np.sqrt(2.0), 0.0)]
+    J, I = np.meshgrid(np.arange(ny + 2), np.arange(nx + 2), indexing="ij")
+    ids = ext
+    cnt = np.zeros(N, dtype=np.int64)
+    ghost = np.zeros(N, dtype=bool); ghost[:nb] = True
+    for dj, di, dl, vl in offs:
+        jj, ii = J + dj, I + di
+        ok = (jj >= 0) & (jj < ny + 2) & (ii >= 0) & (ii < nx + 2)
+        src = ids[J[ok], I[ok]]; dst = ids[jj[ok], ii[ok]]
+        s = cnt[src]
+        ngb[src, s] = dst
+        gg = ghost[src] & ghost[dst]
+        elen[src, s] = np.where(gg, 0.0, dl)
+        vor[src, s] = np.where(gg, 0.0, vl)
+        cnt[src] += 1
+    area = np.full(N, dx * dx); area[:nb] = 0.0
+    area = area.astype(np.float32).astype(np.float64)
+    elen = elen.astype(np.float32).astype(np.float64)
+    vor = vor.astype(np.float32).astype(np.float64)
+    fv = FVmesh(node_coords=pts, neighbours=ngb, edge_length=elen, vor_edges=vor, control_volumes=area)
+    rg = RecGrid(regX=xs, regY=ys, regZ=z.T.copy(), resEdges=float(dx), areaDel=float(dx * dx), nx=nx, ny=ny,
+                 rnx=nx, rny=ny, boundsPt=nb, edgesPt=2 * nx + 2 * (ny - 2))
+    elev = np.full(N, -1.0e6)
+    elev[nb:] = z.ravel()
+    elev, parent = _boundary_elevation(elev, ngb, elen, nb, btype)
+    borders, borders2, inside = _masks(fv, rg)
+    # grid table: every (ny+2, nx+2) output cell is exactly a node
+    idx = np.zeros(((ny + 2) * (nx + 2), 3), dtype=np.int32)
+    idx[:, 0] = ext.ravel()
+    w = np.zeros((len(idx), 3)); w[:, 0] = np.inf
+    exact = np.ones(len(idx), dtype=np.int32)
+    return MeshArrays(recGrid=rg, FVmesh=fv, elevation=elev, parentIDs=parent.astype(np.int32), borders=borders,
+                      borders2=borders2, insideIDs=inside, btype=btype, grid_nx=nx + 2, grid_ny=ny + 2,
+                      grid_idx=idx, grid_w=w, grid_exact=exact,
+                      hillslope_min_edge2=float(np.amin(elen[elen > 0.0] ** 2)))

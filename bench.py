@@ -118,8 +118,9 @@ def run_reference(args):
     line = dict(impl="reference", metric="mcmc_forward_model_evals_per_sec", value=val, unit="evals/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=dt / args.steps * 1e3,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload="Examples/%s full blackBox+likelihood, T=%d a, N=%d TIN nodes" % (cfg, simtime, m.N),
-                            proposals_per_step=per_step),
+                config=dict(workload="Examples/%s full blackBox+likelihood, T=%d a, N=%d TIN nodes, G=%d grid cells"
+                                     % (cfg, simtime, m.N, m.grid_nx * m.grid_ny),
+                            proposals_per_step=per_step, parallelism="%d host processes" % ncores),
                 cpu_baseline=dict(value=val, unit="evals/s", cores=ncores, kind="port",
                                   sample="%d evaluations per step over %d processes, CPU oracle "
                                          "(reference itself cannot run: py2+gfortran+Triangle)" % (per_step, ncores)),

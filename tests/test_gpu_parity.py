@@ -156,3 +156,46 @@ def test_crater_generic_path_bit_exact(crater_fast, monkeypatch):
             om.streamflow(); om.sediment_flux(15000.0)
             for f in INT_FIELDS + FP_FIELDS:
                 assert np.array_equal(eng.field(f, b), getattr(om, f)), (step, b, f)
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+def test_synthetic_uplift_regular_grid_bit_exact(generic, monkeypatch):
+    """BASELINE config 5 in miniature: regular grid (D8 stencil as the neighbour list), noisy flat start, uplift
+    map applied every step (buildFlux.py:312-313), purely erosive (dep = 0), row-major numbering (deep Gauss-Seidel
+    dependency levels -> exercises the level schedule of the fill)."""
+    import os
+    from bayeslands_b200 import config, mesh, forcing
+    from bayeslands_b200.engine import Engine
+    from oracle import oracle
+    from conftest import ROOT
+    if generic:
+        monkeypatch.setenv("BL_FORCE_GENERIC", "1")
+    nx, ny, dx = (24, 18, 100.0) if not generic else (40, 28, 100.0)   # 58 / 94 Gauss-Seidel levels
+    rng = np.random.default_rng(1234)
+    z0 = 10.0 + rng.uniform(0, 1, (ny, nx))
+    m = mesh.build_regular(nx, ny, dx, z0, btype="fixed")
+    xml = str(np.load(os.path.join(ROOT, "data", "crater_fast.npz"))["xml"])
+    xml = xml.replace("<end>15000.</end>", "<end>200000.</end>").replace("<rend>15000.</rend>", "<rend>200000.</rend>")
+    xml = xml.replace("<display>5000.</display>", "<display>50000.</display>").replace("<fillmax>15.</fillmax>", "<dep>0</dep>")
+    xml = xml.replace("<caerial>2.e-2</caerial>", "<caerial>8.e-1</caerial>").replace("<cmarine>5.e-2</cmarine>", "<cmarine>1.</cmarine>")
+    inp = config.parse_xml(xml)
+    assert inp.depo == 0 and inp.fillmax == 200.0
+    X, Y = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    bump = 1e-3 * 200000.0 * np.sin(np.pi * X / (nx - 1)) * np.sin(np.pi * Y / (ny - 1))      # cumulative uplift (m)
+    disp = forcing.load_tecto_map(m, bump.T.ravel(order="F"), 0.0, 200000.0)
+    assert disp.shape == (m.N,) and disp.max() <= 1.0001e-3 and disp.min() >= 0.0
+    B = 3
+    rain = np.array([0.6, 1.5, 2.4]); erod = np.array([3.2e-6, 5e-6, 6.8e-6]); seeds = np.array([1, 2, 3], dtype=np.int64)
+    eng = Engine(m, inp, B, disp=disp)
+    eng.reset(rain, erod, seeds)
+    oms = [oracle.OracleModel(m, inp, seed=int(s), disp=disp) for s in seeds]
+    for b, om in enumerate(oms):
+        om.reset(rain[b], erod[b], seed=int(seeds[b]))
+    for step in range(8):
+        eng.step(200000.0)
+        sc = eng.scalars()
+        for b, om in enumerate(oms):
+            om.streamflow(); om.sediment_flux(200000.0)
+            for f in INT_FIELDS + FP_FIELDS:
+                assert np.array_equal(eng.field(f, b), getattr(om, f)), (step, b, f)
+            assert sc["tNow"][b] == om.tNow and sc["status"][b] == 0
