@@ -32,3 +32,25 @@ def likelihood_surface(mc: bayeslands_mcmc, rainlimits, erodlimits, n: int = 50,
             for a, b, c in zip(r, e, lik):
                 f.write("{0}\t{1}\t{2}\n".format(a, b, c))
     return rain, erod, lik.reshape(n, n), mse.reshape(n, n)
+
+
+def topo_generator(mc: bayeslands_mcmc, rain: float, erod: float, out_dir=None, final_noise: bool = True, seed=None):
+    """`bl_topogenr.topoGenerator` (reference: `bl_topogenr.py:102-220`): run the model at the chosen "true"
+    parameters, add Gaussian noise of variance `max * 0.01 + 0.5` to the final-time outputs (`:160-181`) and write
+    `data/final_elev.txt`, `final_erdp.txt`, `final_erdp_pts.txt`, `initial_elev.txt` (`%.5f`, `:187-217`).
+    Returns (final_elev, final_erdp, erdp_pts[nt, npts]) as written."""
+    sse, pts, elev, erdp = mc.blackBox_batch([rain], [erod], grids=True)
+    elev, erdp, pts = elev[0], erdp[0], pts[0].copy()
+    rs = np.random.RandomState(seed)
+    fe, fd = elev[-1].copy(), erdp[-1].copy()
+    if final_noise:
+        fe = fe + rs.normal(0, np.sqrt(abs(fe.max() * 0.01 + 0.5)), fe.size).reshape(fe.shape)
+        fd = fd + rs.normal(0, np.sqrt(abs(fd.max() * 0.01 + 0.5)), fd.size).reshape(fd.shape)
+        pts[-1] = pts[-1] + rs.normal(0, np.sqrt(abs(pts[-1].max() * 0.01 + 0.5)), pts[-1].size)
+    if out_dir:
+        os.makedirs(out_dir, exist_ok=True)
+        np.savetxt(os.path.join(out_dir, "initial_elev.txt"), elev[0], fmt="%.5f")
+        np.savetxt(os.path.join(out_dir, "final_elev.txt"), fe, fmt="%.5f")
+        np.savetxt(os.path.join(out_dir, "final_erdp.txt"), fd, fmt="%.5f")
+        np.savetxt(os.path.join(out_dir, "final_erdp_pts.txt"), pts, fmt="%.5f")
+    return fe, fd, pts

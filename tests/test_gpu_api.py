@@ -111,3 +111,42 @@ def test_model_mirror_load_xml_run_to_time(crater_fast):
     model.run_to_time(1e9, muted=True)          # clamped to the XML end (model.py:240-243)
     assert model.tNow == 15000.0
     assert model.FVmesh.node_coords.shape == (m.N, 2) and model.flow.receivers.shape == (m.N,)
+
+
+def test_likelihood_surface_argmax_matches_shipped_sweep(crater_fast, tmp_path):
+    """the 50 x 50 sweep of bl_surflikl over (rain, erod) - 2500 forward models - must put its
+    maximum on the shipped surface's ridge through (1.5, 5e-5) and follow the shipped surface's shape."""
+    from bayeslands_b200.surflikl import likelihood_surface
+    d, inp, m = crater_fast
+    mc = _mc(crater_fast, 500, likl_sed=False)
+    rain, erod, lik, mse = likelihood_surface(mc, [0.0, 3.0], [3.e-5, 7.e-5], n=50, out_dir=str(tmp_path))
+    i, j = np.unravel_index(np.argmax(lik), lik.shape)
+    ship = d["surf_false"]
+    si = int(np.argmax(ship[:, 2]))
+    ti, tj = divmod(si, 50)                              # shipped rows: rain outer loop, erod inner
+    assert np.isclose(ship[si, 0], rain[ti]) and np.isclose(ship[si, 1], erod[tj])
+    # The surface is a long ridge K * sqrt(rain) = const (incision ~ K (rain A)^m, m = 0.5): on a different mesh
+    # the maximum slides along it, so the invariant is the ridge, and the 1-D slices through the shipped truth.
+    ridge = erod[j] * np.sqrt(rain[i])
+    assert abs(ridge / (erod[tj] * np.sqrt(rain[ti])) - 1.0) < 0.05, (rain[i], erod[j])
+    assert abs(int(np.argmax(lik[ti, :])) - tj) <= 2 and abs(int(np.argmax(lik[:, tj])) - ti) <= 3
+    # rain = 0 row: no fluvial erosion, likelihood independent of erodibility
+    assert np.ptp(lik[0]) == 0.0
+    # same shape as the shipped sweep (different mesh => compare ranks, not values)
+    from scipy.stats import spearmanr
+    rho = spearmanr(lik.ravel(), ship[:, 2]).correlation
+    assert rho > 0.9, rho
+    rows = np.loadtxt(tmp_path / "exp_data.txt")
+    assert rows.shape == (2500, 3) and np.allclose(rows[:, 2], lik.ravel())
+
+
+def test_topo_generator_writes_reference_files(crater_fast, tmp_path):
+    from bayeslands_b200.surflikl import topo_generator
+    mc = _mc(crater_fast, 2)
+    fe, fd, pts = topo_generator(mc, 1.5, 5e-5, out_dir=str(tmp_path), seed=0)
+    assert fe.shape == (123, 123) and pts.shape == (5, 10) and np.all(pts[0] == 0)
+    back = np.loadtxt(tmp_path / "final_elev.txt")
+    assert back.shape == (123, 123) and np.abs(back - fe).max() < 1e-5
+    clean, _, _ = topo_generator(mc, 1.5, 5e-5, final_noise=False)
+    noise_var = np.var(fe - clean)
+    assert 0.8 * (clean.max() * 0.01 + 0.5) < noise_var < 1.2 * (clean.max() * 0.01 + 0.5)
