@@ -11,6 +11,7 @@ struct Smem {
     int lev_off[LEVMAX + 1];   // copy of c.lev_off: every CTA reads it every pass (one hot L2 line otherwise)
     int fl_head[LEVMAX + 1], fl_tail[LEVMAX + 1], fl_base[LEVMAX + 1], fl_mask[LEVMAX + 1];   // per-level worklist rings of the fill
     unsigned char *dsm;        // dynamic shared memory of the fast kernel (nullptr on the generic path)
+    unsigned short boff[2048]; // depth-bucket offsets of the tree passes (fast path)
     int dsm_bytes;
     int scan[NWARP + 1];
     double red[NWARP];
@@ -1033,7 +1034,6 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
     marine = __syncthreads_or(marine);
     if (c.depo != 0) {
         const int *isl = S.P.i[I_KIND];
-        const long long tland = clock64();
         const int nland = blk_compact(N, land, [&](int i) { return isl[i] == 1; }, S);
         // land pits (flowNetwork.py:750-763): members = where(pitID == p) in ascending id; the basin's nodes
         // are a contiguous segment of the real-surface stack.  Small basins: one thread gathers + sorts its
@@ -1089,9 +1089,7 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
         }
         for (int q = tid; q < nland; q += TPB) dep[land[q]] = 0.;
         __syncthreads();
-        if (tid == 0) c.phase_cyc[(size_t)blockIdx.x * NPHASE + 15] += clock64() - tland;
-        { long long tq = clock64(); if (marine) phase_marine_distribution(c, S, sea);     // flowNetwork.py:769-776
-          if (tid == 0) c.phase_cyc[(size_t)blockIdx.x * NPHASE + 14] += clock64() - tq; }
+        if (marine) phase_marine_distribution(c, S, sea);     // flowNetwork.py:769-776
         // forced deposition of anything left (flowNetwork.py:782-785)
         int any = 0;
         for (int k = tid; k < N; k += TPB) any |= (dep[k] != 0.);
@@ -1267,6 +1265,7 @@ bl_run_kernel(const DevConst cpar, int nstops, const double *__restrict__ stops,
     __syncthreads();
     const DevConst &c = S.c;
     for (int i = tid; i <= c.nlev && i <= LEVMAX; i += TPB) S.lev_off[i] = c.lev_off[i];
+    if (tid < 8) S.ibuf[tid] = 0;
     __syncthreads();
     double tNow = c.tnow[b];
     long long step = c.steps[b];

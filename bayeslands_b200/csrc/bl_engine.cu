@@ -285,7 +285,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
         }
     const int Nq = (int)rup((size_t)N, 64);
     int KDT = 0;
-    if (N < 32760 && nlev <= LEVMAX && (size_t)17 * Nq + 256 <= (size_t)DYN_SMEM) KDT = (KD <= 8) ? 8 : (KD <= 12 ? 12 : 20);
+    if (N < 32760 && nlev <= LEVMAX && (size_t)17 * Nq + Nq / 8 + 256 <= (size_t)DYN_SMEM) KDT = (KD <= 8) ? 8 : (KD <= 12 ? 12 : 20);
     if (getenv("BL_FORCE_GENERIC")) KDT = 0;
     const int KDrow = KDT ? KDT : BL_KP;
     std::vector<unsigned short> ngb16((size_t)BL_KP * Nq, 0xFFFFu);
@@ -416,7 +416,7 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
     CUDA_OK(cudaMemcpyAsync(ctx->d_ckpt, ck.data(), (size_t)nstops * 4, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaStreamSynchronize(st)); // ck is a stack vector
     // the fast path needs 17 bytes of shared memory per node: small meshes leave room for several CTAs per SM
-    size_t need = (size_t)17 * ctx->c.Nq + 256;
+    size_t need = (size_t)17 * ctx->c.Nq + ctx->c.Nq / 8 + 256;
     if (ctx->c.CDr > 0. || ctx->c.nsea > 0) need = std::max(need, (size_t)ctx->c.Nq * (25 + 2 * ctx->c.KDT) + 256);
     const int dyn = (int)std::min((size_t)DYN_SMEM, rup(need, 1024));
 #define LAUNCH(NS, T, K, DYN)                                                                                   \

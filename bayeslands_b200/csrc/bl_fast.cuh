@@ -59,6 +59,7 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
     unsigned char *lev8 = dsm + (size_t)12 * Nq + 128;                  // [Nq] level of each node
     unsigned *bits = (unsigned *)(dsm + (size_t)13 * Nq + 256);         // [Nq/32] "is pending"
     const double *z = S.P.f[F_Z];
+#pragma unroll 4
     for (int i = tid; i < N; i += TPB) W[i] = (i < nb) ? z[i] : 1.e6;
     for (int i = tid; i < Nq / 32; i += TPB) bits[i] = 0u;
     {   // ring i of level l lives at pend[fl_base[l] + (i & fl_mask[l])], capacity = level size rounded up to 2^k
@@ -145,17 +146,18 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
         }
         change = __syncthreads_or(loc);
     }
-    if (tid == 0) pcd[12] += nsweepd;                                   // diagnostics: sweeps
-    if (nevald) atomicAdd((unsigned long long *)&pcd[13], (unsigned long long)nevald);   // and node evaluations
+    (void)pcd; (void)nsweepd; (void)nevald;
     // stage z next to W for the receiver search
     double *zs = W + Nq;
     __syncthreads();
+#pragma unroll 4
     for (int i = tid; i < N; i += TPB) zs[i] = z[i];
     __syncthreads();
     // receivers on both surfaces
     int *rcv = S.P.i[I_RCV], *rcv1 = S.P.i[I_RCV1];
     double *maxh = S.P.f[F_MAXH], *fillH = S.P.f[F_FILLH];
     int mar = 0;
+#pragma unroll 2
     for (int g = tid; g < N; g += TPB) {
         Ids<KDT> ids;
         load_ids<KDT>(c, g, ids);
@@ -195,6 +197,7 @@ __device__ void links_stack(const DevConst &c, Smem &S, unsigned char *dsm, cons
     unsigned short *r16 = (unsigned short *)(dsm + (size_t)8 * Nq);  // [Nq]
     unsigned long long *K = (unsigned long long *)(dsm + (size_t)10 * Nq + 64 - ((size_t)10 * Nq) % 8);
     const int kcap = (int)(((size_t)17 * Nq - (size_t)10 * Nq - 128) / 8);
+#pragma unroll 4
     for (int v = tid; v < N; v += TPB) r16[v] = (unsigned short)rcvg[v];
     __syncthreads();
     unsigned short *lc16 = (unsigned short *)S.P.i[I_LC], *ps16 = (unsigned short *)S.P.i[I_PS];
@@ -290,6 +293,7 @@ __device__ void basins(const DevConst &c, Smem &S, unsigned char *dsm, const int
     const int *rcv1 = S.P.i[I_RCV1], *pos1 = S.P.i[I_POS1], *ns1 = S.P.i[I_NS];
     int *pitID = S.P.i[I_PITID];
     double *pitVol = S.P.f[F_PITVOL];
+#pragma unroll 4
     for (int v = tid; v < N; v += TPB) root16[v] = (unsigned short)rcv1[v];
     __syncthreads();
     int ch = 1;
@@ -301,6 +305,7 @@ __device__ void basins(const DevConst &c, Smem &S, unsigned char *dsm, const int
         }
         ch = __syncthreads_or(loc);
     }
+#pragma unroll 2
     for (int v = tid; v < N; v += TPB) {
         const double wv = W[v], zv = z[v];
         const bool wet = wv > zv;
@@ -406,8 +411,9 @@ __device__ void drainage(const DevConst &c, Smem &S, unsigned char *dsm, const i
 struct ScanSm {
     double *vals;
     unsigned short *lc, *ps, *r16;
-    unsigned *cntw;           // working donor counters, 4 per word
-    unsigned char *cnt0, *kind;
+    unsigned short *order;    // nodes sorted by depth in the receiver tree (deepest bucket last)
+    unsigned char *kind;
+    unsigned *evbits;         // lake-entry events by reverse stack position
 };
 __device__ inline ScanSm scan_layout(unsigned char *dsm, int Nq)
 {
@@ -416,57 +422,87 @@ __device__ inline ScanSm scan_layout(unsigned char *dsm, int Nq)
     s.lc = (unsigned short *)(dsm + (size_t)8 * Nq);
     s.ps = s.lc + Nq;
     s.r16 = s.ps + Nq;
-    s.cntw = (unsigned *)(dsm + (size_t)14 * Nq);
-    s.cnt0 = dsm + (size_t)15 * Nq;
+    s.order = (unsigned short *)(dsm + (size_t)14 * Nq);
     s.kind = dsm + (size_t)16 * Nq;
+    s.evbits = (unsigned *)(dsm + (size_t)17 * Nq);
     return s;
 }
-__device__ inline unsigned cnt_dec(unsigned *cntw, int v)   // returns the previous byte value
-{
-    const unsigned sh = 8u * (v & 3);
-    const unsigned old = atomicSub(&cntw[v >> 2], 1u << sh);
-    return (old >> sh) & 0xFFu;
-}
+constexpr int DEPMAX = 2040;   // bucket offsets kept in static shared memory up to this tree depth
 
-// FLOWalgo.f90:53-81 (see phase_discharge); leaves Q in sm.vals and in global F_Q
+// FLOWalgo.f90:53-81 (see phase_discharge); leaves Q in sm.vals and in global F_Q.
+// Ordered accumulation without atomics: nodes are bucketed by their depth in the receiver tree (pointer jumping
+// + counting sort); buckets are processed from the deepest to the roots with a barrier in between, so when a
+// node is evaluated all its donors (depth + 1) are final and it sums them in the fixed descending-id order.
+// The same buckets serve the sediment routing of streampower().
 __device__ void discharge(const DevConst &c, Smem &S, unsigned char *dsm, double rain)
 {
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     ScanSm sm = scan_layout(dsm, Nq);
     const unsigned short *lc16 = (const unsigned short *)S.P.i[I_LC], *ps16 = (const unsigned short *)S.P.i[I_PS];
-    const unsigned char *cnt8 = (const unsigned char *)S.P.i[I_CNT];
     const int *rcv = S.P.i[I_RCV];
-    for (int v = tid; v < N; v += TPB) {
-        sm.lc[v] = lc16[v]; sm.ps[v] = ps16[v]; sm.r16[v] = (unsigned short)rcv[v];
-        sm.cnt0[v] = cnt8[v];
-        sm.vals[v] = c.area[v] * ((v >= c.bounds) ? rain : 0.);
-    }
-    for (int v = tid; v < Nq / 4; v += TPB) sm.cntw[v] = ((const unsigned *)cnt8)[v];
+#pragma unroll 4
+    for (int v = tid; v < N; v += TPB) { sm.lc[v] = lc16[v]; sm.ps[v] = ps16[v]; sm.r16[v] = (unsigned short)rcv[v]; }
     __syncthreads();
-    volatile double *vals = sm.vals;
-    for (int v = tid; v < N; v += TPB) {
-        if (sm.cnt0[v] != 0) continue;
-        int cur = v;
-        double acc = vals[cur];                 // leaf: own value only
-        for (;;) {
-            const int r = sm.r16[cur];
-            if (r == cur) break;
-            if (sm.cnt0[r] == 1) {              // single donor: no counter, no fence - this thread owns the chain
-                acc = vals[r] + acc;
-                vals[r] = acc;
-                cur = r;
-                continue;
-            }
-            __threadfence_block();
-            if (cnt_dec(sm.cntw, r) != 1u) break;
-            cur = r;
-            acc = vals[cur];
-            for (unsigned d = sm.lc[cur]; d != NONE16; d = sm.ps[d]) acc = acc + vals[d];
-            vals[cur] = acc;
+    // depth(v) = hops to the root: (jump:16 | dist:16) words updated in place, as in links_stack
+    unsigned *jd = (unsigned *)sm.vals;                       // [Nq] scratch in the (not yet used) value array
+    int *hist = (int *)(jd + Nq);                             // [Nq] scratch
+    for (int v = tid; v < N; v += TPB) { const unsigned r = sm.r16[v]; jd[v] = (r << 16) | (r == (unsigned)v ? 0u : 1u); hist[v] = 0; }
+    __syncthreads();
+    int act = 1;
+    while (act) {
+        int loc = 0;
+        for (int v = tid; v < N; v += TPB) {
+            const unsigned w = jd[v], j = w >> 16;
+            const unsigned wj = jd[j];
+            if ((wj >> 16) != j) { jd[v] = (wj & 0xFFFF0000u) | ((w + wj) & 0xFFFFu); loc = 1; }
         }
+        act = __syncthreads_or(loc);
+    }
+    int md = 0;
+    for (int v = tid; v < N; v += TPB) { const int d = jd[v] & 0xFFFFu; md = max(md, d); atomicAdd(&hist[d], 1); }
+    md = __reduce_max_sync(0xffffffffu, md);
+    if ((tid & 31) == 0) atomicMax(&S.ibuf[2], md);
+    __syncthreads();
+    const int maxd = S.ibuf[2];
+    __syncthreads();
+    if (tid == 0) S.ibuf[2] = 0;
+    // exclusive scan of the histogram -> bucket offsets (static shared memory, or global scratch for very deep trees)
+    int *boffg = S.P.i[I_EVENTS];
+    const bool deep = (maxd + 2 > DEPMAX);
+    {
+        int carry = 0;
+        for (int base = 0; base <= maxd; base += TPB) {
+            const int d = base + tid;
+            const int h = (d <= maxd) ? hist[d] : 0;
+            int tot;
+            const int ex = blk_exscan(h, tot, S) + carry;
+            if (d <= maxd) { if (deep) boffg[d] = ex; else S.boff[d] = (unsigned short)ex; hist[d] = ex; }
+            carry += tot;
+        }
+        if (tid == 0) { if (deep) boffg[maxd + 1] = N; else S.boff[maxd + 1] = (unsigned short)N; }
+    }
+    __syncthreads();
+    for (int v = tid; v < N; v += TPB) { const int d = jd[v] & 0xFFFFu; sm.order[atomicAdd(&hist[d], 1)] = (unsigned short)v; }
+    __syncthreads();
+    if (tid == 0) S.ibuf[3] = maxd;
+#pragma unroll 4
+    for (int v = tid; v < N; v += TPB) sm.vals[v] = c.area[v] * ((v >= c.bounds) ? rain : 0.);
+    __syncthreads();
+    for (int d = maxd; d >= 0; --d) {
+        const int b0 = deep ? boffg[d] : S.boff[d], b1 = deep ? boffg[d + 1] : S.boff[d + 1];
+        for (int i = b0 + tid; i < b1; i += TPB) {
+            const int v = sm.order[i];
+            unsigned dn = sm.lc[v];
+            if (dn == NONE16) continue;
+            double acc = sm.vals[v];
+            for (; dn != NONE16; dn = sm.ps[dn]) acc = acc + sm.vals[dn];
+            sm.vals[v] = acc;
+        }
+        __syncthreads();
     }
     __syncthreads();
     double *Q = S.P.f[F_Q];
+#pragma unroll 4
     for (int v = tid; v < N; v += TPB) Q[v] = sm.vals[v];
 }
 
@@ -476,6 +512,7 @@ __device__ double flow_cfl(const DevConst &c, Smem &S, unsigned char *dsm, doubl
     ScanSm sm = scan_layout(dsm, Nq);
     const double *W = S.P.f[F_FILLH];
     double cfl = 1.e6;
+#pragma unroll 2
     for (int d = threadIdx.x; d < N; d += TPB) {
         const int r = sm.r16[d];
         const double q = sm.vals[d];
@@ -502,7 +539,11 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
     const double *z = S.P.f[F_Z], *W = S.P.f[F_FILLH], *Qg = S.P.f[F_Q], *maxhA = S.P.f[F_MAXH];
     const double *pitVol1 = S.P.f[F_PITVOL];
     double *depo = S.P.f[F_DEPO], *ero = S.P.f[F_ERO], *pdep = S.P.f[F_PDEP], *pitVol = S.P.f[F_PITVOLW];
+    long long *pcs = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
+    long long ts0 = clock64();
+#define STICK(i) do { if (tid == 0) { long long t1_ = clock64(); pcs[i] += t1_ - ts0; ts0 = t1_; } } while (0)
     // (1) per-node pre-pass
+#pragma unroll 2
     for (int d = tid; d < N; d += TPB) {
         const int r = sm.r16[d];
         const double zd = z[d], zr = z[r], fh = W[d], area = c.area[d];
@@ -549,78 +590,114 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
         depo[d] = 0.;
         ero[d] = 0.;
     }
-    for (int v = tid; v < Nq / 4; v += TPB) sm.cntw[v] = ((const unsigned *)sm.cnt0)[v];
+    for (int v = tid; v < Nq / 32; v += TPB) sm.evbits[v] = 0u;
+    const int *posg = S.P.i[I_POS];
     __syncthreads();
     // (2) ordered sediment routing
-    volatile double *vals = sm.vals;
-    for (int v = tid; v < N; v += TPB) {
-        if (sm.cnt0[v] != 0) continue;
-        int cur = v;
-        double acc = 0. * dt;                   // a leaf receives nothing
-        for (;;) {
-            const int k = sm.kind[cur];
-            const double own = vals[cur];
-            double Qs = 0., erodep = 0.;
-            if (k == 0) { erodep = own; Qs = -erodep + acc; }
-            else if (k == 1) { if (acc != 0.) { pdep[cur] = acc; sm.kind[cur] = 6; } }
-            else if (k == 2) { erodep = acc; }
-            else if (k == 3) {
-                const double area = c.area[cur];
-                const double totflx = 0. + acc, maxh = own;
-                if (totflx / area < maxh) erodep = acc;
-                else { const double frac = acc / totflx; erodep = frac * maxh * area; Qs = acc - erodep; }
-            } else if (k == 4) Qs = acc;
-            if (!(k == 1 && acc != 0.)) {
-                if (erodep < 0.) ero[cur] = 0. + erodep;
-                else if (erodep != 0.) depo[cur] = 0. + erodep;
+    {
+        // (2) ordered sediment routing over the depth buckets built by discharge()
+        const int maxd = S.ibuf[3];
+        const int *boffg = S.P.i[I_EVENTS];
+        const bool deep = (maxd + 2 > DEPMAX);
+        double *vals = sm.vals;
+        for (int d = maxd; d >= 0; --d) {
+            const int b0 = deep ? boffg[d] : S.boff[d], b1 = deep ? boffg[d + 1] : S.boff[d + 1];
+            for (int i = b0 + tid; i < b1; i += TPB) {
+                const int cur = sm.order[i];
+                double acc = 0. * dt;
+                for (unsigned dn = sm.lc[cur]; dn != NONE16; dn = sm.ps[dn]) acc = acc + vals[dn];
+                const int k = sm.kind[cur];
+                const double own = vals[cur];
+                double Qs = 0., erodep = 0.;
+                if (k == 0) { erodep = own; Qs = -erodep + acc; }
+                else if (k == 1) {
+                    if (acc != 0.) {
+                        pdep[cur] = acc;
+                        if (acc > 0.) { const int ri = N - 1 - posg[cur]; atomicOr(&sm.evbits[ri >> 5], 1u << (ri & 31)); }
+                    }
+                }
+                else if (k == 2) { erodep = acc; }
+                else if (k == 3) {
+                    const double area = c.area[cur];
+                    const double totflx = 0. + acc, maxh = own;
+                    if (totflx / area < maxh) erodep = acc;
+                    else { const double frac = acc / totflx; erodep = frac * maxh * area; Qs = acc - erodep; }
+                } else if (k == 4) Qs = acc;
+                if (!(k == 1 && acc != 0.)) {
+                    if (erodep < 0.) ero[cur] = 0. + erodep;
+                    else if (erodep != 0.) depo[cur] = 0. + erodep;
+                }
+                vals[cur] = Qs;
             }
-            vals[cur] = Qs;
-            const int r = sm.r16[cur];
-            if (r == cur) break;
-            if (sm.cnt0[r] == 1) {              // single donor: this thread carries the flux down the chain
-                acc = 0. * dt + Qs;
-                cur = r;
-                continue;
-            }
-            __threadfence_block();
-            if (cnt_dec(sm.cntw, r) != 1u) break;
-            cur = r;
-            acc = 0. * dt;
-            for (unsigned d = sm.lc[cur]; d != NONE16; d = sm.ps[d]) acc = acc + vals[d];
+            __syncthreads();
         }
     }
     __syncthreads();
-    // (3) lake-entry events in reverse stack order
-    const int nev = blk_compact(N, events, [&](int i) { const int v = stack[N - 1 - i]; return sm.kind[v] == 6 && pdep[v] > 0.; }, S);
+    STICK(1);   // prepass + scan
+    // (3) lake-entry events in reverse stack order: compact the bitmap, stage (pit, load, donor) per event in the
+    // shared-memory regions the routing no longer needs (vals -> loads, lc -> pits, ps -> donors)
+    double *ev_dep = sm.vals;
+    unsigned short *ev_pit = sm.lc, *ev_donor = sm.ps;
+    int nev;
+    {
+        const int nw = (N + 31) >> 5;
+        int wcount[4], tot_mine = 0;         // up to 4 bitmap words per thread (N <= 32768 -> 1024 words)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int wi = tid * 4 + u;
+            wcount[u] = (wi < nw && tid * 4 < TPB * 4) ? __popc(sm.evbits[wi]) : 0;
+            tot_mine += wcount[u];
+        }
+        const int off0 = blk_exscan(tot_mine, nev, S);
+        unsigned words[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int wi = tid * 4 + u; words[u] = (wi < nw) ? sm.evbits[wi] : 0u; }
+        __syncthreads();                     // every thread has its words: vals / lc / ps may be overwritten now
+        int off = off0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            unsigned wbits = words[u];
+            while (wbits) {
+                const int bit = __ffs(wbits) - 1;
+                wbits &= wbits - 1;
+                ev_donor[off++] = (unsigned short)((tid * 4 + u) * 32 + bit);     // reverse stack index for now
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nev; e += TPB) {       // one event per thread: the dependent global lookups run in parallel
+        const int donor = stack[N - 1 - ev_donor[e]];
+        const int pit = pitID[donor];
+        const bool ok = (pit >= 0 && c.area[pit] > 0.);
+        ev_pit[e] = ok ? (unsigned short)pit : NONE16;
+        ev_donor[e] = (unsigned short)donor;
+        ev_dep[e] = pdep[donor];
+    }
+    __syncthreads();
+    STICK(12);  // event compaction
     if (nev == 0) return;
     // parallel replay: when no event overflows its own pit (the usual case) events of different pits are
     // independent and events of one pit are applied in order by one thread -> same sums as the serial loop
     int over = 0;
-    int *evpit = S.P.i[I_MEMB];
-    for (int e = tid; e < nev; e += TPB) {
-        const int donor = stack[N - 1 - events[e]];
-        const int pit = pitID[donor];
-        const bool ok = (pit >= 0 && c.area[pit] > 0.);
-        evpit[e] = ok ? pit : -1;
-        if (ok && W[pit] < sea) over = 1;
-    }
-    __syncthreads();
+    if (S.ibuf[1])      // some node lies under the sea: an event whose pit is submerged needs the serial path
+        for (int e = tid; e < nev; e += TPB) { const int pit = ev_pit[e]; if (pit != NONE16 && W[pit] < sea) over = 1; }
     for (int i = tid; i < nbase1; i += TPB) {
         const int pit = base1[i];
         double dp = depo[pit];
-        const double vol = pitVol1[pit];
-        bool touched = false;
+        bool any = false;
+        double vol = 0.;
         for (int e = 0; e < nev; ++e) {
-            if (evpit[e] != pit) continue;
-            const double pitDep = pdep[stack[N - 1 - events[e]]];
+            if (ev_pit[e] != pit) continue;
+            if (!any) { vol = pitVol1[pit]; any = true; }
+            const double pitDep = ev_dep[e];
             const double totdist = 0. + pitDep, tmpdist = 0. + dp;
-            if (tmpdist + totdist <= vol || pitDrain[pit] == pit) { dp = dp + pitDep; touched = true; }
+            if (tmpdist + totdist <= vol || pitDrain[pit] == pit) dp = dp + pitDep;
             else { over = 1; break; }
         }
         S.P.f[F_VAL][pit] = dp;   // staged, committed below when no event overflowed
-        (void)touched;
     }
     over = __syncthreads_or(over);
+    STICK(13);  // parallel replay
     if (!over) {
         for (int i = tid; i < nbase1; i += TPB) { const int pit = base1[i]; depo[pit] = S.P.f[F_VAL][pit]; }
         __syncthreads();
@@ -633,12 +710,12 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
     if (tid == 0) {
         unsigned st = 0;
         for (int e = 0; e < nev; ++e) {
-            const int donor = stack[N - 1 - events[e]];
+            if (ev_pit[e] == NONE16) continue;
+            const int donor = ev_donor[e];
             const int recvr = sm.r16[donor];
-            double pitDep = pdep[donor];
+            double pitDep = ev_dep[e];
             double totdist = 0. + pitDep;
-            if (!(pitID[donor] >= 0 && c.area[pitID[donor]] > 0.)) continue;
-            int tmpID = pitID[donor], nID = tmpID;
+            int tmpID = ev_pit[e], nID = tmpID;
             long guard = 0;
             while (totdist > 0.) {
                 if (++guard > 1000000 || tmpID < 0) { st |= BL_ST_CASCADE_GUARD; break; }
@@ -673,7 +750,9 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
         if (st) atomicOr(&c.status[blockIdx.x], st);
     }
     __syncthreads();
+    STICK(14);  // serial replay
     if (S.ibuf[0]) phase_streampower_serial(c, S, erod, sea, dt);
+#undef STICK
 }
 
 // buildFlux.py:193-195, :252-272, :292-315 (see phase_apply) with z staged in shared memory for the gather
@@ -697,6 +776,7 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
         }
     }
     __syncthreads();
+#pragma unroll 2
     for (int g = tid; g < N; g += TPB) {
         double acc = 0.;
         const unsigned char fg = c.flags[g];
@@ -756,6 +836,7 @@ __device__ void time_step(const DevConst &c, Smem &S, unsigned char *dsm, double
 #define TICK(i) do { if (tid == 0) { long long t1_ = clock64(); pc[i] += t1_ - t0; t0 = t1_; } } while (0)
     int any_marine;
     fill_sfd<KDT>(c, S, dsm, sea, any_marine);
+    if (tid == 0) S.ibuf[1] = any_marine;
     TICK(0);
     int nbase1, nbase;
     links_stack<KDT>(c, S, dsm, S.P.i[I_RCV1], S.P.i[I_STACK1], S.P.i[I_POS1], S.P.i[I_LA], nbase1, false, false, 0ull);

@@ -28,7 +28,6 @@ print("config", cfg, "B", B, "wall ms", dt * 1e3, "mean steps", steps.mean())
 print("mean cycles/step per phase:")
 for i, nm in enumerate(_lib.PHASES):
     print("  %-12s %10.0f cyc  %5.1f%%" % (nm, (pc[:, i] / steps).mean(), 100 * pc[:, i].sum() / tot.sum()))
-print("  diag: fill sweeps/step %.1f node evaluations/step %.0f" % ((pc[:,12]/steps).mean(), (pc[:,13]/steps).mean()))
-print("  diag: erodep land-pit part %.0f cyc/step, marine_distribution %.0f cyc/step" % ((pc[:,15]/steps).mean(), (pc[:,14]/steps).mean()))
+print("  diag streampower split (cyc/step): prepass+scan %.0f, event compaction %.0f, parallel replay %.0f, serial replay %.0f" % tuple((pc[:,i]/steps).mean() for i in (1,12,13,14)))
 tot = pc[:, :12].sum(1)
 print("  total        %10.0f cyc/step  (%.1f us at 1.965 GHz)" % ((tot / steps).mean(), (tot / steps).mean() / 1965.0))
