@@ -12,6 +12,10 @@ struct Smem {
     int fl_head[LEVMAX + 1], fl_tail[LEVMAX + 1], fl_base[LEVMAX + 1], fl_mask[LEVMAX + 1];   // per-level worklist rings of the fill
     unsigned char *dsm;        // dynamic shared memory of the fast kernel (nullptr on the generic path)
     unsigned short boff[2048]; // depth-bucket offsets of the tree passes (fast path)
+    static constexpr int FB_WORDS = (NWARP >= 4) ? 128 : 32 * NWARP;   // fill: bitmap words compacted per round
+    unsigned fb_word[FB_WORDS];
+    unsigned short fb_pre[FB_WORDS];
+    int fb_tot[FB_WORDS / 32];
     int dsm_bytes;
     int scan[NWARP + 1];
     double red[NWARP];

@@ -139,6 +139,7 @@ struct bl_ctx {
     int *d_ckpt;
     int stops_cap;
     long long launches;
+    size_t const_bytes;   // mesh constants at the start of the workspace (kept L2-persistent)
 };
 
 #define CUDA_OK(x)                                                                      \
@@ -377,6 +378,14 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     ctx->d_ckpt = (int *)(ws + L.off_ckpt);
     ctx->stops_cap = STOPS_CAP;
     ctx->launches = 0;
+    ctx->const_bytes = L.off_rain;
+    {   // the mesh constants are read by every CTA all the time while ~3.5 MB of per-proposal scratch per CTA streams
+        // through L2: pin them (persisting L2 carve-out + access-policy window set per launch)
+        int maxp = 0;
+        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, device);
+        if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)maxp, rup(ctx->const_bytes, 1 << 20)));
+        cudaGetLastError();
+    }
     CUDA_OK(cudaMemset(ws + L.off_rain, 0, L.off_stops - L.off_rain));
     *out = ctx;
     return BL_OK;
@@ -415,6 +424,17 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
     CUDA_OK(cudaMemcpyAsync(ctx->d_stops, stops, (size_t)nstops * 8, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(ctx->d_ckpt, ck.data(), (size_t)nstops * 4, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaStreamSynchronize(st)); // ck is a stack vector
+    if (!getenv("BL_NO_L2_PERSIST")) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.base_ptr = ctx->ws;
+        av.accessPolicyWindow.num_bytes = ctx->const_bytes;
+        av.accessPolicyWindow.hitRatio = 1.0f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
     // the fast path needs 17 bytes of shared memory per node: small meshes leave room for several CTAs per SM
     size_t need = (size_t)17 * ctx->c.Nq + ctx->c.Nq / 8 + 256;
     if (ctx->c.CDr > 0. || ctx->c.nsea > 0) need = std::max(need, (size_t)ctx->c.Nq * (25 + 2 * ctx->c.KDT) + 256);

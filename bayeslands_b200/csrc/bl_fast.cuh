@@ -41,6 +41,161 @@ __device__ __forceinline__ void none_ids(Ids<KDT> &ids)
     for (int q = 0; q < KDT / 2; ++q) ids.w[q] = 0xFFFFFFFFu;
 }
 
+// sfd.c:55-153 on W / z held in shared memory ([Nq] each at the start of dsm): receivers on both surfaces
+template <int KDT>
+__device__ void fill_receivers(const DevConst &c, Smem &S, unsigned char *dsm, double sea, int &any_marine)
+{
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    double *W = (double *)dsm, *zs = W + Nq;
+    // receivers on both surfaces
+    int *rcv = S.P.i[I_RCV], *rcv1 = S.P.i[I_RCV1];
+    double *maxh = S.P.f[F_MAXH], *fillH = S.P.f[F_FILLH];
+    int mar = 0;
+#pragma unroll 2
+    for (int g = tid; g < N; g += TPB) {
+        Ids<KDT> ids;
+        load_ids<KDT>(c, g, ids);
+        const double zg = zs[g], wg = W[g];
+        int low1 = g, low = g;
+        double zl = zg, wl = wg, dH = 1.e6;
+#pragma unroll
+        for (int p = 0; p < KDT; ++p) {
+            if (ids.get(p) == NONE16) continue;
+            const int j = ids.get(p);
+            const double zj = zs[j], wj = W[j];
+            if (zj < zl) { low1 = j; zl = zj; }
+            if (wj < wl) { low = j; wl = wj; }
+            const double dh = zj - zg;
+            if (dh >= 0. && dh < dH) dH = dh;
+        }
+        rcv1[g] = low1;
+        rcv[g] = low;
+        if (dH > 9.99e5) dH = 0.;
+        maxh[g] = dH;
+        fillH[g] = wg;
+        mar |= (wg < sea);
+    }
+    any_marine = __syncthreads_or(mar);
+}
+
+// ---- depression filling, bitmap worklists (levels contiguous in node id) -------------------------------
+// Same literal Gauss-Seidel sweep as below, for meshes whose level-l nodes are the id range
+// [bounds + lev_off[l], bounds + lev_off[l+1]) (mesh.py numbers them so).  The pending set is one bit per node;
+// a changed node just ORs its neighbours' bits (no lists, no level lookup).  At a level's turn the level's
+// bitmap words are compacted block-wide (popc + prefix sums) and thread t evaluates the t-th pending node, so
+// the work of a spatially clustered front is spread over all warps.  W and z both stay in shared memory; the only
+// global access in the sweep is the node's packed neighbour ids.
+template <int KDT>
+__device__ void fill_bitmap(const DevConst &c, Smem &S, unsigned char *dsm, double sea)
+{
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x, nb = c.bounds;
+    const int lane = tid & 31, warp = tid >> 5;
+    double *W = (double *)dsm, *zs = W + Nq;
+    unsigned *bits = (unsigned *)(zs + Nq);                   // [Nq/32 + 1]
+    const double *z = S.P.f[F_Z];
+    for (int i = tid; i < N; i += TPB) { const double zi = z[i]; zs[i] = zi; W[i] = (i < nb) ? zi : 1.e6; }
+    for (int i = tid; i <= Nq / 32; i += TPB) {               // every interior node starts pending
+        const int lo = i * 32;
+        unsigned m = 0xFFFFFFFFu;
+        if (lo + 32 <= nb || lo >= N) m = 0u;
+        else {
+            if (lo < nb) m &= ~((1u << (nb - lo)) - 1u);
+            if (lo + 32 > N) m &= (1u << (N - lo)) - 1u;
+        }
+        bits[i] = m;
+    }
+    __syncthreads();
+    const double eps = c.eps, TH = c.TH;
+    constexpr int CHW = Smem::FB_WORDS;                        // bitmap words compacted per round
+    int change = 1;
+    while (change) {
+        int loc = 0;
+        for (int l = 0; l < c.nlev; ++l) {
+            const int n0 = nb + S.lev_off[l], n1 = nb + S.lev_off[l + 1];     // node id range of the level
+            const int wf = n0 >> 5, wl = (n1 - 1) >> 5;
+            for (int wbase = wf; wbase <= wl; wbase += CHW) {
+                // (a) warps 0..CHW/32-1: one word per lane -> count, prefix within the warp, consume the bits
+                if (warp < CHW / 32) {
+                    const int wi = wbase + tid;
+                    unsigned word = 0u;
+                    if (wi <= wl) {
+                        const int lo = wi * 32;
+                        unsigned m = 0xFFFFFFFFu;
+                        if (lo < n0) m &= ~((1u << (n0 - lo)) - 1u);
+                        if (lo + 32 > n1) m &= (1u << (n1 - lo)) - 1u;
+                        word = bits[wi] & m;
+                        if (word) atomicAnd(&bits[wi], ~word);
+                    }
+                    int inc = __popc(word);
+                    const int cnt = inc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                    S.fb_word[tid] = word;
+                    S.fb_pre[tid] = (unsigned short)(inc - cnt);
+                    if (lane == 31) S.fb_tot[warp] = inc;
+                }
+                __syncthreads();
+                // (b) thread t takes the t-th pending node of the round
+                int tot = 0, cum[CHW / 32];
+#pragma unroll
+                for (int q = 0; q < CHW / 32; ++q) { cum[q] = tot; tot += S.fb_tot[q]; }
+                for (int t = tid; t < tot; t += TPB) {
+                    int q = 0;
+#pragma unroll
+                    for (int u = 1; u < CHW / 32; ++u) if (t >= cum[u]) q = u;
+                    int r = t - cum[q];
+                    int lo_ = q * 32, hi_ = lo_ + 31;          // last word of the group with prefix <= r
+                    while (lo_ < hi_) { const int mid = (lo_ + hi_ + 1) >> 1; if ((int)S.fb_pre[mid] <= r) lo_ = mid; else hi_ = mid - 1; }
+                    r -= S.fb_pre[lo_];
+                    unsigned w = S.fb_word[lo_];
+                    int posb = 0;
+#pragma unroll
+                    for (int h = 16; h >= 1; h >>= 1) {
+                        const unsigned lowmask = (1u << h) - 1u;
+                        const int cl = __popc(w & lowmask);
+                        if (r >= cl) { r -= cl; w >>= h; posb += h; } else w &= lowmask;
+                    }
+                    const int k = (wbase + lo_) * 32 + posb;
+                    const double wk = W[k], zk = zs[k];
+                    if (!(wk > zk)) continue;
+                    Ids<KDT> ids;
+                    load_ids<KDT>(c, k, ids);
+                    double hm[KDT];
+#pragma unroll
+                    for (int p = 0; p < KDT; ++p) hm[p] = (ids.get(p) != NONE16) ? W[ids.get(p)] : 2.e6;
+                    double hmin;
+                    if (KDT == 8) {      // min is exact: any association gives the same bits
+                        hmin = fmin(fmin(fmin(hm[0], hm[1]), fmin(hm[2], hm[3])), fmin(fmin(hm[4], hm[5]), fmin(hm[6], hm[7])));
+                    } else {
+                        hmin = 2.e6;
+#pragma unroll
+                        for (int p = 0; p < KDT; ++p) hmin = fmin(hmin, hm[p]);
+                    }
+                    hmin = fmin(hmin, 2.e6);
+                    const double he = hmin + eps;
+                    double nw = wk;
+                    if (zk >= he) nw = zk;
+                    else if (wk > he) {
+                        nw = he;
+                        if (zk >= sea) { if (nw - zk > TH) nw = zk + TH; else loc = 1; }
+                        else           { if (nw - sea > TH) nw = sea + TH; else loc = 1; }
+                    }
+                    if (nw != wk) {
+                        W[k] = nw;
+#pragma unroll
+                        for (int p = 0; p < KDT; ++p) {
+                            const unsigned j = ids.get(p);
+                            if (j != NONE16 && (int)j >= nb) atomicOr(&bits[j >> 5], 1u << (j & 31));
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        change = __syncthreads_or(loc);
+    }
+}
+
 // ---- depression filling + receivers ---------------------------------------------------------------
 // PDalgo.f90:19-91 with the literal sweep semantics of phase_fill.  A node is re-evaluated only when one of
 // its neighbours changed since its last evaluation (re-evaluating it otherwise is a no-op: after an
@@ -54,6 +209,7 @@ template <int KDT>
 __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double sea, int &any_marine)
 {
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x, nb = c.bounds;
+    if (c.lev_contig) { fill_bitmap<KDT>(c, S, dsm, sea); fill_receivers<KDT>(c, S, dsm, sea, any_marine); return; }
     double *W = (double *)dsm;                                          // [Nq]
     unsigned short *pend = (unsigned short *)(dsm + (size_t)8 * Nq);    // [<2Nq] one power-of-two ring per level
     unsigned char *lev8 = dsm + (size_t)12 * Nq + 128;                  // [Nq] level of each node
@@ -137,6 +293,7 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
                             const int lj = lev8[j];
                             const int t = atomicAdd(&S.fl_tail[lj], 1);
                             pend[S.fl_base[lj] + (t & S.fl_mask[lj])] = (unsigned short)j;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(z + j));      // z(j) is read at j's next turn
                         }
                     }
                 }
@@ -153,35 +310,7 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
 #pragma unroll 4
     for (int i = tid; i < N; i += TPB) zs[i] = z[i];
     __syncthreads();
-    // receivers on both surfaces
-    int *rcv = S.P.i[I_RCV], *rcv1 = S.P.i[I_RCV1];
-    double *maxh = S.P.f[F_MAXH], *fillH = S.P.f[F_FILLH];
-    int mar = 0;
-#pragma unroll 2
-    for (int g = tid; g < N; g += TPB) {
-        Ids<KDT> ids;
-        load_ids<KDT>(c, g, ids);
-        const double zg = zs[g], wg = W[g];
-        int low1 = g, low = g;
-        double zl = zg, wl = wg, dH = 1.e6;
-#pragma unroll
-        for (int p = 0; p < KDT; ++p) {
-            if (ids.get(p) == NONE16) continue;
-            const int j = ids.get(p);
-            const double zj = zs[j], wj = W[j];
-            if (zj < zl) { low1 = j; zl = zj; }
-            if (wj < wl) { low = j; wl = wj; }
-            const double dh = zj - zg;
-            if (dh >= 0. && dh < dH) dH = dh;
-        }
-        rcv1[g] = low1;
-        rcv[g] = low;
-        if (dH > 9.99e5) dH = 0.;
-        maxh[g] = dH;
-        fillH[g] = wg;
-        mar |= (wg < sea);
-    }
-    any_marine = __syncthreads_or(mar);
+    fill_receivers<KDT>(c, S, dsm, sea, any_marine);
 }
 
 // ---- stack order ----------------------------------------------------------------------------------
@@ -633,7 +762,7 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
         }
     }
     __syncthreads();
-    STICK(1);   // prepass + scan
+    STICK(15);  // prepass + routing
     // (3) lake-entry events in reverse stack order: compact the bitmap, stage (pit, load, donor) per event in the
     // shared-memory regions the routing no longer needs (vals -> loads, lc -> pits, ps -> donors)
     double *ev_dep = sm.vals;

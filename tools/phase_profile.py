@@ -28,6 +28,6 @@ print("config", cfg, "B", B, "wall ms", dt * 1e3, "mean steps", steps.mean())
 print("mean cycles/step per phase:")
 for i, nm in enumerate(_lib.PHASES):
     print("  %-12s %10.0f cyc  %5.1f%%" % (nm, (pc[:, i] / steps).mean(), 100 * pc[:, i].sum() / tot.sum()))
-print("  diag streampower split (cyc/step): prepass+scan %.0f, event compaction %.0f, parallel replay %.0f, serial replay %.0f" % tuple((pc[:,i]/steps).mean() for i in (1,12,13,14)))
+print("  diag streampower split (cyc/step): prepass+scan %.0f, event compaction %.0f, parallel replay %.0f, serial replay %.0f" % tuple((pc[:,i]/steps).mean() for i in (15,12,13,14)))
 tot = pc[:, :12].sum(1)
 print("  total        %10.0f cyc/step  (%.1f us at 1.965 GHz)" % ((tot / steps).mean(), (tot / steps).mean() / 1965.0))
