@@ -267,6 +267,15 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg_bytes / (kernel_ms[-1] * 1e-3) / 1e9
+        # DRAM traffic of this launch, scaled from the committed ncu --set full capture (bytes per node-step there
+        # times the node-steps of this launch); null when the capture is for another config
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if cfg == "crater" and tj.get("N") == m.N:
+                traffic = float(tj["dram_bytes_per_node_step"] * np.sum(steps_last) * m.N)
+        except Exception:
+            pass
         cpu = cpu_baseline(cfg) if world == 1 and not args.no_cpu else None
         line = dict(metric="mcmc_forward_model_evals_per_sec", value=value, unit="evals/s", n_gpus=world,
                     steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
@@ -280,7 +289,7 @@ def run_ours(args):
                     e2e=dict(value=e2e_val, unit="evals/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=int(launches),
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                                  traffic=None, kernel="bl_run_kernel", kernel_ms=kernel_ms[-1],
+                                  traffic=traffic, kernel="bl_run_kernel", kernel_ms=kernel_ms[-1],
                                   peak_source="MEASURED_PEAKS.json" if peaks else "fallback",
                                   share_of_step=sum(kernel_ms) / ms),
                     clocks=clocks)
