@@ -739,6 +739,87 @@ __device__ double pairwise_sum(const double *a, int n)
     return vstk[0];
 }
 
+// ordered compaction of a bitmap: out[] receives the indices of the set bits of bm[0 .. nbits) in ascending order
+__device__ inline int blk_compact_bits(const unsigned *bm, int nbits, int *out, Smem &S)
+{
+    const int nw = (nbits + 31) >> 5;
+    const int wpt = (nw + TPB - 1) / TPB;
+    const int w0 = min(nw, (int)threadIdx.x * wpt), w1 = min(nw, w0 + wpt);
+    int cnt = 0;
+    for (int w = w0; w < w1; ++w) cnt += __popc(bm[w]);
+    int total;
+    int off = blk_exscan(cnt, total, S);
+    for (int w = w0; w < w1; ++w) {
+        unsigned bits = bm[w];
+        while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; out[off++] = w * 32 + b; }
+    }
+    __syncthreads();
+    return total;
+}
+
+// numpy's pairwise summation (see pairwise_sum) evaluated by the whole block: thread 0 lists the <= 128-element
+// leaf blocks of the recursion, one thread sums each leaf with numpy's 8-accumulator loop, thread 0 folds the
+// leaf sums back up the same recursion tree.  Bit-identical to the serial routine; result returned to all threads.
+__device__ inline double pw_leaf(const double *a, int m)
+{
+    double res;
+    if (m < 8) {
+        res = 0.;
+        for (int i = 0; i < m; ++i) res += a[i];
+    } else {
+        double r[8];
+        int i;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = a[k];
+        for (i = 8; i < m - (m % 8); i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+        }
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < m; ++i) res += a[i];
+    }
+    return res;
+}
+__device__ double blk_pairwise_sum(const double *a, int n, Smem &S, int *loff, int *llen, double *lsum)
+{
+    if (threadIdx.x == 0) {
+        int ostk[40], nstk[40], sp = 0, nl = 0;
+        ostk[0] = 0; nstk[0] = n; sp = 1;
+        while (sp > 0) {                       // leaves left to right
+            const int o = ostk[sp - 1], m = nstk[sp - 1];
+            --sp;
+            if (m <= 128) { loff[nl] = o; llen[nl] = m; ++nl; }
+            else {
+                int n2 = m / 2;
+                n2 -= n2 % 8;
+                ostk[sp] = o + n2; nstk[sp] = m - n2; ++sp;     // right pushed first, left popped first
+                ostk[sp] = o; nstk[sp] = n2; ++sp;
+            }
+        }
+        S.ibuf[4] = nl;
+    }
+    __syncthreads();
+    const int nl = S.ibuf[4];
+    for (int t = threadIdx.x; t < nl; t += TPB) lsum[t] = pw_leaf(a + loff[t], llen[t]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // post-order fold: same recursion, consuming the leaf sums in order
+        double vstk[40];
+        int nstk[40], sstk[40], sp = 0, vp = 0, li = 0;
+        nstk[0] = n; sstk[0] = 0; sp = 1;
+        while (sp > 0) {
+            const int m = nstk[sp - 1], st = sstk[sp - 1];
+            if (m <= 128) { vstk[vp++] = lsum[li++]; --sp; }
+            else if (st == 0) { int n2 = m / 2; n2 -= n2 % 8; sstk[sp - 1] = 1; nstk[sp] = n2; sstk[sp] = 0; ++sp; }
+            else if (st == 1) { int n2 = m / 2; n2 -= n2 % 8; sstk[sp - 1] = 2; nstk[sp] = m - n2; sstk[sp] = 0; ++sp; }
+            else { const double b = vstk[--vp], a0 = vstk[--vp]; vstk[vp++] = a0 + b; --sp; }
+        }
+        S.dbuf[1] = vstk[0];
+    }
+    __syncthreads();
+    return S.dbuf[1];
+}
+
 // PDalgo.f90:136-269 marine_distribution (single rock): a strictly sequential "drop the sediment, spill what does
 // not fit to the lowest neighbour" walk over the marine deposit nodes, diffnb passes, elevation updated in
 // place.  Kept literal on one thread per proposal (parallelism is across proposals); the per-pass reset of the
@@ -1077,7 +1158,16 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
             const int nr = ns1[pit];
             const int hi = (nr != NONE_I) ? pos1[nr] : N;
             if (hi - lo <= SMALL) continue;
-            const int nm = blk_compact(N, memb, [&](int i) { return pitID[i] == pit; }, S);
+            // members in ascending id: mark them (they all lie in the basin's stack segment), compact the bitmap
+            unsigned *bm = (unsigned *)S.P.i[I_MARK];
+            for (int w = tid; w < (N + 31) / 32; w += TPB) bm[w] = 0u;
+            __syncthreads();
+            for (int i = lo + tid; i < hi; i += TPB) {
+                const int v = stack1[i];
+                if (pitID[v] == pit) atomicOr(&bm[v >> 5], 1u << (v & 31));
+            }
+            __syncthreads();
+            const int nm = blk_compact_bits(bm, N, memb, S);
             for (int i = tid; i < nm; i += TPB) {
                 const int v = memb[i];
                 const double dd = (W[v] - z[v]) * 1.0;
@@ -1085,7 +1175,8 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
                 tmpv[i] = dd * c.area[v];
             }
             __syncthreads();
-            if (tid == 0) S.dbuf[0] = (0. + dep[pit]) / pairwise_sum(tmpv, nm);
+            const double tmpd = blk_pairwise_sum(tmpv, nm, S, S.P.i[I_EVENTS], S.P.i[I_SUCC], S.P.f[F_CAPH]);
+            if (tid == 0) S.dbuf[0] = (0. + dep[pit]) / tmpd;
             __syncthreads();
             const double dfrac = S.dbuf[0];
             for (int i = tid; i < nm; i += TPB) dth[memb[i]] *= dfrac;

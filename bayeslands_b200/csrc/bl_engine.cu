@@ -40,6 +40,7 @@ struct DevConst {
     const int *ngb;             // [KD][N]
     const unsigned short *ngb16; // [N][KDT] node-major u16 copy for the shared-memory path (0xFFFF = none)
     int Nq, KDT;                // N rounded up to 64; rows of ngb16
+    const float *ve32;          // [N][KDT][2] (vor, edge) as float pairs when both are float32-representable, else null
     int lev_contig;             // lev_nodes[i] == bounds + i (colour-major numbering)
     int dbg;                    // BL_DEBUG experiments (timing only)
     const double *vor, *edge;   // [KD][N]
@@ -156,7 +157,7 @@ extern "C" int bl_version(void) { return 100; }
 
 namespace {
 struct Layout {
-    size_t off_ngb16, off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
+    size_t off_ve32, off_ngb16, off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
         off_levo, off_gidx, off_gw, off_gex, off_real, off_pts, off_seat, off_seav, off_rain, off_erod, off_seed,
         off_tnow, off_lastdt, off_steps, off_status, off_phase, off_stops, off_ckpt, off_prop, total;
     int KD, nlev;
@@ -183,6 +184,7 @@ Layout make_layout(const bl_mesh *m, const bl_params *p, int B, int KD, int nlev
     auto take = [&](size_t bytes) { size_t r = o; o = rup(o + bytes, 256); return r; };
     L.off_ngb = take((size_t)KD * N * 4);
     L.off_ngb16 = take((size_t)BL_KP * rup(N, 64) * 2);
+    L.off_ve32 = take((size_t)BL_KP * rup(N, 64) * 8);
     L.off_vor = take((size_t)KD * N * 8);
     L.off_edge = take((size_t)KD * N * 8);
     L.off_area = take(N * 8);
@@ -296,6 +298,16 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
             if (j < 0) break;
             ngb16[(size_t)i * KDrow + q] = (unsigned short)j;
         }
+    std::vector<float> ve32((size_t)BL_KP * Nq * 2, 0.f);
+    bool ve_ok = KDT > 0;
+    for (int i = 0; i < N && ve_ok; ++i)
+        for (int q = 0; q < KD; ++q) {
+            if (m->ngb[(size_t)i * BL_KP + q] < 0) break;
+            const double v = m->vor[(size_t)i * BL_KP + q], e = m->edge[(size_t)i * BL_KP + q];
+            if ((double)(float)v != v || (double)(float)e != e) { ve_ok = false; break; }
+            ve32[((size_t)i * KDrow + q) * 2] = (float)v;
+            ve32[((size_t)i * KDrow + q) * 2 + 1] = (float)e;
+        }
     std::vector<unsigned char> flags(N);
     for (int i = 0; i < N; ++i)
         flags[i] = (unsigned char)((m->borders[i] ? 1 : 0) | (m->borders2[i] ? 2 : 0) | (m->indomain[i] ? 4 : 0));
@@ -311,6 +323,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
 #define UP(off, src, bytes) CUDA_OK(cudaMemcpy(ws + (off), (src), (bytes), cudaMemcpyHostToDevice))
     UP(L.off_ngb, ngbT.data(), ngbT.size() * 4);
     UP(L.off_ngb16, ngb16.data(), ngb16.size() * 2);
+    UP(L.off_ve32, ve32.data(), ve32.size() * 4);
     UP(L.off_vor, vorT.data(), vorT.size() * 8);
     UP(L.off_edge, edgeT.data(), edgeT.size() * 8);
     UP(L.off_area, m->area, (size_t)N * 8);
@@ -337,6 +350,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     c.ngb = (const int *)(ws + L.off_ngb);
     c.ngb16 = (const unsigned short *)(ws + L.off_ngb16);
     c.Nq = Nq; c.KDT = KDT;
+    c.ve32 = ve_ok ? (const float *)(ws + L.off_ve32) : nullptr;
     c.lev_contig = 1;
     c.dbg = getenv("BL_DEBUG") ? atoi(getenv("BL_DEBUG")) : 0;
     for (size_t i = 0; i < levn.size() && (int)i < N - m->bounds; ++i)

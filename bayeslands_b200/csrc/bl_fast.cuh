@@ -890,37 +890,58 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
 {
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     double *zs = (double *)dsm, *cd = zs + Nq;
+    unsigned char *fls = (unsigned char *)(cd + Nq);          // node flags staged for the neighbour test
     double *z = S.P.f[F_Z], *cumdiff = S.P.f[F_CUMDIFF], *cumhill = S.P.f[F_CUMHILL];
     const double *sedflux = S.P.f[F_SEDFLUX];
     if (c.CDr > 0.) {            // river-borne marine sediment diffusion works on the global arrays
         for (int k = tid; k < N; k += TPB) { const double sf = sedflux[k]; z[k] += sf; cumdiff[k] += sf; }
         __syncthreads();
         phase_marine_diffusion(c, S, sea, timestep);
-        for (int k = tid; k < N; k += TPB) zs[k] = z[k];
+        for (int k = tid; k < N; k += TPB) { zs[k] = z[k]; fls[k] = c.flags[k]; }
     } else {
         for (int k = tid; k < N; k += TPB) {
             const double sf = sedflux[k];
             zs[k] = z[k] + sf;
             cumdiff[k] += sf;
+            fls[k] = c.flags[k];
         }
     }
     __syncthreads();
-#pragma unroll 2
     for (int g = tid; g < N; g += TPB) {
         double acc = 0.;
-        const unsigned char fg = c.flags[g];
+        const unsigned char fg = fls[g];
         const double zg = zs[g];
         if (fg & 2) {
             Ids<KDT> ids;
             load_ids<KDT>(c, g, ids);
+            if (c.ve32) {
+                // Voronoi / Delaunay edge lengths are float32-rounded by construction (FVmethod.py:152,236,273):
+                // fetched as packed float pairs (half the bytes, 128-bit loads) and widened exactly
+                const float4 *ve = reinterpret_cast<const float4 *>(c.ve32 + (size_t)g * KDT * 2);
 #pragma unroll
-            for (int p = 0; p < KDT; ++p) {
-                if (ids.get(p) == NONE16) continue;
-                const int j = ids.get(p);
-                const double di = c.edge[(size_t)p * N + g], ed = c.vor[(size_t)p * N + g], zj = zs[j];
-                const bool bj = c.flags[j] & 2;
-                if (bj && di > 0.) acc += ed * (zj - zg) / di;
-                if (!bj) { if (zj < zg && di > 0.) acc += ed * (zj - zg) / di; }
+                for (int q = 0; q < KDT / 2; ++q) {
+                    const float4 v4 = __ldg(ve + q);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int p = 2 * q + h;
+                        if (ids.get(p) == NONE16) continue;
+                        const int j = ids.get(p);
+                        const double ed = (double)(h ? v4.z : v4.x), di = (double)(h ? v4.w : v4.y), zj = zs[j];
+                        const bool bj = fls[j] & 2;
+                        if (bj && di > 0.) acc += ed * (zj - zg) / di;
+                        if (!bj) { if (zj < zg && di > 0.) acc += ed * (zj - zg) / di; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < KDT; ++p) {
+                    if (ids.get(p) == NONE16) continue;
+                    const int j = ids.get(p);
+                    const double di = c.edge[(size_t)p * N + g], ed = c.vor[(size_t)p * N + g], zj = zs[j];
+                    const bool bj = fls[j] & 2;
+                    if (bj && di > 0.) acc += ed * (zj - zg) / di;
+                    if (!bj) { if (zj < zg && di > 0.) acc += ed * (zj - zg) / di; }
+                }
             }
         }
         const double area = c.area[g];
@@ -932,7 +953,7 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
     __syncthreads();
     for (int k = tid; k < N; k += TPB) {
         double zn = zs[k];
-        if (c.flags[k] & 1) { const double d = cd[k]; zn += d; cumdiff[k] += d; cumhill[k] += d; }
+        if (fls[k] & 1) { const double d = cd[k]; zn += d; cumdiff[k] += d; cumhill[k] += d; }
         zs[k] = zn;
     }
     __syncthreads();
