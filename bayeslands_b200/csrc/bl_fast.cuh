@@ -889,21 +889,26 @@ template <int KDT>
 __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea, double timestep)
 {
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
-    double *zs = (double *)dsm, *cd = zs + Nq;
-    unsigned char *fls = (unsigned char *)(cd + Nq);          // node flags staged for the neighbour test
-    double *z = S.P.f[F_Z], *cumdiff = S.P.f[F_CUMDIFF], *cumhill = S.P.f[F_CUMHILL];
-    const double *sedflux = S.P.f[F_SEDFLUX];
+    double *__restrict__ zs = (double *)dsm;
+    double *__restrict__ cd = zs + Nq;
+    unsigned char *__restrict__ fls = (unsigned char *)(cd + Nq);          // node flags staged for the neighbour test
+    double *__restrict__ z = S.P.f[F_Z];
+    double *__restrict__ cumdiff = S.P.f[F_CUMDIFF];
+    double *__restrict__ cumhill = S.P.f[F_CUMHILL];
+    const double *__restrict__ sedflux = S.P.f[F_SEDFLUX];
+    const unsigned char *__restrict__ gflags = c.flags;
     if (c.CDr > 0.) {            // river-borne marine sediment diffusion works on the global arrays
         for (int k = tid; k < N; k += TPB) { const double sf = sedflux[k]; z[k] += sf; cumdiff[k] += sf; }
         __syncthreads();
         phase_marine_diffusion(c, S, sea, timestep);
         for (int k = tid; k < N; k += TPB) { zs[k] = z[k]; fls[k] = c.flags[k]; }
     } else {
+#pragma unroll 4
         for (int k = tid; k < N; k += TPB) {
             const double sf = sedflux[k];
             zs[k] = z[k] + sf;
             cumdiff[k] += sf;
-            fls[k] = c.flags[k];
+            fls[k] = gflags[k];
         }
     }
     __syncthreads();
@@ -951,9 +956,12 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
         cd[g] = coeff * acc * timestep;
     }
     __syncthreads();
+#pragma unroll 4
     for (int k = tid; k < N; k += TPB) {
         double zn = zs[k];
-        if (fls[k] & 1) { const double d = cd[k]; zn += d; cumdiff[k] += d; cumhill[k] += d; }
+        const double d = (fls[k] & 1) ? cd[k] : 0.;
+        const double c0 = cumdiff[k], h0 = cumhill[k];
+        if (fls[k] & 1) { zn += d; cumdiff[k] = c0 + d; cumhill[k] = h0 + d; }
         zs[k] = zn;
     }
     __syncthreads();
@@ -967,6 +975,7 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
         for (int k = tid; k < c.bounds; k += TPB) zs[k] = cd[k];
         __syncthreads();
     }
+#pragma unroll 4
     for (int k = tid; k < N; k += TPB) {
         double zn = zs[k];
         if (c.disp) zn += c.disp[k] * timestep;
