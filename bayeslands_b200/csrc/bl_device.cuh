@@ -838,15 +838,14 @@ __device__ void phase_marine_distribution(const DevConst &c, Smem &S, double sea
     const double *areaA = c.area;
     const unsigned char *flagA = c.flags;
     const int KDT = c.KDT;
-    if (S.dsm && (size_t)c.Nq * (25 + 2 * KDT) + 64 <= (size_t)S.dsm_bytes) {
+    if (S.dsm && (size_t)c.Nq * (17 + 2 * KDT) + 64 <= (size_t)S.dsm_bytes) {
         elev = (double *)S.dsm;
         seadep = elev + c.Nq;
-        double *ar = seadep + c.Nq;
-        unsigned short *nb = (unsigned short *)(ar + c.Nq);
+        unsigned short *nb = (unsigned short *)(seadep + c.Nq);
         unsigned char *fl = (unsigned char *)(nb + (size_t)c.Nq * KDT);
         for (int i = tid; i < N * KDT; i += TPB) nb[i] = c.ngb16[i];
-        for (int i = tid; i < N; i += TPB) { ar[i] = c.area[i]; fl[i] = c.flags[i]; }
-        nb16 = nb; areaA = ar; flagA = fl;
+        for (int i = tid; i < N; i += TPB) fl[i] = c.flags[i];
+        nb16 = nb; flagA = fl;
     }
     for (int k = tid; k < N; k += TPB) elev[k] = z[k];
     __syncthreads();
