@@ -209,11 +209,87 @@ class bayeslands_mcmc(object):
         return dict(pos_rain=pos_rain, pos_erod=pos_erod, pos_likl=pos_likl, accept_ratio=naccept / max(1, S_ - 1) * 100.0)
 
     def sampler(self):
-        """Single chain with the reference's draw order (global numpy stream + stdlib random)."""
-        out = self.sampler_chains(1, np_seed=0, py_seed=0)
-        if self.filename:
-            os.makedirs(self.filename, exist_ok=True)
-            with open(os.path.join(self.filename, "exp_data.txt"), "w") as f:       # storeParams, :457-480
-                for r, e, l in zip(out["pos_rain"][:, 0], out["pos_erod"][:, 0], out["pos_likl"][:, 0]):
+        """Single random-walk Metropolis chain with the reference's draw order and output files
+        (`bl_mcmc.py:515-835`): numpy's global stream for the start point, the proposals and the three unused eta
+        draws, stdlib `random` for the accept test; `description.txt`, `exp_data.txt` (one `rain erod likl` row per
+        sample, `storeParams` :457-480), `prediction_data/mean_pred_{elev,erdp}_<t>.txt` and `mean_pred_erdp_pts.txt`
+        (post burn-in running means, :776-815) and `experiment_stats.txt` (:817-833).  Plots are out of scope.
+        Returns (pos_rain, pos_erod, pos_likl, accept_ratio)."""
+        start = time.time()
+        samples = self.samples
+        fn = self.filename
+        if fn:
+            os.makedirs(os.path.join(fn, "prediction_data"), exist_ok=True)
+        pos_rain = np.zeros(samples); pos_erod = np.zeros(samples)
+        rain = np.random.uniform(self.rainlimits[0], self.rainlimits[1])
+        erod = np.random.uniform(self.erodlimits[0], self.erodlimits[1])
+        m, n = 0.5, 1.0
+        if fn:
+            with open(os.path.join(fn, "description.txt"), "a") as f:                         # :589-605
+                for k, v in (("samples", samples), ("step_rain", self.step_rain), ("step_erod", self.step_erod),
+                             ("step_m", self.step_m), ("step_n", self.step_n), ("Initial_proposed_rain", rain),
+                             ("Initial_proposed_erod", erod), ("Initial_proposed_m", m), ("Initial_proposed_n", n),
+                             ("erod_limits", self.erodlimits), ("rain_limits", self.rainlimits),
+                             ("m_limit", self.mlimit), ("n_limit", self.nlimit)):
+                    f.write("\n\t{0}: {1}".format(k, v))
+
+        def evaluate(r, e):
+            sse, pts, elev, erdp = self.blackBox_batch([r], [e], grids=True)
+            lik, _ = log_likelihood(sse, self.G, pts, self.real_erdp_pts, self.likl_sed)
+            return float(lik[0]), elev[0], erdp[0], pts[0]
+
+        def store(r, e, l):
+            if fn:
+                with open(os.path.join(fn, "exp_data.txt"), "a") as f:
                     f.write("{0} {1} {2} \n".format(r, e, l))
-        return out["pos_rain"][:, 0], out["pos_erod"][:, 0], out["pos_likl"][:, 0], out["accept_ratio"][0]
+
+        self.blackBox_batch([rain], [erod])                  # the reference evaluates the start twice (:569, :610)
+        likelihood, elev, erdp, pts = evaluate(rain, erod)
+        pos_likl = np.full(samples, likelihood)              # np.zeros(samples, likelihood) in the reference (F11)
+        prev = (elev, erdp, pts)
+        store(pos_rain[0], pos_erod[0], pos_likl[0])
+        sum_elev, sum_erdp, sum_pts = elev.copy(), erdp.copy(), pts.copy()
+        burnsamples = int(samples * self.burn_in)
+        num_div = 0
+        accept_counter = 0
+        for i in range(samples - 1):
+            p_rain = rain + np.random.normal(0, self.step_rain)
+            if p_rain < self.rainlimits[0] or p_rain > self.rainlimits[1]:
+                p_rain = rain
+            p_erod = erod + np.random.normal(0, self.step_erod)
+            if p_erod < self.erodlimits[0] or p_erod > self.erodlimits[1]:
+                p_erod = erod
+            for _ in range(3):
+                np.random.normal(0, 1.0, 1)                  # eta walk draws, consumed and unused (:670-677, F8)
+            likelihood_proposal, elev, erdp, pts = evaluate(p_rain, p_erod)
+            diff_likelihood = likelihood_proposal - likelihood
+            try:
+                mh_prob = min(1, math.exp(diff_likelihood))
+            except OverflowError:
+                mh_prob = 1
+            u = random.uniform(0, 1)
+            if u < mh_prob:
+                likelihood, rain, erod = likelihood_proposal, p_rain, p_erod
+                pos_rain[i + 1], pos_erod[i + 1], pos_likl[i + 1] = rain, erod, likelihood
+                prev = (elev, erdp, pts)
+                accept_counter += 1
+            else:
+                pos_rain[i + 1], pos_erod[i + 1], pos_likl[i + 1] = pos_rain[i], pos_erod[i], pos_likl[i]
+            store(pos_rain[i + 1], pos_erod[i + 1], pos_likl[i + 1])
+            if i > burnsamples:
+                sum_elev += prev[0]; sum_erdp += prev[1]; sum_pts += prev[2]
+                num_div += 1
+        accept_ratio = accept_counter / (samples * 1.0) * 100
+        if fn:
+            div = max(num_div, 1)
+            for x, T in enumerate(self.sim_interval):
+                np.savetxt(os.path.join(fn, "prediction_data", "mean_pred_elev_%s.txt" % T), sum_elev[x] / div, fmt="%.5f")
+                np.savetxt(os.path.join(fn, "prediction_data", "mean_pred_erdp_%s.txt" % T), sum_erdp[x] / div, fmt="%.5f")
+            np.savetxt(os.path.join(fn, "prediction_data", "mean_pred_erdp_pts.txt"), sum_pts / div, fmt="%.5f")
+            burn = int(samples * self.burn_in)
+            with open(os.path.join(fn, "experiment_stats.txt"), "w") as f:
+                f.write("Time:(s) {0}\nTime:(mins) {1}\nAccept ratio: {2} %\nSamples accepted: {3} out of {4}\n".format(
+                    time.time() - start, (time.time() - start) / 60.0, accept_ratio, accept_counter, samples))
+                f.write("Mean rain after burn-in: {0}\nMean erod after burn-in: {1}\n".format(
+                    pos_rain[burn:].mean(), pos_erod[burn:].mean()))
+        return pos_rain, pos_erod, pos_likl, accept_ratio

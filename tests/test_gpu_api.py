@@ -150,3 +150,23 @@ def test_topo_generator_writes_reference_files(crater_fast, tmp_path):
     clean, _, _ = topo_generator(mc, 1.5, 5e-5, final_noise=False)
     noise_var = np.var(fe - clean)
     assert 0.8 * (clean.max() * 0.01 + 0.5) < noise_var < 1.2 * (clean.max() * 0.01 + 0.5)
+
+
+def test_sampler_writes_reference_outputs_and_is_seeded(crater_fast, tmp_path):
+    """bl_mcmc.sampler: global numpy stream + stdlib random => the chain is reproducible from the two seeds and
+    leaves the reference's files behind (exp_data.txt rows, description.txt, stats, mean prediction grids)."""
+    import os
+    out = []
+    for rep in range(2):
+        d_ = tmp_path / ("run%d" % rep)
+        mc = _mc(crater_fast, 1, samples=8)
+        mc.filename = str(d_)
+        np.random.seed(11); random.seed(12)
+        out.append(mc.sampler())
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][2], out[1][2])
+    rows = np.loadtxt(tmp_path / "run0" / "exp_data.txt")
+    assert rows.shape == (8, 3) and np.allclose(rows[1:, 0], out[0][0][1:]) and np.allclose(rows[:, 2], out[0][2])
+    assert os.path.isfile(tmp_path / "run0" / "description.txt") and os.path.isfile(tmp_path / "run0" / "experiment_stats.txt")
+    g = np.loadtxt(tmp_path / "run0" / "prediction_data" / "mean_pred_elev_15000.txt")
+    assert g.shape == (123, 123) and 20.0 < g.mean() < 120.0
+    assert 0.0 <= out[0][3] <= 100.0
