@@ -47,8 +47,16 @@ class BlParams(C.Structure):
                 ("seav", c_dp), ("real_elev", c_dp), ("npts", C.c_int32), ("pts_cell", c_ip)]
 
 
+class BlLattice(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("dist", C.c_double * 8), ("vor", C.c_double * 8),
+                ("edge", C.c_double * 8), ("area", C.c_double), ("z0", c_dp), ("flags", C.POINTER(C.c_uint8)),
+                ("disp", c_dp), ("parent", c_ip), ("real_elev", c_dp)]
+
+
 EXPORTS = ("bl_last_error", "bl_version", "bl_workspace_bytes", "bl_ctx_create", "bl_ctx_destroy", "bl_reset",
-           "bl_run", "bl_step", "bl_get_field", "bl_get_scalars", "bl_get_phase_cycles", "bl_launch_count")
+           "bl_run", "bl_step", "bl_get_field", "bl_get_scalars", "bl_get_phase_cycles", "bl_launch_count",
+           "bl_grid_workspace_bytes", "bl_grid_create", "bl_grid_destroy", "bl_grid_reset", "bl_grid_run",
+           "bl_grid_step", "bl_grid_get_field", "bl_grid_get_scalars", "bl_grid_launch_count")
 
 _lib = None
 
@@ -85,6 +93,19 @@ def load():
     L.bl_get_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bl_launch_count.restype = C.c_int64
     L.bl_launch_count.argtypes = [C.c_void_p]
+    L.bl_grid_workspace_bytes.restype = C.c_size_t
+    L.bl_grid_workspace_bytes.argtypes = [C.POINTER(BlLattice), C.c_int, C.c_int]
+    L.bl_grid_create.argtypes = [C.POINTER(BlLattice), C.POINTER(BlParams), C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                 C.c_int, C.POINTER(C.c_void_p)]
+    L.bl_grid_destroy.argtypes = [C.c_void_p]
+    L.bl_grid_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.bl_grid_run.argtypes = [C.c_void_p, C.c_int, c_dp, c_ip, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                              C.c_void_p]
+    L.bl_grid_step.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+    L.bl_grid_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.bl_grid_get_scalars.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bl_grid_launch_count.restype = C.c_int64
+    L.bl_grid_launch_count.argtypes = [C.c_void_p]
     _lib = L
     return L
 

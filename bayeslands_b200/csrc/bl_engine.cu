@@ -557,3 +557,5 @@ extern "C" int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst, void *stream)
 }
 
 extern "C" int64_t bl_launch_count(const bl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+#include "bl_grid.cuh"

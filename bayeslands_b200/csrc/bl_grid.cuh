@@ -1,0 +1,867 @@
+// bl_grid.cuh - lattice engine: the hot path on a regular D8 lattice too large for one CTA (BASELINE config 5:
+// 2048 x 2048 nodes x 256 proposals), included at the end of bl_engine.cu.
+//
+// Where bl_run_kernel gives one CTA a whole landscape, here every phase of the time step is a grid-wide kernel
+// batched over all proposals (blockIdx.z / task index = proposal), state is structure-of-arrays [B][LY][LXP] in HBM
+// and the streaming phases are bandwidth bound.  Scope: the purely erosive configuration (flow.depo = 0, constant
+// sea level): with no deposition the pit cascade, basin volumes and both stack orders cannot influence the state
+// (FLOWalgo.f90:875-892 writes erosion from node-local values only; getid1's overfill test FLOWalgo.f90:1047-1086
+// needs eroded volume > pit volume > 0, impossible for erosion <= 0), so the step reduces to
+//   fill (PDalgo.f90:19-91) -> receivers on the filled surface (sfd.c:55-111) -> discharge (FLOWalgo.f90:53-81)
+//   -> flowcfl (FLOWalgo.f90:299-330) + dt logic (buildFlux.py:154-177, flowNetwork.py:687-698)
+//   -> detachment-limited erosion (FLOWalgo.f90:635-714, :875-892) -> hillslope diffusion (sfd.c:155-185,
+//   diffLinear.py:150-182, buildFlux.py:252-272) -> boundary rule + uplift (buildFlux.py:292-313).
+// Order-dependent semantics kept bit-exact:
+//   * fillPD's ascending-id Gauss-Seidel sweep: mesh.build_regular(order="colour") numbers interior nodes by the
+//     2x2 parity class, so a sweep is 4 race-free colour passes; pending nodes live in a two-level bitmap per
+//     (proposal, colour) and a pass touches only the front; the reference's early stop (`change`) is per proposal;
+//   * discharge: Q[r] = (q0[r] + Q[d1]) + Q[d2] ... with donors in DESCENDING mesh id (what the reverse walk of the
+//     pre-order stack does) - evaluated by a wait-free traversal: the thread that completes the last donor of r
+//     (atomic arrival counter) sums r and walks on downstream; nobody ever spins;
+//   * SFD ties: first lowest neighbour in slot order E,NE,N,NW,W,SW,S,SE (the builder's neighbour order).
+
+namespace grid {
+
+struct GConst {
+    int nx, ny, LX, LY, LXP, B, hx, ncol, W0, W1, nb, btype, npts, has_parent;
+    size_t NLP;                 // LY*LXP rounded up: length of one per-proposal array
+    double m, n, eps, TH, CDa, CDm, minDT, maxDT, hill, sea, area, boff;
+    double dist[8], vor[8], edge[8];
+    const unsigned char *flags; // [NLP] bit0 borders, bit1 borders2
+    const double *z0, *disp, *real;
+    const int *parentL, *ghostL; // [nb] lattice index of ghost g / of its parent
+    const int *pts_cell;
+    double *z, *W, *Q, *cumdiff, *cumhill, *fdbg; // [B][NLP]
+    unsigned char *rcv, *don;   // [B][NLP] receiver slot (8 = self), donor mask
+    unsigned *cnt;              // [B][NLP/4] arrival counters, one byte per node
+    unsigned *l0, *l1;          // [B][4][W0p], [B][4][W1p] pending bitmaps
+    int W0p, W1p;
+    double *rain, *erod, *tnow, *dt, *lastdt, *partial;
+    unsigned long long *cflbits;
+    long long *steps, *sweeps;
+    int *running, *fill_active, *change, *si, *ckflag;
+    int *counters;              // [0] running proposals, [1] proposals still sweeping, [2] sweeps this step
+    const double *stops;
+    const int *ckpt;
+    int nstops, npart;
+};
+
+__constant__ int c_di[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+__constant__ int c_dj[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+
+__device__ __forceinline__ double powm(double x, double e)
+{
+    if (e == 0.5) return sqrt(x);
+    if (e == 1.0) return x;
+    if (e == 0.0) return 1.0;
+    return pow(x, e);
+}
+__device__ __forceinline__ double floorish(double x) { return (x > 1.) ? round(x - 0.5) : x; }
+__device__ __forceinline__ bool is_ghost(const GConst &g, int I, int J) { return I == 0 || J == 0 || I == g.LX - 1 || J == g.LY - 1; }
+
+// mesh id of lattice node (I, J): ghost ring in raster2TIN order, interior colour-major (mesh.build_regular)
+__device__ __forceinline__ int mesh_id(const GConst &g, int I, int J)
+{
+    if (J == 0) return I;
+    if (J == g.LY - 1) return g.LX + g.ny + I;
+    if (I == 0) return g.LX + (J - 1);
+    if (I == g.LX - 1) return 2 * g.LX + g.ny + (J - 1);
+    const int i = I - 1, j = J - 1;
+    return g.nb + ((j & 1) * 2 + (i & 1)) * g.ncol + (j >> 1) * g.hx + (i >> 1);
+}
+
+__global__ void k_reset(GConst g, const double *rain, const double *erod, double tStart)
+{
+    const int p = blockIdx.y;
+    const size_t L = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (L < g.NLP) {
+        const size_t o = (size_t)p * g.NLP + L;
+        g.z[o] = g.z0[L];
+        g.cumdiff[o] = 0.;
+        g.cumhill[o] = 0.;
+        g.W[o] = 0.;
+        g.Q[o] = 0.;
+        g.rcv[o] = 8;
+        g.don[o] = 0;
+        if (g.fdbg) g.fdbg[o] = 0.;
+    }
+    if (L == 0) {
+        g.rain[p] = rain[p]; g.erod[p] = erod[p]; g.tnow[p] = tStart; g.dt[p] = 0.; g.lastdt[p] = 0.;
+        g.steps[p] = 0; g.sweeps[p] = 0; g.running[p] = 0; g.fill_active[p] = 0; g.change[p] = 0; g.si[p] = 0; g.ckflag[p] = 0;
+    }
+}
+
+// Model.run_to_time bookkeeping (model.py:266-490): advance the clock, pass stop times, flag checkpoints
+__global__ void k_advance(GConst g, int do_step, int restart)
+{
+    __shared__ int s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < g.B; p += blockDim.x) {
+        if (restart) { g.running[p] = 1; g.si[p] = 0; }
+        int ck = 0;
+        if (g.running[p]) {
+            if (do_step) { g.tnow[p] += g.dt[p]; g.lastdt[p] = g.dt[p]; g.steps[p] += 1; }
+            int si = g.si[p];
+            while (si < g.nstops && !(g.tnow[p] < g.stops[si])) {
+                if (g.ckpt[si] >= 0) ck |= 1 << g.ckpt[si];
+                ++si;
+            }
+            g.si[p] = si;
+            if (si >= g.nstops) g.running[p] = 0; else atomicAdd(&s_run, 1);
+        }
+        g.ckflag[p] = ck;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) g.counters[0] = s_run;
+}
+
+// ---- depression filling ----------------------------------------------------------------------------------
+__global__ void k_fill_init(GConst g)
+{
+    const int p = blockIdx.y;
+    if (!g.running[p]) { if (blockIdx.x == 0 && threadIdx.x == 0) g.fill_active[p] = 0; return; }
+    const size_t L = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (L < (size_t)g.LY * g.LXP) {
+        const int I = (int)(L % g.LXP), J = (int)(L / g.LXP);
+        if (I < g.LX) {
+            const size_t o = (size_t)p * g.NLP + L;
+            g.W[o] = is_ghost(g, I, J) ? g.z[o] : 1.e6;                    // PDalgo.f90:19-35
+        }
+    }
+    if (L < (size_t)4 * g.W0p) {
+        const int c = (int)(L / g.W0p), w = (int)(L % g.W0p);
+        unsigned m = 0u;
+        if (w < g.W0) { m = 0xFFFFFFFFu; if (w * 32 + 32 > g.ncol) m = (1u << (g.ncol - w * 32)) - 1u; }
+        g.l0[((size_t)p * 4 + c) * g.W0p + w] = m;
+    }
+    if (L < (size_t)4 * g.W1p) {
+        const int c = (int)(L / g.W1p), w = (int)(L % g.W1p);
+        unsigned m = 0u;
+        if (w < g.W1) { m = 0xFFFFFFFFu; if (w * 32 + 32 > g.W0) m = (1u << (g.W0 - w * 32)) - 1u; }
+        g.l1[((size_t)p * 4 + c) * g.W1p + w] = m;
+    }
+    if (L == 0) {
+        g.fill_active[p] = 1; g.change[p] = 0;
+        g.cflbits[p] = (unsigned long long)__double_as_longlong(1.e6);
+    }
+}
+
+// one colour pass of the Gauss-Seidel sweep (PDalgo.f90:37-91).  One warp per level-1 bitmap word (1024 nodes of
+// the colour); pending nodes of the same colour are never adjacent, so the pass is race free.
+__global__ void __launch_bounds__(256) k_fill_pass(GConst g, int c)
+{
+    if (g.counters[1] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long ntask = (long long)g.B * g.W1;
+    const int hx = g.hx, LXP = g.LXP;
+    const double eps = g.eps, TH = g.TH, sea = g.sea;
+    for (long long t = warp; t < ntask; t += nwarps) {
+        const int p = (int)(t / g.W1), w1 = (int)(t % g.W1);
+        if (!g.fill_active[p]) continue;
+        unsigned *L1 = g.l1 + ((size_t)p * 4 + c) * g.W1p;
+        unsigned m1 = 0u;
+        if (lane == 0) { m1 = L1[w1]; if (m1) L1[w1] = 0u; }
+        m1 = __shfl_sync(0xffffffffu, m1, 0);
+        if (!m1) continue;
+        unsigned *L0 = g.l0 + ((size_t)p * 4 + c) * g.W0p + (size_t)w1 * 32;
+        unsigned w0 = 0u;
+        if ((m1 >> lane) & 1u) { w0 = L0[lane]; if (w0) L0[lane] = 0u; }
+        unsigned nz = __ballot_sync(0xffffffffu, w0 != 0u);
+        double *W = g.W + (size_t)p * g.NLP;
+        const double *z = g.z + (size_t)p * g.NLP;
+        int loc = 0;
+        while (nz) {
+            const int src = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const unsigned word = __shfl_sync(0xffffffffu, w0, src);
+            if (!((word >> lane) & 1u)) continue;
+            const int q = (w1 * 32 + src) * 32 + lane;
+            const int qy = q / hx, qx = q - qy * hx;
+            const int i = 2 * qx + (c & 1), j = 2 * qy + (c >> 1);
+            const size_t L = (size_t)(j + 1) * LXP + (i + 1);
+            const double wk = W[L], zk = z[L];
+            if (!(wk > zk)) continue;
+            const double *r0 = W + L - LXP, *r2 = W + L + LXP;
+            double hmin = fmin(fmin(fmin(r0[-1], r0[0]), fmin(r0[1], W[L - 1])), fmin(fmin(W[L + 1], r2[-1]), fmin(r2[0], r2[1])));
+            hmin = fmin(hmin, 2.e6);
+            const double he = hmin + eps;
+            double nw = wk;
+            if (zk >= he) nw = zk;
+            else if (wk > he) {
+                nw = he;
+                if (zk >= sea) { if (nw - zk > TH) nw = zk + TH; else loc = 1; }
+                else           { if (nw - sea > TH) nw = sea + TH; else loc = 1; }
+            }
+            if (nw != wk) {
+                W[L] = nw;
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    const int i2 = i + c_di[o], j2 = j + c_dj[o];
+                    if (i2 < 0 || j2 < 0 || i2 >= g.nx || j2 >= g.ny) continue;
+                    const int c2 = (j2 & 1) * 2 + (i2 & 1);
+                    const int q2 = (j2 >> 1) * hx + (i2 >> 1);
+                    const unsigned old = atomicOr(g.l0 + ((size_t)p * 4 + c2) * g.W0p + (q2 >> 5), 1u << (q2 & 31));
+                    if (old == 0u) atomicOr(g.l1 + ((size_t)p * 4 + c2) * g.W1p + (q2 >> 10), 1u << ((q2 >> 5) & 31));
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, loc) && lane == 0) g.change[p] = 1;
+    }
+}
+
+// end of a sweep: the reference's `do while (change)` per proposal
+__global__ void k_fill_end(GConst g)
+{
+    __shared__ int s_act;
+    if (threadIdx.x == 0) s_act = 0;
+    __syncthreads();
+    if (threadIdx.x == 0 && g.counters[1] > 0) g.counters[2] += 1;      // sweeps this step (max over proposals)
+    for (int p = threadIdx.x; p < g.B; p += blockDim.x) {
+        if (g.fill_active[p]) {
+            g.sweeps[p] += 1;
+            if (g.change[p] == 0) g.fill_active[p] = 0; else atomicAdd(&s_act, 1);
+            g.change[p] = 0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) g.counters[1] = s_act;
+}
+__global__ void k_fill_begin(GConst g)
+{
+    __shared__ int s_act;
+    if (threadIdx.x == 0) s_act = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < g.B; p += blockDim.x) if (g.fill_active[p]) atomicAdd(&s_act, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { g.counters[1] = s_act; g.counters[2] = 0; }
+}
+
+// ---- receivers on the filled surface (sfd.c:55-111) ---------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sfd(GConst g)
+{
+    const int p = blockIdx.z;
+    if (!g.running[p]) return;
+    const int I = blockIdx.x * 32 + threadIdx.x, J = blockIdx.y * 8 + threadIdx.y;
+    if (I >= g.LX || J >= g.LY) return;
+    const size_t L = (size_t)J * g.LXP + I, o = (size_t)p * g.NLP + L;
+    const double *W = g.W + (size_t)p * g.NLP;
+    double wl = W[L];
+    if (g.fdbg) g.fdbg[o] = wl;
+    int low = 8;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const int I2 = I + c_di[s], J2 = J + c_dj[s];
+        if (I2 < 0 || J2 < 0 || I2 >= g.LX || J2 >= g.LY) continue;
+        const double wj = W[(size_t)J2 * g.LXP + I2];
+        if (wj < wl) { low = s; wl = wj; }
+    }
+    g.rcv[o] = (unsigned char)low;
+}
+
+// donor mask (which neighbours drain into me) + arrival counters
+__global__ void __launch_bounds__(256) k_donors(GConst g)
+{
+    const int p = blockIdx.z;
+    if (!g.running[p]) return;
+    const int I = blockIdx.x * 32 + threadIdx.x, J = blockIdx.y * 8 + threadIdx.y;
+    if (I >= g.LXP || J >= g.LY) return;
+    const size_t L = (size_t)J * g.LXP + I, o = (size_t)p * g.NLP + L;
+    if ((I & 3) == 0) g.cnt[o >> 2] = 0u;
+    if (I >= g.LX) return;
+    const unsigned char *rcv = g.rcv + (size_t)p * g.NLP;
+    unsigned m = 0u;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const int I2 = I + c_di[s], J2 = J + c_dj[s];
+        if (I2 < 0 || J2 < 0 || I2 >= g.LX || J2 >= g.LY) continue;
+        if (rcv[(size_t)J2 * g.LXP + I2] == ((s + 4) & 7)) m |= 1u << s;
+    }
+    g.don[o] = (unsigned char)m;
+}
+
+// discharge (FLOWalgo.f90:53-81; compute_flow flowNetwork.py:418-443): wait-free tree accumulation
+__global__ void __launch_bounds__(256) k_discharge(GConst g)
+{
+    const int p = blockIdx.z;
+    if (!g.running[p]) return;
+    int I = blockIdx.x * 32 + threadIdx.x, J = blockIdx.y * 8 + threadIdx.y;
+    if (I >= g.LX || J >= g.LY) return;
+    const size_t base = (size_t)p * g.NLP;
+    const unsigned char *rcv = g.rcv + base, *don = g.don + base;
+    double *Q = g.Q + base;
+    unsigned *cnt = g.cnt + (base >> 2);
+    size_t L = (size_t)J * g.LXP + I;
+    if (don[L] != 0) return;                                  // only leaves start a walk
+    const double q0i = g.area * g.rain[p];                    // rain is 0 on ghost nodes (model.py:278-279)
+    double acc = is_ghost(g, I, J) ? 0. : q0i;
+    for (;;) {
+        Q[L] = acc;
+        const int s = rcv[L];
+        if (s == 8) break;
+        const int Ir = I + c_di[s], Jr = J + c_dj[s];
+        const size_t R = (size_t)Jr * g.LXP + Ir;
+        __threadfence();
+        const unsigned sh = 8u * (unsigned)(R & 3);
+        const unsigned old = atomicAdd(cnt + (R >> 2), 1u << sh);
+        unsigned mask = don[R];
+        if ((int)((old >> sh) & 0xFFu) + 1 != __popc(mask)) break;   // somebody else will finish R
+        __threadfence();
+        acc = is_ghost(g, Ir, Jr) ? 0. : q0i;
+        while (mask) {                                        // donors in descending mesh id
+            int best = -1, bid = -1;
+            for (unsigned mm = mask; mm; mm &= mm - 1) {
+                const int o = __ffs(mm) - 1;
+                const int id = mesh_id(g, Ir + c_di[o], Jr + c_dj[o]);
+                if (id > bid) { bid = id; best = o; }
+            }
+            acc = acc + __ldcg(Q + (size_t)(Jr + c_dj[best]) * g.LXP + (Ir + c_di[best]));
+            mask &= ~(1u << best);
+        }
+        I = Ir; J = Jr; L = R;
+    }
+}
+
+// flowcfl (FLOWalgo.f90:299-330) on the filled surface (buildFlux.py:169)
+__global__ void __launch_bounds__(256) k_cfl(GConst g)
+{
+    const int p = blockIdx.z;
+    if (!g.running[p]) return;
+    const int I = blockIdx.x * 32 + threadIdx.x, J = blockIdx.y * 8 + threadIdx.y;
+    double tmp = 1.e6;
+    if (I < g.LX && J < g.LY) {
+        const size_t base = (size_t)p * g.NLP, L = (size_t)J * g.LXP + I;
+        const int s = g.rcv[base + L];
+        if (s != 8) {
+            const double *W = g.W + base;
+            const double dz = W[L] - W[(size_t)(J + c_dj[s]) * g.LXP + (I + c_di[s])];
+            const double q = g.Q[base + L];
+            if (dz > 0. && q > 0.) {
+                const double dist = g.dist[s];
+                tmp = dist / (g.erod[p] * powm(q, g.m) * powm(dz / dist, g.n - 1.));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) tmp = fmin(tmp, __shfl_xor_sync(0xffffffffu, tmp, o));
+    __shared__ double s_min[8];
+    if (threadIdx.x == 0) s_min[threadIdx.y] = tmp;
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        for (int w = 1; w < 8; ++w) tmp = fmin(tmp, s_min[w]);
+        if (tmp < 1.e6) atomicMin(g.cflbits + p, (unsigned long long)__double_as_longlong(tmp));   // positive doubles order as integers
+    }
+}
+
+// buildFlux.py:154-177 + flowNetwork.py:687-698 (newdt = py2-rounded dt; the re-run uses it)
+__global__ void k_dt(GConst g)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.B || !g.running[p]) return;
+    const double flowcfl = __longlong_as_double((long long)g.cflbits[p]);
+    double cfl = fmin(flowcfl, g.hill);
+    cfl = floorish(cfl);
+    cfl = fmin(cfl, g.stops[g.si[p]] - g.tnow[p]);
+    cfl = fmax(g.minDT, cfl);
+    cfl = fmin(g.maxDT, cfl);
+    double newdt = floorish(cfl);
+    newdt = fmax(g.minDT, newdt);
+    g.dt[p] = newdt;
+}
+
+// detachment-limited erosion (FLOWalgo.f90:635-714, :875-892; flowNetwork.py:706-712, buildFlux.py:193-195).
+// Writes the eroded surface over W (fillH is dead after this kernel: only the node's own value is read).
+__global__ void __launch_bounds__(256) k_erode(GConst g)
+{
+    const int p = blockIdx.z;
+    if (!g.running[p]) return;
+    const int I = blockIdx.x * 32 + threadIdx.x, J = blockIdx.y * 8 + threadIdx.y;
+    if (I >= g.LX || J >= g.LY) return;
+    const size_t base = (size_t)p * g.NLP, L = (size_t)J * g.LXP + I;
+    const double *z = g.z + base;
+    const int s = g.rcv[base + L];
+    const double zd = z[L];
+    double sed = 0.;
+    if ((g.flags[L] & 1) && s != 8) {
+        const double zr = z[(size_t)(J + c_dj[s]) * g.LXP + (I + c_di[s])];
+        const double sea = g.sea, dt = g.dt[p];
+        double dh = 0.95 * (zd - zr);
+        if (zd > sea && zr < sea) dh = 0.99 * (zd - sea);
+        if (dh < 0.001) dh = 0.;
+        const double fh = g.W[base + L];
+        const double waterH = fh - zd;
+        if (dh > 0. && waterH == 0. && fh >= sea) {
+            const double dist = g.dist[s];
+            const double slp = dh / dist;
+            if (dist > 0.) {
+                double SPL = -g.erod[p] * 1. * 1. * powm(g.Q[base + L], g.m) * powm(slp, g.n);
+                double totspl = 0. + SPL;
+                if (-totspl * dt > dh) {
+                    const double frac = dh / (-totspl * dt);
+                    SPL = SPL * frac;
+                    totspl = -dh;
+                }
+                if (totspl < 0.) {
+                    const double erodep = SPL * dt * g.area;
+                    const double cero = 0. + erodep;
+                    sed = cero / g.area + 0.;
+                }
+            }
+        }
+    }
+    g.W[base + L] = zd + sed;
+    g.cumdiff[base + L] += sed;
+}
+
+// hillslope diffusion (sfd.c:155-185; diffLinear.py:150-182; buildFlux.py:252-272) on the eroded surface held in W;
+// FUSE: no boundary rule to apply (btype fixed) -> uplift (buildFlux.py:312-313) in the same pass
+template <int FUSE>
+__global__ void __launch_bounds__(256) k_diffuse(GConst g)
+{
+    const int p = blockIdx.z;
+    if (!g.running[p]) return;
+    const int I = blockIdx.x * 32 + threadIdx.x, J = blockIdx.y * 8 + threadIdx.y;
+    if (I >= g.LX || J >= g.LY) return;
+    const size_t base = (size_t)p * g.NLP, L = (size_t)J * g.LXP + I;
+    const double *zs = g.W + base;
+    const unsigned char fl = g.flags[L];
+    const double zg = zs[L], dt = g.dt[p];
+    double acc = 0.;
+    if (fl & 2) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const double ed = g.vor[s], di = g.edge[s];
+            if (ed == 0.) continue;                      // diagonal slots carry no Voronoi edge: the term is +-0
+            const size_t L2 = (size_t)(J + c_dj[s]) * g.LXP + (I + c_di[s]);
+            const double zj = zs[L2];
+            if (g.flags[L2] & 2) { if (di > 0.) acc += ed * (zj - zg) / di; }
+            else if (zj < zg && di > 0.) acc += ed * (zj - zg) / di;
+        }
+    }
+    double znew = zg;
+    if (fl & 1) {
+        const double ac = (g.area > 0.) ? 1. / g.area : 0.;
+        double coeff = ac * ((zg >= g.sea) ? g.CDa : g.CDm);
+        if (!(fl & 2)) { coeff = 0.; acc = 0.; }
+        const double flux = coeff * acc * dt;
+        znew = zg + flux;
+        g.cumdiff[base + L] += flux;
+        g.cumhill[base + L] += flux;
+    }
+    if (FUSE && g.disp) znew += g.disp[L] * dt;
+    g.z[base + L] = znew;
+}
+
+// buildFlux.py:292-302 ghost nodes follow their parent; then uplift on every node (:312-313)
+__global__ void k_boundary(GConst g)
+{
+    const int p = blockIdx.y;
+    if (!g.running[p]) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= g.nb) return;
+    double *z = g.z + (size_t)p * g.NLP;
+    z[g.ghostL[k]] = z[g.parentL[k]] + g.boff;
+}
+__global__ void k_uplift(GConst g)
+{
+    const int p = blockIdx.y;
+    if (!g.running[p]) return;
+    const size_t L = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (L >= (size_t)g.LY * g.LXP || (int)(L % g.LXP) >= g.LX) return;
+    g.z[(size_t)p * g.NLP + L] += g.disp[L] * g.dt[p];
+}
+
+// checkpoints: lattice cell = node (the k=3 IDW table of interpolateArray degenerates to exact hits), SSE against the
+// observed grid in a fixed reduction order (bl_mcmc.py:482-513), optional grid copies
+__global__ void __launch_bounds__(256) k_ckpt(GConst g, double *out_elev, double *out_erdp, int nck)
+{
+    const int p = blockIdx.y;
+    const int ck = g.ckflag[p];
+    if (!ck) return;
+    const size_t Gn = (size_t)g.LX * g.LY;
+    double acc = 0.;
+    for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < Gn; cell += (size_t)gridDim.x * blockDim.x) {
+        const int J = (int)(cell / g.LX), I = (int)(cell % g.LX);
+        const size_t o = (size_t)p * g.NLP + (size_t)J * g.LXP + I;
+        const double zv = g.z[o];
+        if (g.real) { const double d = zv - g.real[(size_t)J * g.LXP + I]; acc += d * d; }
+        if (out_elev || out_erdp) {
+            const double cd = g.cumdiff[o];
+            for (int k = 0; k < nck; ++k) if ((ck >> k) & 1) {
+                if (out_elev) out_elev[((size_t)p * nck + k) * Gn + cell] = zv;
+                if (out_erdp) out_erdp[((size_t)p * nck + k) * Gn + cell] = cd;
+            }
+        }
+    }
+    __shared__ double s_acc[256];
+    s_acc[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o >= 1; o >>= 1) { if ((int)threadIdx.x < o) s_acc[threadIdx.x] += s_acc[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) g.partial[(size_t)p * g.npart + blockIdx.x] = s_acc[0];
+}
+__global__ void k_ckpt_final(GConst g, double *out_sse, double *out_pts)
+{
+    const int p = blockIdx.x;
+    const int ck = g.ckflag[p];
+    if (!ck) return;
+    if (threadIdx.x == 0 && out_sse && g.real) {
+        double a = 0.;
+        for (int i = 0; i < g.npart; ++i) a += g.partial[(size_t)p * g.npart + i];
+        out_sse[p] = a;
+    }
+    if (out_pts && (int)threadIdx.x < g.npts) {
+        const int cell = g.pts_cell[threadIdx.x];
+        const size_t o = (size_t)p * g.NLP + (size_t)(cell / g.LX) * g.LXP + (cell % g.LX);
+        for (int k = 0; k < BL_NCKPT_MAX; ++k) if ((ck >> k) & 1) out_pts[((size_t)p * BL_NCKPT_MAX + k) * BL_NPTS_MAX + threadIdx.x] = g.cumdiff[o];
+    }
+}
+
+} // namespace grid
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+struct bl_grid {
+    grid::GConst g;
+    int device, B, debug;
+    long long launches;
+    long long last_sweeps;     // sweeps the previous step's fill needed (first chunk size)
+    int *h_counters;           // pinned [4]
+    double *d_stops;
+    int *d_ckpt;
+};
+
+namespace {
+constexpr int GRID_STOPS_CAP = 4096;
+constexpr int GRID_NPART = 64;
+
+struct GLayout {
+    size_t flags, z0, disp, real, parentL, ghostL, pts, stops, ckpt, scal, z, W, Q, cumdiff, cumhill, fdbg, rcv, don, cnt, l0, l1,
+        partial, total;
+    size_t NLP;
+    int LX, LY, LXP, ncol, W0, W1, W0p, W1p, nb;
+};
+
+bool grid_layout(const bl_lattice *lt, int B, int debug, GLayout &L)
+{
+    if (!lt || B <= 0 || lt->nx < 2 || lt->ny < 2 || (lt->nx & 1) || (lt->ny & 1)) return false;
+    L.LX = lt->nx + 2; L.LY = lt->ny + 2;
+    L.LXP = (int)rup((size_t)L.LX, 16);
+    L.NLP = rup((size_t)L.LY * L.LXP, 64);
+    L.ncol = (lt->nx / 2) * (lt->ny / 2);
+    L.W0 = (L.ncol + 31) / 32; L.W1 = (L.W0 + 31) / 32;
+    L.W0p = (int)rup((size_t)L.W1 * 32, 32); L.W1p = (int)rup((size_t)L.W1, 32);
+    L.nb = 2 * L.LX + 2 * lt->ny;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = rup(o + bytes, 256); return r; };
+    L.flags = take(L.NLP);
+    L.z0 = take(L.NLP * 8);
+    L.disp = take(L.NLP * 8);
+    L.real = take(L.NLP * 8);
+    L.parentL = take((size_t)L.nb * 4);
+    L.ghostL = take((size_t)L.nb * 4);
+    L.pts = take(BL_NPTS_MAX * 4);
+    L.stops = take((size_t)GRID_STOPS_CAP * 8);
+    L.ckpt = take((size_t)GRID_STOPS_CAP * 4);
+    L.scal = take((size_t)B * 128 + 256);
+    L.partial = take((size_t)B * GRID_NPART * 8);
+    L.z = take((size_t)B * L.NLP * 8);
+    L.W = take((size_t)B * L.NLP * 8);
+    L.Q = take((size_t)B * L.NLP * 8);
+    L.cumdiff = take((size_t)B * L.NLP * 8);
+    L.cumhill = take((size_t)B * L.NLP * 8);
+    L.fdbg = take(debug ? (size_t)B * L.NLP * 8 : 8);
+    L.rcv = take((size_t)B * L.NLP);
+    L.don = take((size_t)B * L.NLP);
+    L.cnt = take((size_t)B * L.NLP);
+    L.l0 = take((size_t)B * 4 * L.W0p * 4);
+    L.l1 = take((size_t)B * 4 * L.W1p * 4);
+    L.total = o;
+    return true;
+}
+} // namespace
+
+extern "C" size_t bl_grid_workspace_bytes(const bl_lattice *lt, int B, int debug)
+{
+    GLayout L;
+    return grid_layout(lt, B, debug, L) ? L.total : 0;
+}
+
+extern "C" int bl_grid_create(const bl_lattice *lt, const bl_params *p, int B, int device, void *workspace,
+                              size_t workspace_bytes, int debug, bl_grid **out)
+{
+    if (!lt || !p || !out || !workspace || !lt->z0 || !lt->flags) { g_err = "bl_grid_create: null argument"; return BL_ERR_ARG; }
+    GLayout L;
+    if (!grid_layout(lt, B, debug, L)) { g_err = "bl_grid_create: nx, ny must be even and >= 2, B > 0"; return BL_ERR_ARG; }
+    if (p->depo != 0 || p->nsea > 0 || p->CDr > 0.) {
+        g_err = "bl_grid_create: the lattice engine covers the erosive configuration only (depo = 0, constant sea level, CDr = 0)";
+        return BL_ERR_UNSUPPORTED;
+    }
+    if (p->npts > BL_NPTS_MAX) { g_err = "bl_grid_create: too many erdp points"; return BL_ERR_ARG; }
+    if (p->btype != 0 && !lt->parent) { g_err = "bl_grid_create: parent ids are needed for this boundary type"; return BL_ERR_ARG; }
+    if (workspace_bytes < L.total) { g_err = "bl_grid_create: workspace too small"; return BL_ERR_SPACE; }
+    CUDA_OK(cudaSetDevice(device));
+    char *ws = (char *)workspace;
+    const size_t Gn = (size_t)L.LX * L.LY;
+    // pitch the lattice rows
+    std::vector<unsigned char> flags(L.NLP, 0);
+    std::vector<double> z0(L.NLP, 0.), disp(L.NLP, 0.), real(L.NLP, 0.);
+    for (int J = 0; J < L.LY; ++J)
+        for (int I = 0; I < L.LX; ++I) {
+            const size_t s = (size_t)J * L.LX + I, d = (size_t)J * L.LXP + I;
+            flags[d] = lt->flags[s]; z0[d] = lt->z0[s];
+            if (lt->disp) disp[d] = lt->disp[s];
+            if (lt->real_elev) real[d] = lt->real_elev[s];
+        }
+    (void)Gn;
+    std::vector<int> ghostL(L.nb), parentL(L.nb, 0);
+    {
+        int k = 0;
+        for (int I = 0; I < L.LX; ++I) ghostL[k++] = I;                                    // south row
+        for (int J = 1; J <= lt->ny; ++J) ghostL[k++] = J * L.LXP;                          // x = -dx column
+        for (int I = 0; I < L.LX; ++I) ghostL[k++] = (L.LY - 1) * L.LXP + I;                // north row
+        for (int J = 1; J <= lt->ny; ++J) ghostL[k++] = J * L.LXP + (L.LX - 1);             // x = nx*dx column
+    }
+    if (lt->parent)
+        for (int k = 0; k < L.nb; ++k) {
+            const int s = lt->parent[k];
+            if (s < 0 || (size_t)s >= (size_t)L.LX * L.LY) { g_err = "bl_grid_create: parent index out of range"; return BL_ERR_ARG; }
+            parentL[k] = (s / L.LX) * L.LXP + (s % L.LX);
+        }
+    std::vector<int> pts(BL_NPTS_MAX, 0);
+    for (int i = 0; i < p->npts; ++i) pts[i] = p->pts_cell[i];
+#define UP(off, src, bytes) CUDA_OK(cudaMemcpy(ws + (off), (src), (bytes), cudaMemcpyHostToDevice))
+    UP(L.flags, flags.data(), L.NLP);
+    UP(L.z0, z0.data(), L.NLP * 8);
+    UP(L.disp, disp.data(), L.NLP * 8);
+    UP(L.real, real.data(), L.NLP * 8);
+    UP(L.parentL, parentL.data(), (size_t)L.nb * 4);
+    UP(L.ghostL, ghostL.data(), (size_t)L.nb * 4);
+    UP(L.pts, pts.data(), BL_NPTS_MAX * 4);
+#undef UP
+    CUDA_OK(cudaMemset(ws + L.scal, 0, (size_t)B * 128 + 256));
+    bl_grid *ctx = new bl_grid();
+    grid::GConst &g = ctx->g;
+    memset(&g, 0, sizeof(g));
+    g.nx = lt->nx; g.ny = lt->ny; g.LX = L.LX; g.LY = L.LY; g.LXP = L.LXP; g.B = B; g.hx = lt->nx / 2; g.ncol = L.ncol;
+    g.W0 = L.W0; g.W1 = L.W1; g.W0p = L.W0p; g.W1p = L.W1p; g.nb = L.nb; g.btype = p->btype; g.npts = p->npts;
+    g.has_parent = lt->parent ? 1 : 0;
+    g.NLP = L.NLP;
+    g.m = p->spl_m; g.n = p->spl_n; g.eps = p->eps; g.TH = p->fill_th; g.CDa = p->CDa; g.CDm = p->CDm;
+    g.minDT = p->minDT; g.maxDT = p->maxDT; g.hill = p->hill_cfl; g.sea = p->seapos; g.area = lt->area;
+    g.boff = (p->btype == 1) ? -0.1 : (p->btype == 3 ? 100. : 0.);
+    for (int s = 0; s < 8; ++s) { g.dist[s] = lt->dist[s]; g.vor[s] = lt->vor[s]; g.edge[s] = lt->edge[s]; }
+    g.flags = (const unsigned char *)(ws + L.flags);
+    g.z0 = (const double *)(ws + L.z0);
+    g.disp = lt->disp ? (const double *)(ws + L.disp) : nullptr;
+    g.real = lt->real_elev ? (const double *)(ws + L.real) : nullptr;
+    g.parentL = (const int *)(ws + L.parentL);
+    g.ghostL = (const int *)(ws + L.ghostL);
+    g.pts_cell = (const int *)(ws + L.pts);
+    g.z = (double *)(ws + L.z); g.W = (double *)(ws + L.W); g.Q = (double *)(ws + L.Q);
+    g.cumdiff = (double *)(ws + L.cumdiff); g.cumhill = (double *)(ws + L.cumhill);
+    g.fdbg = debug ? (double *)(ws + L.fdbg) : nullptr;
+    g.rcv = (unsigned char *)(ws + L.rcv); g.don = (unsigned char *)(ws + L.don); g.cnt = (unsigned *)(ws + L.cnt);
+    g.l0 = (unsigned *)(ws + L.l0); g.l1 = (unsigned *)(ws + L.l1);
+    {
+        char *s = ws + L.scal;
+        const size_t Bs = (size_t)B;
+        g.rain = (double *)s; g.erod = g.rain + Bs; g.tnow = g.erod + Bs; g.dt = g.tnow + Bs; g.lastdt = g.dt + Bs;
+        g.cflbits = (unsigned long long *)(g.lastdt + Bs);
+        g.steps = (long long *)(g.cflbits + Bs); g.sweeps = g.steps + Bs;
+        g.running = (int *)(g.sweeps + Bs); g.fill_active = g.running + Bs; g.change = g.fill_active + Bs;
+        g.si = g.change + Bs; g.ckflag = g.si + Bs; g.counters = g.ckflag + Bs;
+    }
+    g.partial = (double *)(ws + L.partial);
+    g.npart = GRID_NPART;
+    ctx->d_stops = (double *)(ws + L.stops);
+    ctx->d_ckpt = (int *)(ws + L.ckpt);
+    g.stops = ctx->d_stops; g.ckpt = ctx->d_ckpt; g.nstops = 0;
+    ctx->device = device; ctx->B = B; ctx->debug = debug; ctx->launches = 0; ctx->last_sweeps = 0;
+    CUDA_OK(cudaMallocHost((void **)&ctx->h_counters, 4 * sizeof(int)));
+    *out = ctx;
+    return BL_OK;
+}
+
+extern "C" int bl_grid_destroy(bl_grid *ctx)
+{
+    if (ctx) { if (ctx->h_counters) cudaFreeHost(ctx->h_counters); delete ctx; }
+    return BL_OK;
+}
+
+extern "C" int bl_grid_reset(bl_grid *ctx, const double *rain_dev, const double *erod_dev, double tStart, void *stream)
+{
+    if (!ctx || !rain_dev || !erod_dev) { g_err = "bl_grid_reset: null argument"; return BL_ERR_ARG; }
+    CUDA_OK(cudaSetDevice(ctx->device));
+    const grid::GConst &g = ctx->g;
+    dim3 gr((unsigned)((g.NLP + 255) / 256), (unsigned)ctx->B);
+    grid::k_reset<<<gr, 256, 0, (cudaStream_t)stream>>>(g, rain_dev, erod_dev, tStart);
+    ctx->launches++;
+    ctx->last_sweeps = 0;
+    CUDA_OK(cudaGetLastError());
+    return BL_OK;
+}
+
+namespace {
+// one time step for every running proposal; returns the number of proposals still running afterwards (via h_counters)
+int grid_one_step(bl_grid *ctx, double *out_pts, double *out_sse, double *out_elev, double *out_erdp, int nck, cudaStream_t st)
+{
+    const grid::GConst &g = ctx->g;
+    const int B = ctx->B;
+    const dim3 b2(32, 8), g2((unsigned)((g.LX + 31) / 32), (unsigned)((g.LY + 7) / 8), (unsigned)B);
+    const dim3 g2p((unsigned)((g.LXP + 31) / 32), (unsigned)((g.LY + 7) / 8), (unsigned)B);
+    const dim3 g1((unsigned)((std::max((size_t)g.LY * g.LXP, (size_t)4 * g.W0p) + 255) / 256), (unsigned)B);
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const long long ntask = (long long)B * g.W1;
+    const int pass_blocks = (int)std::max<long long>(1, std::min<long long>((ntask + 7) / 8, (long long)nsm * 8));
+    grid::k_fill_init<<<g1, 256, 0, st>>>(g);
+    grid::k_fill_begin<<<1, 256, 0, st>>>(g);
+    ctx->launches += 2;
+    long long done = 0, chunk = std::max<long long>(2, std::min<long long>(ctx->last_sweeps, 4096));
+    for (;;) {
+        for (long long s = 0; s < chunk; ++s) {
+            for (int c = 0; c < 4; ++c) grid::k_fill_pass<<<pass_blocks, 256, 0, st>>>(g, c);
+            grid::k_fill_end<<<1, 256, 0, st>>>(g);
+        }
+        ctx->launches += 5 * chunk;
+        done += chunk;
+        CUDA_OK(cudaMemcpyAsync(ctx->h_counters, g.counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        if (ctx->h_counters[1] == 0) break;
+        if (done > 50000000) { g_err = "bl_grid: depression filling did not terminate"; return BL_ERR_CUDA; }
+        chunk = std::max<long long>(8, std::min<long long>(done / 4, 1024));
+    }
+    ctx->last_sweeps = ctx->h_counters[2] + 1;   // the next step's first chunk: landscapes change slowly
+    grid::k_sfd<<<g2, b2, 0, st>>>(g);
+    grid::k_donors<<<g2p, b2, 0, st>>>(g);
+    grid::k_discharge<<<g2, b2, 0, st>>>(g);
+    grid::k_cfl<<<g2, b2, 0, st>>>(g);
+    grid::k_dt<<<(B + 127) / 128, 128, 0, st>>>(g);
+    grid::k_erode<<<g2, b2, 0, st>>>(g);
+    ctx->launches += 6;
+    if (g.btype == 0 || !g.has_parent) {
+        grid::k_diffuse<1><<<g2, b2, 0, st>>>(g);
+        ctx->launches += 1;
+    } else {
+        grid::k_diffuse<0><<<g2, b2, 0, st>>>(g);
+        grid::k_boundary<<<dim3((unsigned)((g.nb + 127) / 128), (unsigned)B), 128, 0, st>>>(g);
+        ctx->launches += 2;
+        if (g.disp) {
+            grid::k_uplift<<<dim3((unsigned)(((size_t)g.LY * g.LXP + 255) / 256), (unsigned)B), 256, 0, st>>>(g);
+            ctx->launches += 1;
+        }
+    }
+    grid::k_advance<<<1, 256, 0, st>>>(g, 1, 0);
+    grid::k_ckpt<<<dim3(GRID_NPART, (unsigned)B), 256, 0, st>>>(g, out_elev, out_erdp, nck);
+    grid::k_ckpt_final<<<B, 32, 0, st>>>(g, out_sse, out_pts);
+    ctx->launches += 3;
+    CUDA_OK(cudaGetLastError());
+    return BL_OK;
+}
+
+int grid_run_common(bl_grid *ctx, int nstops, const double *stops, const int32_t *ckpt, double *out_pts, double *out_sse,
+                    double *out_elev, double *out_erdp, int nck, int single, cudaStream_t st)
+{
+    if (!ctx || nstops <= 0 || !stops) { g_err = "bl_grid_run: bad arguments"; return BL_ERR_ARG; }
+    if (nstops > GRID_STOPS_CAP) { g_err = "bl_grid_run: too many stops"; return BL_ERR_ARG; }
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::vector<int> ck(nstops, -1);
+    if (ckpt)
+        for (int i = 0; i < nstops; ++i) {
+            ck[i] = ckpt[i];
+            if (ck[i] >= BL_NCKPT_MAX || ((out_elev || out_erdp) && ck[i] >= nck)) {
+                g_err = "bl_grid_run: checkpoint index too large"; return BL_ERR_ARG;
+            }
+        }
+    CUDA_OK(cudaMemcpyAsync(ctx->d_stops, stops, (size_t)nstops * 8, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(ctx->d_ckpt, ck.data(), (size_t)nstops * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    ctx->g.nstops = nstops;
+    const grid::GConst &g = ctx->g;
+    // stops already reached count as checkpoints without a step (run_to_time(t <= tNow))
+    grid::k_advance<<<1, 256, 0, st>>>(g, 0, 1);
+    grid::k_ckpt<<<dim3(GRID_NPART, (unsigned)ctx->B), 256, 0, st>>>(g, out_elev, out_erdp, nck);
+    grid::k_ckpt_final<<<ctx->B, 32, 0, st>>>(g, out_sse, out_pts);
+    ctx->launches += 3;
+    CUDA_OK(cudaMemcpyAsync(ctx->h_counters, g.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    long long guard = 0;
+    while (ctx->h_counters[0] > 0) {
+        int rc = grid_one_step(ctx, out_pts, out_sse, out_elev, out_erdp, nck, st);
+        if (rc != BL_OK) return rc;
+        CUDA_OK(cudaMemcpyAsync(ctx->h_counters, g.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        if (single) break;
+        if (++guard > 100000000) { g_err = "bl_grid_run: step guard"; return BL_ERR_CUDA; }
+    }
+    return BL_OK;
+}
+} // namespace
+
+extern "C" int bl_grid_run(bl_grid *ctx, int nstops, const double *stops, const int32_t *ckpt, double *out_pts,
+                           double *out_sse, double *out_elev, double *out_erdp, int nck, void *stream)
+{
+    return grid_run_common(ctx, nstops, stops, ckpt, out_pts, out_sse, out_elev, out_erdp, nck, 0, (cudaStream_t)stream);
+}
+
+extern "C" int bl_grid_step(bl_grid *ctx, double tStop, void *stream)
+{
+    return grid_run_common(ctx, 1, &tStop, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 1, (cudaStream_t)stream);
+}
+
+extern "C" int bl_grid_get_field(bl_grid *ctx, int field, int proposal, void *dst, void *stream)
+{
+    if (!ctx || !dst || proposal < 0 || proposal >= ctx->B) { g_err = "bl_grid_get_field: bad arguments"; return BL_ERR_ARG; }
+    CUDA_OK(cudaSetDevice(ctx->device));
+    const grid::GConst &g = ctx->g;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t base = (size_t)proposal * g.NLP;
+    const double *fsrc = nullptr;
+    switch (field) {
+        case BL_F_Z: fsrc = g.z; break;
+        case BL_F_CUMDIFF: fsrc = g.cumdiff; break;
+        case BL_F_CUMHILL: fsrc = g.cumhill; break;
+        case BL_F_FILLH:
+            if (!g.fdbg) { g_err = "bl_grid_get_field: fillH is kept only by a debug context"; return BL_ERR_UNSUPPORTED; }
+            fsrc = g.fdbg; break;
+        case BL_F_Q: fsrc = g.Q; break;
+        case BL_F_RCV: break;
+        default: g_err = "bl_grid_get_field: field not kept by the lattice engine"; return BL_ERR_UNSUPPORTED;
+    }
+    if (fsrc) {   // strip the row pitch
+        CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)g.LX * 8, fsrc + base, (size_t)g.LXP * 8, (size_t)g.LX * 8, g.LY,
+                                  cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        return BL_OK;
+    }
+    std::vector<unsigned char> code((size_t)g.LX * g.LY);
+    CUDA_OK(cudaMemcpy2DAsync(code.data(), (size_t)g.LX, g.rcv + base, (size_t)g.LXP, (size_t)g.LX, g.LY, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    static const int di[8] = {1, 1, 0, -1, -1, -1, 0, 1}, dj[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+    int32_t *out = (int32_t *)dst;                       // receiver as a lattice cell index J*LX + I
+    for (int J = 0; J < g.LY; ++J)
+        for (int I = 0; I < g.LX; ++I) {
+            const int s = code[(size_t)J * g.LX + I];
+            out[(size_t)J * g.LX + I] = (s == 8) ? J * g.LX + I : (J + dj[s]) * g.LX + (I + di[s]);
+        }
+    return BL_OK;
+}
+
+extern "C" int bl_grid_get_scalars(bl_grid *ctx, double *tnow, int64_t *steps, int64_t *sweeps, double *last_dt, void *stream)
+{
+    if (!ctx) { g_err = "bl_grid_get_scalars: null ctx"; return BL_ERR_ARG; }
+    CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = ctx->B;
+    if (tnow) CUDA_OK(cudaMemcpyAsync(tnow, ctx->g.tnow, B * 8, cudaMemcpyDeviceToHost, st));
+    if (steps) CUDA_OK(cudaMemcpyAsync(steps, ctx->g.steps, B * 8, cudaMemcpyDeviceToHost, st));
+    if (sweeps) CUDA_OK(cudaMemcpyAsync(sweeps, ctx->g.sweeps, B * 8, cudaMemcpyDeviceToHost, st));
+    if (last_dt) CUDA_OK(cudaMemcpyAsync(last_dt, ctx->g.lastdt, B * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return BL_OK;
+}
+
+extern "C" int64_t bl_grid_launch_count(const bl_grid *ctx) { return ctx ? ctx->launches : 0; }

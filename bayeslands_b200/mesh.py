@@ -390,12 +390,41 @@ def _colour_order(points: np.ndarray, nb: int) -> np.ndarray:
     return np.concatenate((np.arange(nb), inner2[np.lexsort((rank[inner2], level[inner2]))]))
 
 
-def build_regular(nx: int, ny: int, dx: float, z: np.ndarray, btype: str = "fixed") -> MeshArrays:
+def regular_interior_ids(nx: int, ny: int, order: str = "row") -> np.ndarray:
+    """(ny, nx) ids (0-based, before adding boundsPt) of the interior nodes of a regular lattice.
+
+    "row": row-major, x fastest.  "colour": by 2x2 parity class c = (j&1)*2 + (i&1), row-major inside a class -
+    no two D8 neighbours share a class, so fillPD's ascending-id Gauss-Seidel sweep (PDalgo.f90:49-81) has 4
+    dependency levels whatever the lattice size (what the lattice engine emulates exactly)."""
+    if order == "row":
+        return np.arange(nx * ny, dtype=np.int64).reshape(ny, nx)
+    if order != "colour":
+        raise ValueError("order must be 'row' or 'colour'")
+    if nx % 2 or ny % 2:
+        raise ValueError("colour order needs even nx, ny")
+    j, i = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    c = (j & 1) * 2 + (i & 1)
+    return c * ((nx // 2) * (ny // 2)) + (j >> 1) * (nx // 2) + (i >> 1)
+
+
+def regular_ext_ids(nx: int, ny: int, order: str = "row") -> np.ndarray:
+    """(ny+2, nx+2) mesh id of every cell of the extended lattice (ghost ring in raster2TIN order first)."""
+    nb = 2 * (nx + 2) + 2 * ny
+    ext = np.full((ny + 2, nx + 2), -1, dtype=np.int64)
+    ext[0, :] = np.arange(nx + 2)
+    ext[1:-1, 0] = nx + 2 + np.arange(ny)
+    ext[-1, :] = nx + 2 + ny + np.arange(nx + 2)
+    ext[1:-1, -1] = 2 * (nx + 2) + ny + np.arange(ny)
+    ext[1:-1, 1:-1] = nb + regular_interior_ids(nx, ny, order)
+    return ext
+
+
+def build_regular(nx: int, ny: int, dx: float, z: np.ndarray, btype: str = "fixed", order: str = "row") -> MeshArrays:
     """Synthetic regular-grid landscape (BASELINE config 5): D8 stencil as the neighbour list.
 
     Documented deviation: the reference has no regular-grid mode.  Node order: ghost
-    ring first (same order as raster2TIN), then the nx*ny grid row-major (x fastest).  FV arrays are
-    analytic: area dx^2, Voronoi edge dx for the 4 axis neighbours and 0 for the diagonals.
+    ring first (same order as raster2TIN), then the nx*ny grid in `order` (see regular_interior_ids).  FV
+    arrays are analytic: area dx^2, Voronoi edge dx for the 4 axis neighbours and 0 for the diagonals.
     """
     z = np.asarray(z, dtype=np.float64).reshape(ny, nx)
     xs = dx * np.arange(nx)
@@ -408,15 +437,13 @@ def build_regular(nx: int, ny: int, dx: float, z: np.ndarray, btype: str = "fixe
     bounds = np.vstack((bsouth, beast, bnorth, bwest))
     nb = len(bounds)
     X, Y = np.meshgrid(xs, ys, indexing="xy")
-    pts = np.vstack((bounds, np.column_stack((X.ravel(), Y.ravel()))))
-    N = len(pts)
     # id lookup on the (ny+2, nx+2) extended lattice
-    ext = np.full((ny + 2, nx + 2), -1, dtype=np.int64)
-    ext[0, :] = np.arange(nx + 2)
-    ext[1:-1, 0] = nx + 2 + np.arange(ny)
-    ext[-1, :] = nx + 2 + ny + np.arange(nx + 2)
-    ext[1:-1, -1] = 2 * (nx + 2) + ny + np.arange(ny)
-    ext[1:-1, 1:-1] = nb + np.arange(nx * ny).reshape(ny, nx)
+    ext = regular_ext_ids(nx, ny, order)
+    N = nb + nx * ny
+    pts = np.zeros((N, 2))
+    pts[:nb] = bounds
+    pts[ext[1:-1, 1:-1].ravel(), 0] = X.ravel()
+    pts[ext[1:-1, 1:-1].ravel(), 1] = Y.ravel()
     ngb = np.full((N, KP), -2, dtype=np.int32)
     elen = np.zeros((N, KP)); vor = np.zeros((N, KP))
     offs = [(0, 1, dx, dx), (1, 1, dx * np.sqrt(2.0), 0.0), (1, 0, dx, dx), (1, -1, dx * np.sqrt(2.0), 0.0),
@@ -443,7 +470,7 @@ def build_regular(nx: int, ny: int, dx: float, z: np.ndarray, btype: str = "fixe
     rg = RecGrid(regX=xs, regY=ys, regZ=z.T.copy(), resEdges=float(dx), areaDel=float(dx * dx), nx=nx, ny=ny,
                  rnx=nx, rny=ny, boundsPt=nb, edgesPt=2 * nx + 2 * (ny - 2))
     elev = np.full(N, -1.0e6)
-    elev[nb:] = z.ravel()
+    elev[ext[1:-1, 1:-1].ravel()] = z.ravel()
     elev, parent = _boundary_elevation(elev, ngb, elen, nb, btype)
     borders, borders2, inside = _masks(fv, rg)
     # grid table: every (ny+2, nx+2) output cell is exactly a node
@@ -454,4 +481,5 @@ def build_regular(nx: int, ny: int, dx: float, z: np.ndarray, btype: str = "fixe
     return MeshArrays(recGrid=rg, FVmesh=fv, elevation=elev, parentIDs=parent.astype(np.int32), borders=borders,
                       borders2=borders2, insideIDs=inside, btype=btype, grid_nx=nx + 2, grid_ny=ny + 2,
                       grid_idx=idx, grid_w=w, grid_exact=exact,
-                      hillslope_min_edge2=float(np.amin(elen[elen > 0.0] ** 2)))
+                      hillslope_min_edge2=float(np.amin(elen[elen > 0.0] ** 2)),
+                      extra=dict(regular=dict(nx=nx, ny=ny, dx=float(dx), order=order, ext=ext)))

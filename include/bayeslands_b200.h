@@ -148,6 +148,42 @@ int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst_host, void *stream);
 /* number of kernel launches issued by this context so far (for bench.py's gpu_launches) */
 int64_t bl_launch_count(const bl_ctx *ctx);
 
+/* ---- lattice engine: regular D8 lattice too large for one CTA (BASELINE config 5) -------------
+ * Same reference path as above for the purely erosive configuration (flow.depo = 0, constant sea level): every
+ * phase of the time step is a grid-wide kernel batched over all proposals.  Nodes are the (ny+2) x (nx+2) lattice
+ * including the ghost ring, stored row-major (x fastest); mesh ids are those of mesh.build_regular(order="colour")
+ * (ghost ring in raster2TIN order, interior nodes by 2x2 parity class), which define fillPD's sweep order
+ * (PDalgo.f90:49-81) and the donor summation order of the discharge (FLOWalgo.f90:53-81). */
+typedef struct {
+    int32_t nx, ny;            /* interior lattice size, both even */
+    double dist[8];            /* |xy(d) - xy(r)| per D8 slot E,NE,N,NW,W,SW,S,SE (FLOWalgo.f90:299-330, :640-650) */
+    double vor[8], edge[8];    /* FVmesh.vor_edges / edge_length per slot for interior nodes */
+    double area;               /* FVmesh.control_volumes of interior nodes */
+    const double *z0;          /* [(ny+2)*(nx+2)] initial elevation, lattice order, HOST */
+    const uint8_t *flags;      /* [(ny+2)*(nx+2)] bit0 flow.borders, bit1 flow.borders2 (buildFlux.py:139-151) */
+    const double *disp;        /* lattice order displacement rate (m/a) or NULL */
+    const int32_t *parent;     /* [2*(nx+2)+2*ny] lattice cell of each ghost node's parent (flow.parentIDs) or NULL */
+    const double *real_elev;   /* lattice order observed topography or NULL */
+} bl_lattice;
+
+typedef struct bl_grid bl_grid;
+
+size_t bl_grid_workspace_bytes(const bl_lattice *lat, int B, int debug);
+/* debug != 0 keeps a copy of fillH per step for bl_grid_get_field (8 more bytes per node per proposal). */
+int bl_grid_create(const bl_lattice *lat, const bl_params *par, int B, int device, void *workspace,
+                   size_t workspace_bytes, int debug, bl_grid **out);
+int bl_grid_destroy(bl_grid *ctx);
+int bl_grid_reset(bl_grid *ctx, const double *rain_dev, const double *erod_dev, double tStart, void *stream);
+/* as bl_run; grids are [B][nck][(ny+2)*(nx+2)] in lattice order */
+int bl_grid_run(bl_grid *ctx, int nstops, const double *stops, const int32_t *ckpt, double *out_pts,
+                double *out_sse, double *out_elev, double *out_erdp, int nck, void *stream);
+int bl_grid_step(bl_grid *ctx, double tStop, void *stream);
+/* BL_F_Z / CUMDIFF / CUMHILL / Q / FILLH (debug contexts) as double, BL_F_RCV as int32 lattice cell, lattice order */
+int bl_grid_get_field(bl_grid *ctx, int field, int proposal, void *dst_host, void *stream);
+int bl_grid_get_scalars(bl_grid *ctx, double *tnow, int64_t *steps, int64_t *fill_sweeps, double *last_dt,
+                        void *stream);
+int64_t bl_grid_launch_count(const bl_grid *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,96 @@
+"""Lattice engine (`bl_grid_*`, BASELINE config 5) against the CPU oracle, bit for bit, through the C-ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+FP = ("z", "fillH", "Q", "cumdiff", "cumhill")
+
+
+def synthetic(nx, ny, dx=100.0, btype="fixed", T=200000.0, seed=1234, amp=1.0):
+    """SURVEY.md 8d C5 in miniature: z0 = 10 + U(0,1), sin-bump uplift, dep = 0, mountain.xml creep values."""
+    from bayeslands_b200 import config, mesh, forcing, lattice
+    rng = np.random.default_rng(seed)
+    z0 = 10.0 + amp * rng.uniform(0, 1, (ny, nx))
+    m = mesh.build_regular(nx, ny, dx, z0, btype=btype, order="colour")
+    xml = str(np.load(os.path.join(ROOT, "data", "crater_fast.npz"))["xml"])
+    xml = xml.replace("<end>15000.</end>", "<end>%r</end>" % T).replace("<rend>15000.</rend>", "<rend>%r</rend>" % T)
+    xml = xml.replace("<display>5000.</display>", "<display>%r</display>" % (T / 4)).replace("<fillmax>15.</fillmax>", "<dep>0</dep>")
+    xml = xml.replace("<caerial>2.e-2</caerial>", "<caerial>8.e-1</caerial>").replace("<cmarine>5.e-2</cmarine>", "<cmarine>1.</cmarine>")
+    if btype != "fixed":
+        xml = xml.replace("<boundary>fixed</boundary>", "<boundary>%s</boundary>" % btype)
+    inp = config.parse_xml(xml)
+    assert inp.depo == 0 and inp.btype == btype
+    X, Y = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    bump = 1e-3 * T * np.sin(np.pi * X / (nx - 1)) * np.sin(np.pi * Y / (ny - 1))
+    disp = forcing.load_tecto_map(m, bump.T.ravel(order="F"), 0.0, T)
+    return m, inp, disp, lattice.from_mesh(m, disp)
+
+
+@pytest.mark.parametrize("btype,nx,ny", [("fixed", 48, 32), ("slope", 40, 36), ("fixed", 130, 96)])
+def test_lattice_stepwise_bit_exact(btype, nx, ny):
+    from bayeslands_b200.grid_engine import GridEngine
+    from oracle import oracle
+    m, inp, disp, lat = synthetic(nx, ny, btype=btype)
+    rain = np.array([0.6, 1.5, 2.4]); erod = np.array([3.2e-6, 5e-6, 6.8e-6])
+    eng = GridEngine(lat, inp, 3, debug=True)
+    eng.reset(rain, erod)
+    oms = [oracle.OracleModel(m, inp, seed=1, disp=disp) for _ in range(3)]
+    for b, om in enumerate(oms):
+        om.reset(rain[b], erod[b], seed=1)
+    for step in range(6):
+        eng.step(200000.0)
+        sc = eng.scalars()
+        for b, om in enumerate(oms):
+            om.streamflow(); om.sediment_flux(200000.0)
+            assert np.array_equal(eng.field("rcv", b), om.rcv), (step, b, "rcv")
+            for f in FP:
+                assert np.array_equal(eng.field(f, b), getattr(om, f)), (step, b, f)
+            assert sc["tNow"][b] == om.tNow and sc["steps"][b] == step + 1
+
+
+def test_lattice_full_run_and_likelihood():
+    """run_schedule over the blackBox checkpoints: ragged adaptive stepping, grids and SSE against the oracle."""
+    from bayeslands_b200.grid_engine import GridEngine
+    from oracle import oracle
+    T = 60000.0
+    m, inp, disp, lat = synthetic(36, 28, T=T)
+    rain = np.array([0.3, 1.1, 1.9, 2.7]); erod = np.array([3.0e-6, 4.5e-6, 5.0e-5, 2.0e-4])  # the last two are flow-CFL bound
+    truth = oracle.OracleModel(m, inp, seed=1, disp=disp)
+    truth.reset(1.5, 5e-6, seed=1)
+    truth.run_to_time(T)
+    ext = lat.ext
+    real = truth.z[ext]                                   # lattice-order "observed" topography
+    eng = GridEngine(lat, inp, 4, real_elev=real)
+    eng.reset(rain, erod)
+    times = [T / 4, T / 2, 3 * T / 4, T]
+    _, sse, elev, erdp = eng.run_schedule(times, grids=True)
+    sse = sse.cpu().numpy(); elev = elev.cpu().numpy(); erdp = erdp.cpu().numpy()
+    sc = eng.scalars()
+    for b in range(4):
+        om = oracle.OracleModel(m, inp, seed=1, disp=disp)
+        om.reset(rain[b], erod[b], seed=1)
+        for ci, t in enumerate(times):
+            om.run_to_time(t)
+            assert np.array_equal(elev[b, ci], om.z[ext].ravel()), (b, ci)
+            assert np.array_equal(erdp[b, ci], om.cumdiff[ext].ravel()), (b, ci)
+        assert sc["tNow"][b] == T and sc["steps"][b] == om.steps
+        want = float(np.sum((om.z[ext] - real) ** 2))
+        assert abs(sse[b] - want) <= 1e-11 * max(1.0, abs(want))
+    assert len(set(sc["steps"].tolist())) > 1            # the proposals really took different numbers of steps
+
+
+def test_lattice_engine_rejects_out_of_scope():
+    from bayeslands_b200 import _lib, config, lattice
+    from bayeslands_b200.grid_engine import GridEngine
+    xml = str(np.load(os.path.join(ROOT, "data", "crater_fast.npz"))["xml"])
+    inp = config.parse_xml(xml)                            # depo = 1
+    lat = lattice.regular(16, 12, 100.0, np.zeros((12, 16)))
+    with pytest.raises(_lib.BlError):
+        GridEngine(lat, inp, 2)
+    with pytest.raises(ValueError):
+        lattice.regular(15, 12, 100.0, np.zeros((12, 15)))

@@ -87,3 +87,32 @@ def test_engine_fails_loudly_without_gpu():
     from bayeslands_b200.engine import Engine
     with pytest.raises(_lib.BlError):
         Engine(None, None, 1)
+
+
+def test_lattice_arrays_match_the_mesh_builder():
+    """`lattice.regular` (no neighbour tables; what the 2048 x 2048 config uses) == `lattice.from_mesh` of
+    `mesh.build_regular(order="colour")` + `forcing.load_tecto_map`; colour order is a pure renumbering."""
+    from bayeslands_b200 import mesh, forcing, lattice
+    nx, ny, dx, T = 14, 10, 100.0, 1000.0
+    rng = np.random.default_rng(5)
+    z0 = 10.0 + rng.uniform(0, 1, (ny, nx))
+    X, Y = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    bump = 1e-3 * T * np.sin(np.pi * X / (nx - 1)) * np.sin(np.pi * Y / (ny - 1))
+    for btype in ("fixed", "wall"):
+        m = mesh.build_regular(nx, ny, dx, z0, btype=btype, order="colour")
+        disp = forcing.load_tecto_map(m, bump.T.ravel(order="F"), 0.0, T)
+        a = lattice.from_mesh(m, disp)
+        b = lattice.regular(nx, ny, dx, z0, btype=btype, disp_rate=a.disp[1:-1, 1:-1])
+        for f in ("dist", "vor", "edge", "z0", "flags", "parent", "disp"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), (btype, f)
+        assert a.area == b.area and a.hillslope_min_edge2 == b.hillslope_min_edge2
+    # row-major and colour-major meshes are the same landscape under a permutation of the node ids
+    r = mesh.build_regular(nx, ny, dx, z0, order="row")
+    c = mesh.build_regular(nx, ny, dx, z0, order="colour")
+    perm = np.empty(r.N, dtype=np.int64)
+    perm[r.extra["regular"]["ext"].ravel()] = c.extra["regular"]["ext"].ravel()
+    assert np.array_equal(r.elevation, c.elevation[perm]) and np.array_equal(r.borders2, c.borders2[perm])
+    with pytest.raises(ValueError):
+        lattice.from_mesh(r)
+    # the interior uplift rate interpolated by load_tecto_map is the map itself on a lattice = DEM grid
+    assert np.allclose(a.disp[1:-1, 1:-1], bump / T, rtol=0, atol=1e-18)
