@@ -22,6 +22,8 @@
 
 namespace grid {
 
+constexpr int CHS = 32;   // ints between the `change` flags of two proposals (one line each: they are stored to by every warp)
+
 struct GConst {
     int nx, ny, LX, LY, LXP, B, hx, ncol, W0, W1, nb, btype, npts, has_parent;
     size_t NLP;                 // LY*LXP rounded up: length of one per-proposal array
@@ -34,7 +36,10 @@ struct GConst {
     double *z, *W, *Q, *cumdiff, *cumhill, *fdbg; // [B][NLP]
     unsigned char *rcv, *don;   // [B][NLP] receiver slot (8 = self), donor mask
     unsigned *cnt;              // [B][NLP/4] arrival counters, one byte per node
-    unsigned *l0, *l1;          // [B][4][W0p], [B][4][W1p] pending bitmaps
+    unsigned *l0;               // [B][4][W0p] pending bitmaps
+    unsigned *wl;               // [4][wlcap] rings of non-empty bitmap words (entry = p*W0 + word)
+    void *wlctl;                // [4] ring head / tail / snapshot
+    unsigned long long wlcap;   // power of two >= B*W0
     int W0p, W1p;
     double *rain, *erod, *tnow, *dt, *lastdt, *partial;
     unsigned long long *cflbits;
@@ -87,7 +92,7 @@ __global__ void k_reset(GConst g, const double *rain, const double *erod, double
     }
     if (L == 0) {
         g.rain[p] = rain[p]; g.erod[p] = erod[p]; g.tnow[p] = tStart; g.dt[p] = 0.; g.lastdt[p] = 0.;
-        g.steps[p] = 0; g.sweeps[p] = 0; g.running[p] = 0; g.fill_active[p] = 0; g.change[p] = 0; g.si[p] = 0; g.ckflag[p] = 0;
+        g.steps[p] = 0; g.sweeps[p] = 0; g.running[p] = 0; g.fill_active[p] = 0; g.change[p * CHS] = 0; g.si[p] = 0; g.ckflag[p] = 0;
     }
 }
 
@@ -117,11 +122,27 @@ __global__ void k_advance(GConst g, int do_step, int restart)
 }
 
 // ---- depression filling ----------------------------------------------------------------------------------
+// Pending nodes: one bit per node in a per-(proposal, colour) bitmap, and per colour a ring of the bitmap WORDS that
+// hold at least one bit (a word enters the ring when its first bit is set, leaves it when the colour's pass consumes
+// it), so a pass is one warp per non-empty word - no scanning, work proportional to the front.
+struct WlCtl { unsigned long long head, tail, snap, pad[13]; };   // one 128-byte line per colour: tail is an atomic hot spot
+
 __global__ void k_fill_init(GConst g)
 {
     const int p = blockIdx.y;
-    if (!g.running[p]) { if (blockIdx.x == 0 && threadIdx.x == 0) g.fill_active[p] = 0; return; }
     const size_t L = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (L < (size_t)4 * g.W0) {                                      // every word of every colour starts in its ring
+        const int c = (int)(L / g.W0), w = (int)(L % g.W0);
+        unsigned m = 0xFFFFFFFFu;
+        if (w * 32 + 32 > g.ncol) m = (1u << (g.ncol - w * 32)) - 1u;
+        g.l0[((size_t)p * 4 + c) * g.W0p + w] = m;
+        g.wl[(size_t)c * g.wlcap + (size_t)p * g.W0 + w] = (unsigned)((size_t)p * g.W0 + w);
+    }
+    if (p == 0 && L < 4) {
+        WlCtl *ctl = (WlCtl *)g.wlctl + L;
+        ctl->head = 0; ctl->snap = 0; ctl->tail = (unsigned long long)g.B * g.W0;
+    }
+    if (!g.running[p]) { if (L == 0) g.fill_active[p] = 0; return; }
     if (L < (size_t)g.LY * g.LXP) {
         const int I = (int)(L % g.LXP), J = (int)(L / g.LXP);
         if (I < g.LX) {
@@ -129,74 +150,96 @@ __global__ void k_fill_init(GConst g)
             g.W[o] = is_ghost(g, I, J) ? g.z[o] : 1.e6;                    // PDalgo.f90:19-35
         }
     }
-    if (L < (size_t)4 * g.W0p) {
-        const int c = (int)(L / g.W0p), w = (int)(L % g.W0p);
-        unsigned m = 0u;
-        if (w < g.W0) { m = 0xFFFFFFFFu; if (w * 32 + 32 > g.ncol) m = (1u << (g.ncol - w * 32)) - 1u; }
-        g.l0[((size_t)p * 4 + c) * g.W0p + w] = m;
-    }
-    if (L < (size_t)4 * g.W1p) {
-        const int c = (int)(L / g.W1p), w = (int)(L % g.W1p);
-        unsigned m = 0u;
-        if (w < g.W1) { m = 0xFFFFFFFFu; if (w * 32 + 32 > g.W0) m = (1u << (g.W0 - w * 32)) - 1u; }
-        g.l1[((size_t)p * 4 + c) * g.W1p + w] = m;
-    }
     if (L == 0) {
-        g.fill_active[p] = 1; g.change[p] = 0;
+        g.fill_active[p] = 1; g.change[p * CHS] = 0;
         g.cflbits[p] = (unsigned long long)__double_as_longlong(1.e6);
     }
 }
 
-// one colour pass of the Gauss-Seidel sweep (PDalgo.f90:37-91).  One warp per level-1 bitmap word (1024 nodes of
-// the colour); pending nodes of the same colour are never adjacent, so the pass is race free.
+// one colour pass of the Gauss-Seidel sweep (PDalgo.f90:37-91): one warp per pending bitmap word.  Nodes of one
+// colour are never adjacent, so the pass is race free and equals the sequential sweep over that id range.
 __global__ void __launch_bounds__(256) k_fill_pass(GConst g, int c)
 {
     if (g.counters[1] == 0) return;
+    WlCtl *ctl = (WlCtl *)g.wlctl;
+    const unsigned long long h = ctl[c].head, t = ctl[c].tail;      // nobody appends to colour c during its own pass
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl[c].snap = t;
+        const int cp = (c + 3) & 3;
+        ctl[cp].head = ctl[cp].snap;                                // retire what the previous pass consumed
+    }
     const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long ntask = (long long)g.B * g.W1;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     const int hx = g.hx, LXP = g.LXP;
     const double eps = g.eps, TH = g.TH, sea = g.sea;
-    for (long long t = warp; t < ntask; t += nwarps) {
-        const int p = (int)(t / g.W1), w1 = (int)(t % g.W1);
-        if (!g.fill_active[p]) continue;
-        unsigned *L1 = g.l1 + ((size_t)p * 4 + c) * g.W1p;
-        unsigned m1 = 0u;
-        if (lane == 0) { m1 = L1[w1]; if (m1) L1[w1] = 0u; }
-        m1 = __shfl_sync(0xffffffffu, m1, 0);
-        if (!m1) continue;
-        unsigned *L0 = g.l0 + ((size_t)p * 4 + c) * g.W0p + (size_t)w1 * 32;
-        unsigned w0 = 0u;
-        if ((m1 >> lane) & 1u) { w0 = L0[lane]; if (w0) L0[lane] = 0u; }
-        unsigned nz = __ballot_sync(0xffffffffu, w0 != 0u);
-        double *W = g.W + (size_t)p * g.NLP;
-        const double *z = g.z + (size_t)p * g.NLP;
-        int loc = 0;
-        while (nz) {
-            const int src = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const unsigned word = __shfl_sync(0xffffffffu, w0, src);
-            if (!((word >> lane) & 1u)) continue;
-            const int q = (w1 * 32 + src) * 32 + lane;
+    const unsigned *ring = g.wl + (size_t)c * g.wlcap;
+    for (unsigned long long e = h + warp; e < t; e += nwarps) {
+        const unsigned ent = ring[e & (g.wlcap - 1)];
+        const int p = (int)(ent / (unsigned)g.W0), w = (int)(ent % (unsigned)g.W0);
+        if (!__ldg(g.fill_active + p)) continue;
+        unsigned *L0 = g.l0 + ((size_t)p * 4 + c) * g.W0p + w;
+        unsigned word = 0u;
+        if (lane == 0) { word = *L0; *L0 = 0u; }
+        word = __shfl_sync(0xffffffffu, word, 0);
+        int loc = 0, changed = 0;
+        if ((word >> lane) & 1u) {
+            double *W = g.W + (size_t)p * g.NLP;
+            const double *z = g.z + (size_t)p * g.NLP;
+            const int q = w * 32 + lane;
             const int qy = q / hx, qx = q - qy * hx;
             const int i = 2 * qx + (c & 1), j = 2 * qy + (c >> 1);
             const size_t L = (size_t)(j + 1) * LXP + (i + 1);
             const double wk = W[L], zk = z[L];
-            if (!(wk > zk)) continue;
-            const double *r0 = W + L - LXP, *r2 = W + L + LXP;
-            double hmin = fmin(fmin(fmin(r0[-1], r0[0]), fmin(r0[1], W[L - 1])), fmin(fmin(W[L + 1], r2[-1]), fmin(r2[0], r2[1])));
-            hmin = fmin(hmin, 2.e6);
-            const double he = hmin + eps;
-            double nw = wk;
-            if (zk >= he) nw = zk;
-            else if (wk > he) {
-                nw = he;
-                if (zk >= sea) { if (nw - zk > TH) nw = zk + TH; else loc = 1; }
-                else           { if (nw - sea > TH) nw = sea + TH; else loc = 1; }
+            if (wk > zk) {
+                const double *r0 = W + L - LXP, *r2 = W + L + LXP;
+                double hmin = fmin(fmin(fmin(r0[-1], r0[0]), fmin(r0[1], W[L - 1])), fmin(fmin(W[L + 1], r2[-1]), fmin(r2[0], r2[1])));
+                hmin = fmin(hmin, 2.e6);
+                const double he = hmin + eps;
+                double nw = wk;
+                if (zk >= he) nw = zk;
+                else if (wk > he) {
+                    nw = he;
+                    if (zk >= sea) { if (nw - zk > TH) nw = zk + TH; else loc = 1; }
+                    else           { if (nw - sea > TH) nw = sea + TH; else loc = 1; }
+                }
+                if (nw != wk) { W[L] = nw; changed = 1; }
             }
-            if (nw != wk) {
-                W[L] = nw;
+        }
+        // wake the neighbours of every changed node (they are of the other three colours)
+        const unsigned M = __ballot_sync(0xffffffffu, changed);
+        if (M) {
+            if ((hx & 31) == 0) {
+                // the word's 32 nodes share a lattice row and neighbour slot o of all of them lies in one or two
+                // words of one colour: lanes 0..7 each post one slot with at most two atomics
+                if (lane < 8) {
+                    const int cx = c & 1, qx0 = (w * 32) % hx, jw = 2 * ((w * 32) / hx) + (c >> 1);
+                    const int j2 = jw + c_dj[lane], tx = cx + c_di[lane];
+                    if (j2 >= 0 && j2 < g.ny) {
+                        const int sx = (tx + 2) / 2 - 1;                           // floor(tx / 2), tx in -1..2
+                        const int c2 = (j2 & 1) * 2 + (tx & 1);
+                        unsigned M2 = M;
+                        if (sx < 0 && qx0 == 0) M2 &= ~1u;                         // i2 = -1
+                        if (sx > 0 && qx0 + 32 == hx) M2 &= 0x7FFFFFFFu;           // i2 = nx
+                        const int w2 = ((j2 >> 1) * hx + qx0) >> 5;
+                        unsigned *B2 = g.l0 + ((size_t)p * 4 + c2) * g.W0p;
+                        unsigned b0 = M2, b1 = 0u; int w1 = w2;
+                        if (sx > 0) { b0 = M2 << 1; b1 = M2 >> 31; w1 = w2 + 1; }
+                        else if (sx < 0) { b0 = M2 >> 1; b1 = (M2 & 1u) << 31; w1 = w2 - 1; }
+                        if (b0 && atomicOr(B2 + w2, b0) == 0u) {
+                            const unsigned long long pos = atomicAdd(&ctl[c2].tail, 1ull);
+                            g.wl[(size_t)c2 * g.wlcap + (pos & (g.wlcap - 1))] = (unsigned)((size_t)p * g.W0 + w2);
+                        }
+                        if (b1 && atomicOr(B2 + w1, b1) == 0u) {
+                            const unsigned long long pos = atomicAdd(&ctl[c2].tail, 1ull);
+                            g.wl[(size_t)c2 * g.wlcap + (pos & (g.wlcap - 1))] = (unsigned)((size_t)p * g.W0 + w1);
+                        }
+                    }
+                }
+            } else if (changed) {
+                const int q = w * 32 + lane;
+                const int qy = q / hx, qx = q - qy * hx;
+                const int i = 2 * qx + (c & 1), j = 2 * qy + (c >> 1);
 #pragma unroll
                 for (int o = 0; o < 8; ++o) {
                     const int i2 = i + c_di[o], j2 = j + c_dj[o];
@@ -204,11 +247,14 @@ __global__ void __launch_bounds__(256) k_fill_pass(GConst g, int c)
                     const int c2 = (j2 & 1) * 2 + (i2 & 1);
                     const int q2 = (j2 >> 1) * hx + (i2 >> 1);
                     const unsigned old = atomicOr(g.l0 + ((size_t)p * 4 + c2) * g.W0p + (q2 >> 5), 1u << (q2 & 31));
-                    if (old == 0u) atomicOr(g.l1 + ((size_t)p * 4 + c2) * g.W1p + (q2 >> 10), 1u << ((q2 >> 5) & 31));
+                    if (old == 0u) {
+                        const unsigned long long pos = atomicAdd(&ctl[c2].tail, 1ull);
+                        g.wl[(size_t)c2 * g.wlcap + (pos & (g.wlcap - 1))] = (unsigned)((size_t)p * g.W0 + (q2 >> 5));
+                    }
                 }
             }
         }
-        if (__any_sync(0xffffffffu, loc) && lane == 0) g.change[p] = 1;
+        if (__any_sync(0xffffffffu, loc) && lane == 0 && g.change[p * CHS] == 0) g.change[p * CHS] = 1;
     }
 }
 
@@ -222,8 +268,8 @@ __global__ void k_fill_end(GConst g)
     for (int p = threadIdx.x; p < g.B; p += blockDim.x) {
         if (g.fill_active[p]) {
             g.sweeps[p] += 1;
-            if (g.change[p] == 0) g.fill_active[p] = 0; else atomicAdd(&s_act, 1);
-            g.change[p] = 0;
+            if (g.change[p * CHS] == 0) g.fill_active[p] = 0; else atomicAdd(&s_act, 1);
+            g.change[p * CHS] = 0;
         }
     }
     __syncthreads();
@@ -538,7 +584,7 @@ constexpr int GRID_STOPS_CAP = 4096;
 constexpr int GRID_NPART = 64;
 
 struct GLayout {
-    size_t flags, z0, disp, real, parentL, ghostL, pts, stops, ckpt, scal, z, W, Q, cumdiff, cumhill, fdbg, rcv, don, cnt, l0, l1,
+    size_t flags, z0, disp, real, parentL, ghostL, pts, stops, ckpt, scal, z, W, Q, cumdiff, cumhill, fdbg, rcv, don, cnt, l0, wl, wlctl, wlcap,
         partial, total;
     size_t NLP;
     int LX, LY, LXP, ncol, W0, W1, W0p, W1p, nb;
@@ -565,7 +611,7 @@ bool grid_layout(const bl_lattice *lt, int B, int debug, GLayout &L)
     L.pts = take(BL_NPTS_MAX * 4);
     L.stops = take((size_t)GRID_STOPS_CAP * 8);
     L.ckpt = take((size_t)GRID_STOPS_CAP * 4);
-    L.scal = take((size_t)B * 128 + 256);
+    L.scal = take((size_t)B * 256 + 256);
     L.partial = take((size_t)B * GRID_NPART * 8);
     L.z = take((size_t)B * L.NLP * 8);
     L.W = take((size_t)B * L.NLP * 8);
@@ -577,7 +623,9 @@ bool grid_layout(const bl_lattice *lt, int B, int debug, GLayout &L)
     L.don = take((size_t)B * L.NLP);
     L.cnt = take((size_t)B * L.NLP);
     L.l0 = take((size_t)B * 4 * L.W0p * 4);
-    L.l1 = take((size_t)B * 4 * L.W1p * 4);
+    L.wlcap = 1; while (L.wlcap < (size_t)B * L.W0) L.wlcap <<= 1;
+    L.wl = take((size_t)4 * L.wlcap * 4);
+    L.wlctl = take(4 * 128);
     L.total = o;
     return true;
 }
@@ -641,7 +689,7 @@ extern "C" int bl_grid_create(const bl_lattice *lt, const bl_params *p, int B, i
     UP(L.ghostL, ghostL.data(), (size_t)L.nb * 4);
     UP(L.pts, pts.data(), BL_NPTS_MAX * 4);
 #undef UP
-    CUDA_OK(cudaMemset(ws + L.scal, 0, (size_t)B * 128 + 256));
+    CUDA_OK(cudaMemset(ws + L.scal, 0, (size_t)B * 256 + 256));
     bl_grid *ctx = new bl_grid();
     grid::GConst &g = ctx->g;
     memset(&g, 0, sizeof(g));
@@ -664,15 +712,16 @@ extern "C" int bl_grid_create(const bl_lattice *lt, const bl_params *p, int B, i
     g.cumdiff = (double *)(ws + L.cumdiff); g.cumhill = (double *)(ws + L.cumhill);
     g.fdbg = debug ? (double *)(ws + L.fdbg) : nullptr;
     g.rcv = (unsigned char *)(ws + L.rcv); g.don = (unsigned char *)(ws + L.don); g.cnt = (unsigned *)(ws + L.cnt);
-    g.l0 = (unsigned *)(ws + L.l0); g.l1 = (unsigned *)(ws + L.l1);
+    g.l0 = (unsigned *)(ws + L.l0); g.wl = (unsigned *)(ws + L.wl); g.wlctl = (void *)(ws + L.wlctl); g.wlcap = L.wlcap;
     {
         char *s = ws + L.scal;
         const size_t Bs = (size_t)B;
         g.rain = (double *)s; g.erod = g.rain + Bs; g.tnow = g.erod + Bs; g.dt = g.tnow + Bs; g.lastdt = g.dt + Bs;
         g.cflbits = (unsigned long long *)(g.lastdt + Bs);
         g.steps = (long long *)(g.cflbits + Bs); g.sweeps = g.steps + Bs;
-        g.running = (int *)(g.sweeps + Bs); g.fill_active = g.running + Bs; g.change = g.fill_active + Bs;
-        g.si = g.change + Bs; g.ckflag = g.si + Bs; g.counters = g.ckflag + Bs;
+        g.running = (int *)(g.sweeps + Bs); g.fill_active = g.running + Bs;
+        g.si = g.fill_active + Bs; g.ckflag = g.si + Bs; g.counters = g.ckflag + Bs;
+        g.change = (int *)(s + rup(Bs * 84 + 64, 128));          // [B][CHS]
     }
     g.partial = (double *)(ws + L.partial);
     g.npart = GRID_NPART;
@@ -712,10 +761,10 @@ int grid_one_step(bl_grid *ctx, double *out_pts, double *out_sse, double *out_el
     const int B = ctx->B;
     const dim3 b2(32, 8), g2((unsigned)((g.LX + 31) / 32), (unsigned)((g.LY + 7) / 8), (unsigned)B);
     const dim3 g2p((unsigned)((g.LXP + 31) / 32), (unsigned)((g.LY + 7) / 8), (unsigned)B);
-    const dim3 g1((unsigned)((std::max((size_t)g.LY * g.LXP, (size_t)4 * g.W0p) + 255) / 256), (unsigned)B);
+    const dim3 g1((unsigned)((std::max((size_t)g.LY * g.LXP, (size_t)4 * g.W0) + 255) / 256), (unsigned)B);
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    const long long ntask = (long long)B * g.W1;
+    const long long ntask = (long long)B * g.W0;
     const int pass_blocks = (int)std::max<long long>(1, std::min<long long>((ntask + 7) / 8, (long long)nsm * 8));
     grid::k_fill_init<<<g1, 256, 0, st>>>(g);
     grid::k_fill_begin<<<1, 256, 0, st>>>(g);
@@ -733,6 +782,12 @@ int grid_one_step(bl_grid *ctx, double *out_pts, double *out_sse, double *out_el
         if (ctx->h_counters[1] == 0) break;
         if (done > 50000000) { g_err = "bl_grid: depression filling did not terminate"; return BL_ERR_CUDA; }
         chunk = std::max<long long>(8, std::min<long long>(done / 4, 1024));
+    }
+    if (getenv("BL_DEBUG")) {
+        unsigned long long ctl[64];
+        cudaMemcpy(ctl, g.wlctl, sizeof(ctl), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[bl_grid] fill: sweeps %d, ring words consumed per colour %llu %llu %llu %llu (initial %llu)\n", ctx->h_counters[2],
+                ctl[1], ctl[17], ctl[33], ctl[49], (unsigned long long)B * g.W0);
     }
     ctx->last_sweeps = ctx->h_counters[2] + 1;   // the next step's first chunk: landscapes change slowly
     grid::k_sfd<<<g2, b2, 0, st>>>(g);

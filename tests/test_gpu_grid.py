@@ -31,7 +31,7 @@ def synthetic(nx, ny, dx=100.0, btype="fixed", T=200000.0, seed=1234, amp=1.0):
     return m, inp, disp, lattice.from_mesh(m, disp)
 
 
-@pytest.mark.parametrize("btype,nx,ny", [("fixed", 48, 32), ("slope", 40, 36), ("fixed", 130, 96)])
+@pytest.mark.parametrize("btype,nx,ny", [("fixed", 64, 40), ("slope", 40, 36), ("fixed", 130, 96), ("fixed", 128, 6)])
 def test_lattice_stepwise_bit_exact(btype, nx, ny):
     from bayeslands_b200.grid_engine import GridEngine
     from oracle import oracle
