@@ -158,7 +158,7 @@ __global__ void k_fill_init(GConst g)
 
 // one colour pass of the Gauss-Seidel sweep (PDalgo.f90:37-91): one warp per pending bitmap word.  Nodes of one
 // colour are never adjacent, so the pass is race free and equals the sequential sweep over that id range.
-__global__ void __launch_bounds__(256) k_fill_pass(GConst g, int c)
+__global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
 {
     if (g.counters[1] == 0) return;
     WlCtl *ctl = (WlCtl *)g.wlctl;
@@ -190,10 +190,12 @@ __global__ void __launch_bounds__(256) k_fill_pass(GConst g, int c)
             const int qy = q / hx, qx = q - qy * hx;
             const int i = 2 * qx + (c & 1), j = 2 * qy + (c >> 1);
             const size_t L = (size_t)(j + 1) * LXP + (i + 1);
+            // all ten loads go out together (a pending node almost always still has W > z)
+            const double *r0 = W + L - LXP, *r2 = W + L + LXP;
             const double wk = W[L], zk = z[L];
+            const double a0 = r0[-1], a1 = r0[0], a2 = r0[1], a3 = W[L - 1], a4 = W[L + 1], a5 = r2[-1], a6 = r2[0], a7 = r2[1];
             if (wk > zk) {
-                const double *r0 = W + L - LXP, *r2 = W + L + LXP;
-                double hmin = fmin(fmin(fmin(r0[-1], r0[0]), fmin(r0[1], W[L - 1])), fmin(fmin(W[L + 1], r2[-1]), fmin(r2[0], r2[1])));
+                double hmin = fmin(fmin(fmin(a0, a1), fmin(a2, a3)), fmin(fmin(a4, a5), fmin(a6, a7)));
                 hmin = fmin(hmin, 2.e6);
                 const double he = hmin + eps;
                 double nw = wk;
@@ -226,13 +228,15 @@ __global__ void __launch_bounds__(256) k_fill_pass(GConst g, int c)
                         unsigned b0 = M2, b1 = 0u; int w1 = w2;
                         if (sx > 0) { b0 = M2 << 1; b1 = M2 >> 31; w1 = w2 + 1; }
                         else if (sx < 0) { b0 = M2 >> 1; b1 = (M2 & 1u) << 31; w1 = w2 - 1; }
-                        if (b0 && atomicOr(B2 + w2, b0) == 0u) {
-                            const unsigned long long pos = atomicAdd(&ctl[c2].tail, 1ull);
-                            g.wl[(size_t)c2 * g.wlcap + (pos & (g.wlcap - 1))] = (unsigned)((size_t)p * g.W0 + w2);
-                        }
-                        if (b1 && atomicOr(B2 + w1, b1) == 0u) {
-                            const unsigned long long pos = atomicAdd(&ctl[c2].tail, 1ull);
-                            g.wl[(size_t)c2 * g.wlcap + (pos & (g.wlcap - 1))] = (unsigned)((size_t)p * g.W0 + w1);
+                        // both bitmap atomics first, then one ring reservation for the words that were empty
+                        const unsigned o0 = b0 ? atomicOr(B2 + w2, b0) : 1u;
+                        const unsigned o1 = b1 ? atomicOr(B2 + w1, b1) : 1u;
+                        const int n0 = (o0 == 0u), n1 = (o1 == 0u);
+                        if (n0 + n1) {
+                            const unsigned long long pos = atomicAdd(&ctl[c2].tail, (unsigned long long)(n0 + n1));
+                            unsigned *ring2 = g.wl + (size_t)c2 * g.wlcap;
+                            if (n0) ring2[pos & (g.wlcap - 1)] = (unsigned)((size_t)p * g.W0 + w2);
+                            if (n1) ring2[(pos + n0) & (g.wlcap - 1)] = (unsigned)((size_t)p * g.W0 + w1);
                         }
                     }
                 }
