@@ -300,6 +300,132 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 5: synthetic regular-grid landscape on the lattice engine (optional: --config synthetic)
+# ---------------------------------------------------------------------------------------------------
+def _synthetic_cpu(nx, ny, T, nsteps=2):
+    """Oracle on the same lattice: `nsteps` time steps of one proposal (a full evaluation takes hours on one core)."""
+    from bayeslands_b200 import synthetic, mesh, forcing
+    from oracle import oracle
+    inp = synthetic.inputs(T)
+    m = mesh.build_regular(nx, ny, 100.0, synthetic.surface(nx, ny), "fixed", order="colour")
+    rate = np.zeros(m.N)
+    rate[m.extra["regular"]["ext"][1:-1, 1:-1].ravel()] = synthetic.uplift_rate(nx, ny).ravel()
+    disp = forcing.disp_border(np.where(np.arange(m.N) < m.boundsPt, -1.0e6, rate), m.FVmesh.neighbours,
+                               m.FVmesh.edge_length, m.boundsPt)
+    om = oracle.OracleModel(m, inp, seed=1, disp=disp)
+    r, e = synthetic.proposals(1)
+    om.reset(r[0], e[0], seed=1)
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        om.streamflow(); om.sediment_flux(T)
+    return (time.perf_counter() - t0) / nsteps
+
+
+def run_synthetic(args):
+    import torch
+    import torch.distributed as dist
+    from bayeslands_b200 import synthetic
+    from bayeslands_b200.grid_engine import GridEngine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nx = ny = args.nx
+    T = float(args.simtime)
+    B = args.batch
+    lat, inp = synthetic.build(nx, ny, T=T)
+    # observed topography = the initial surface lifted by the full uplift (any fixed grid does for the SSE reduction)
+    real = lat.z0 + lat.disp * T
+    eng = GridEngine(lat, inp, B, device=local, real_elev=real)
+    dev = eng.tdev
+    times = [T / 4, T / 2, 3 * T / 4, T]
+    gather = torch.empty(world * B, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one(step, host=False):
+        r, e = synthetic.proposals(B, offset=1000 * (step + 100000) + rank)
+        if not host:
+            r, e = torch.as_tensor(r, device=dev), torch.as_tensor(e, device=dev)
+        eng.reset(r, e)
+        _, sse, _, _ = eng.run_schedule(times)
+        if world > 1:
+            dist.all_gather_into_tensor(gather, sse)
+        return sse.cpu().numpy() if host else sse
+
+    for w in range(args.warmup):
+        one(-1 - w)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = eng.launches
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record()
+    for k in range(args.steps):
+        one(k)
+    t1e.record()
+    barrier()
+    ms = t0e.elapsed_time(t1e)
+    launches = eng.launches - l0
+    sc = eng.scalars()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        one(500 + k, host=True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        N = (nx + 2) * (ny + 2)
+        S = sc["steps"].astype(np.float64)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # erosive configuration: fill 16 + SFD 9 + donors 2 + discharge 24 + CFL 17 + erosion 41 + diffusion 48 B/node/step
+        alg = 157.0
+        achieved = float(np.sum(S)) * N * alg * args.steps / (ms * 1e-3) / 1e9
+        line = dict(metric="mcmc_forward_model_evals_per_sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f64", data="synthetic",
+                    config=dict(workload="synthetic %dx%d regular grid, uplift + rain, dep=0, T=%d a, N=%d nodes (lattice engine)"
+                                         % (nx, ny, T, N),
+                                proposals_per_gpu_per_step=B, mean_time_steps_per_eval=float(np.mean(S)),
+                                mean_fill_sweeps_per_step=float(sc["fill_sweeps"].sum() / max(1.0, S.sum())),
+                                l2_policy="per-proposal state %.0f MB x %d > L2" % (N * 43 / 1e6, B),
+                                parallelism="proposals sharded, %d per GPU" % B),
+                    e2e=dict(value=world * B * args.steps / e2e_s, unit="evals/s", h2d_bytes_per_step=B * 16, d2h_bytes_per_step=B * 8),
+                    gpu_launches=int(launches),
+                    roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                                  kernel="all lattice kernels (k_fill_pass dominates)", alg_bytes_per_node_step=alg,
+                                  peak_source="MEASURED_PEAKS.json" if peaks else "fallback"),
+                    clocks=clocks)
+        if world == 1 and not args.no_cpu:
+            per_step = _synthetic_cpu(nx, ny, T)
+            line["cpu_baseline"] = dict(value=1.0 / (per_step * float(np.mean(S))), unit="evals/s", cores=1, kind="port",
+                                        sample="2 time steps of one proposal on the same lattice, CPU oracle, scaled by the "
+                                               "%.0f steps of an evaluation" % float(np.mean(S)))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -307,10 +433,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=296)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="crater", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="crater", choices=sorted(CONFIGS) + ["synthetic"])
+    ap.add_argument("--nx", type=int, default=2048, help="synthetic config: lattice size (nx = ny)")
+    ap.add_argument("--simtime", type=float, default=50000.0, help="synthetic config: simulated years")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config == "synthetic":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference is defined on the BASELINE metric config (crater); the synthetic config "
+                             "reports its CPU oracle leg as cpu_baseline")
+        run_synthetic(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -94,3 +94,60 @@ def test_lattice_engine_rejects_out_of_scope():
         GridEngine(lat, inp, 2)
     with pytest.raises(ValueError):
         lattice.regular(15, 12, 100.0, np.zeros((12, 15)))
+
+
+def test_lattice_full_size_properties():
+    """BASELINE config 5 at its full 2048 x 2048 size (the oracle needs minutes per step there): size-independent
+    properties of two time steps - depression-free filled surface, receivers = first lowest neighbour, discharge
+    conservation, elevation bookkeeping, determinism."""
+    import torch
+    from bayeslands_b200 import synthetic
+    from bayeslands_b200.grid_engine import GridEngine
+    nx = ny = 2048
+    T = 50000.0
+    lat, inp = synthetic.build(nx, ny, T=T)
+    rain, erod = synthetic.proposals(2)
+    eng = GridEngine(lat, inp, 2, debug=True)
+    out = []
+    for rep in range(2):
+        eng.reset(rain, erod)
+        eng.step(T)
+        zs = [eng.field("z", b, mesh_order=False) for b in range(2)]
+        eng.step(T)
+        out.append([eng.field(f, 1, mesh_order=False) for f in ("z", "fillH", "Q", "cumdiff", "cumhill", "rcv")])
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)                                     # bit-reproducible run to run
+    z, W, Q, cd, ch, rcv = out[0]
+    sc = eng.scalars()
+    assert sc["steps"].tolist() == [2, 2] and np.all(sc["fill_sweeps"] > 100)
+    # the surface the second step filled is the first step's result
+    z1 = zs[1]
+    assert np.all(W >= z1)
+    Wp = np.pad(W, 1, constant_values=np.inf)
+    nbmin = np.full_like(W, np.inf)
+    first = np.zeros(W.shape, dtype=np.int64)
+    LY, LX = W.shape
+    J, I = np.meshgrid(np.arange(LY), np.arange(LX), indexing="ij")
+    low = W.copy(); lowidx = (J * LX + I)
+    for dj, di in [(0, 1), (1, 1), (1, 0), (1, -1), (0, -1), (-1, -1), (-1, 0), (-1, 1)]:
+        nb = Wp[1 + dj:1 + dj + LY, 1 + di:1 + di + LX]
+        nbmin = np.minimum(nbmin, nb)
+        better = nb < low
+        low = np.where(better, nb, low)
+        lowidx = np.where(better, (J + dj) * LX + (I + di), lowidx)
+    assert np.array_equal(rcv.ravel(), lowidx.ravel())                  # sfd.c:55-111, strict <, first wins
+    inner = np.zeros(W.shape, dtype=bool); inner[1:-1, 1:-1] = True
+    wet = inner & (W > z1)
+    assert np.all(W[wet] <= nbmin[wet] + 0.01 * (1 + 1e-12))            # PDalgo: W <= min_nb W + eps where W > z
+    assert np.all(nbmin[inner] < W[inner])                              # no interior pit left on the filled surface
+    # discharge: what leaves through the self-receivers is what rained (FLOWalgo.f90:53-81)
+    base = rcv.ravel() == np.arange(LY * LX)
+    total = lat.area * rain[1] * nx * ny
+    assert abs(Q.ravel()[base].sum() - total) <= 1e-9 * total
+    assert Q[inner].min() >= lat.area * rain[1]
+    # bookkeeping: z = z0 + cumdiff + uplift (buildFlux.py:193-195, :257-272, :312-313), erosion only lowers
+    t = float(sc["tNow"][1])
+    assert np.allclose(z, lat.z0 + cd + lat.disp * t, rtol=0, atol=1e-9)
+    assert np.all((cd - ch)[inner] <= 1e-12)
+    del eng
+    torch.cuda.empty_cache()
