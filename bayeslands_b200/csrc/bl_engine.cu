@@ -451,6 +451,7 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
     }
     // the fast path needs 17 bytes of shared memory per node: small meshes leave room for several CTAs per SM
     size_t need = (size_t)17 * ctx->c.Nq + ctx->c.Nq / 8 + 256;
+    need = std::max(need, (size_t)16 * ctx->c.Nq + ctx->c.Nq / 8 + 64 + 8192);   // fill: W, z, pending bitmap, id list of a round
     if (ctx->c.CDr > 0. || ctx->c.nsea > 0) need = std::max(need, (size_t)ctx->c.Nq * (17 + 2 * ctx->c.KDT) + 256);
     const int dyn = (int)std::min((size_t)DYN_SMEM, rup(need, 1024));
 #define LAUNCH(NS, T, K, DYN)                                                                                   \

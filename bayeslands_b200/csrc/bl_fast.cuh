@@ -92,6 +92,7 @@ __device__ void fill_bitmap(const DevConst &c, Smem &S, unsigned char *dsm, doub
     const int lane = tid & 31, warp = tid >> 5;
     double *W = (double *)dsm, *zs = W + Nq;
     unsigned *bits = (unsigned *)(zs + Nq);                   // [Nq/32 + 1]
+    unsigned short *flist = (unsigned short *)(dsm + (size_t)16 * Nq + Nq / 8 + 64);   // [CHW * 32] pending ids of a round
     const double *z = S.P.f[F_Z];
     for (int i = tid; i < N; i += TPB) { const double zi = z[i]; zs[i] = zi; W[i] = (i < nb) ? zi : 1.e6; }
     for (int i = tid; i <= Nq / 32; i += TPB) {               // every interior node starts pending
@@ -135,27 +136,31 @@ __device__ void fill_bitmap(const DevConst &c, Smem &S, unsigned char *dsm, doub
                     if (lane == 31) S.fb_tot[warp] = inc;
                 }
                 __syncthreads();
-                // (b) thread t takes the t-th pending node of the round
+                // (a2) every thread expands one nibble of one word into the round's id list (8 threads per word)
                 int tot = 0, cum[CHW / 32];
 #pragma unroll
                 for (int q = 0; q < CHW / 32; ++q) { cum[q] = tot; tot += S.fb_tot[q]; }
-                for (int t = tid; t < tot; t += TPB) {
-                    int q = 0;
+                if (tot == 0) { __syncthreads(); continue; }            // uniform: nothing pending in this round (fb_tot is reused)
+                for (int it = tid; it < CHW * 8; it += TPB) {
+                    const int wq = it >> 3, sub = it & 7;
+                    const unsigned word = S.fb_word[wq];
+                    unsigned nib = (word >> (4 * sub)) & 15u;
+                    if (nib) {
+                        int cq = 0;                                     // (a runtime index into cum[] would put it in local memory)
 #pragma unroll
-                    for (int u = 1; u < CHW / 32; ++u) if (t >= cum[u]) q = u;
-                    int r = t - cum[q];
-                    int lo_ = q * 32, hi_ = lo_ + 31;          // last word of the group with prefix <= r
-                    while (lo_ < hi_) { const int mid = (lo_ + hi_ + 1) >> 1; if ((int)S.fb_pre[mid] <= r) lo_ = mid; else hi_ = mid - 1; }
-                    r -= S.fb_pre[lo_];
-                    unsigned w = S.fb_word[lo_];
-                    int posb = 0;
-#pragma unroll
-                    for (int h = 16; h >= 1; h >>= 1) {
-                        const unsigned lowmask = (1u << h) - 1u;
-                        const int cl = __popc(w & lowmask);
-                        if (r >= cl) { r -= cl; w >>= h; posb += h; } else w &= lowmask;
+                        for (int u = 1; u < CHW / 32; ++u) if ((wq >> 5) >= u) cq = cum[u];
+                        int pos = cq + (int)S.fb_pre[wq] + __popc(word & ((1u << (4 * sub)) - 1u));
+                        const int base = (wbase + wq) * 32 + 4 * sub;
+                        if (nib & 1u) flist[pos++] = (unsigned short)base;
+                        if (nib & 2u) flist[pos++] = (unsigned short)(base + 1);
+                        if (nib & 4u) flist[pos++] = (unsigned short)(base + 2);
+                        if (nib & 8u) flist[pos] = (unsigned short)(base + 3);
                     }
-                    const int k = (wbase + lo_) * 32 + posb;
+                }
+                __syncthreads();
+                // (b) thread t takes the t-th pending node of the round
+                for (int t = tid; t < tot; t += TPB) {
+                    const int k = flist[t];
                     const double wk = W[k], zk = zs[k];
                     if (!(wk > zk)) continue;
                     Ids<KDT> ids;
