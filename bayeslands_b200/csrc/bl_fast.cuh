@@ -187,10 +187,14 @@ __device__ void fill_bitmap(const DevConst &c, Smem &S, unsigned char *dsm, doub
                     }
                     if (nw != wk) {
                         W[k] = nw;
+                        // wake only the neighbours this change can move: re-evaluating j alters W(j) only if
+                        // min_nb W + eps < W(j), and the neighbour that brings the minimum down below W(j) - eps is the
+                        // one that wakes j (hm[p] is W(j) now: other levels do not change during this pass)
+                        const double lim = nw + eps;
 #pragma unroll
                         for (int p = 0; p < KDT; ++p) {
                             const unsigned j = ids.get(p);
-                            if (j != NONE16 && (int)j >= nb) atomicOr(&bits[j >> 5], 1u << (j & 31));
+                            if (j != NONE16 && (int)j >= nb && hm[p] > lim) atomicOr(&bits[j >> 5], 1u << (j & 31));
                         }
                     }
                 }

@@ -183,6 +183,9 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
         if (lane == 0) { word = *L0; *L0 = 0u; }
         word = __shfl_sync(0xffffffffu, word, 0);
         int loc = 0, changed = 0;
+        double av[8], nwv = 0.;                     // neighbour values in slot order E,NE,N,NW,W,SW,S,SE; the new W
+#pragma unroll
+        for (int o = 0; o < 8; ++o) av[o] = 0.;
         if ((word >> lane) & 1u) {
             double *W = g.W + (size_t)p * g.NLP;
             const double *z = g.z + (size_t)p * g.NLP;
@@ -193,9 +196,9 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
             // all ten loads go out together (a pending node almost always still has W > z)
             const double *r0 = W + L - LXP, *r2 = W + L + LXP;
             const double wk = W[L], zk = z[L];
-            const double a0 = r0[-1], a1 = r0[0], a2 = r0[1], a3 = W[L - 1], a4 = W[L + 1], a5 = r2[-1], a6 = r2[0], a7 = r2[1];
+            av[0] = W[L + 1]; av[1] = r2[1]; av[2] = r2[0]; av[3] = r2[-1]; av[4] = W[L - 1]; av[5] = r0[-1]; av[6] = r0[0]; av[7] = r0[1];
             if (wk > zk) {
-                double hmin = fmin(fmin(fmin(a0, a1), fmin(a2, a3)), fmin(fmin(a4, a5), fmin(a6, a7)));
+                double hmin = fmin(fmin(fmin(av[0], av[1]), fmin(av[2], av[3])), fmin(fmin(av[4], av[5]), fmin(av[6], av[7])));
                 hmin = fmin(hmin, 2.e6);
                 const double he = hmin + eps;
                 double nw = wk;
@@ -205,22 +208,30 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
                     if (zk >= sea) { if (nw - zk > TH) nw = zk + TH; else loc = 1; }
                     else           { if (nw - sea > TH) nw = sea + TH; else loc = 1; }
                 }
-                if (nw != wk) { W[L] = nw; changed = 1; }
+                if (nw != wk) { W[L] = nw; changed = 1; nwv = nw; }
             }
         }
-        // wake the neighbours of every changed node (they are of the other three colours)
+        // wake the neighbours a change can move (they are of the other three colours): re-evaluating j alters W(j) only
+        // if min_nb W + eps < W(j), and the neighbour whose drop makes that true is the one that wakes j
+        const double lim = nwv + eps;
         const unsigned M = __ballot_sync(0xffffffffu, changed);
         if (M) {
             if ((hx & 31) == 0) {
                 // the word's 32 nodes share a lattice row and neighbour slot o of all of them lies in one or two
                 // words of one colour: lanes 0..7 each post one slot with at most two atomics
+                unsigned Ms = 0u;
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    const unsigned mo = __ballot_sync(0xffffffffu, changed && av[o] > lim);
+                    if (lane == o) Ms = mo;
+                }
                 if (lane < 8) {
                     const int cx = c & 1, qx0 = (w * 32) % hx, jw = 2 * ((w * 32) / hx) + (c >> 1);
                     const int j2 = jw + c_dj[lane], tx = cx + c_di[lane];
                     if (j2 >= 0 && j2 < g.ny) {
                         const int sx = (tx + 2) / 2 - 1;                           // floor(tx / 2), tx in -1..2
                         const int c2 = (j2 & 1) * 2 + (tx & 1);
-                        unsigned M2 = M;
+                        unsigned M2 = Ms;
                         if (sx < 0 && qx0 == 0) M2 &= ~1u;                         // i2 = -1
                         if (sx > 0 && qx0 + 32 == hx) M2 &= 0x7FFFFFFFu;           // i2 = nx
                         const int w2 = ((j2 >> 1) * hx + qx0) >> 5;
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
 #pragma unroll
                 for (int o = 0; o < 8; ++o) {
                     const int i2 = i + c_di[o], j2 = j + c_dj[o];
-                    if (i2 < 0 || j2 < 0 || i2 >= g.nx || j2 >= g.ny) continue;
+                    if (i2 < 0 || j2 < 0 || i2 >= g.nx || j2 >= g.ny || !(av[o] > lim)) continue;
                     const int c2 = (j2 & 1) * 2 + (i2 & 1);
                     const int q2 = (j2 >> 1) * hx + (i2 >> 1);
                     const unsigned old = atomicOr(g.l0 + ((size_t)p * 4 + c2) * g.W0p + (q2 >> 5), 1u << (q2 & 31));

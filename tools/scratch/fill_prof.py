@@ -15,8 +15,7 @@ torch.cuda.synchronize()
 pc = eng.phase_cycles().astype(np.float64)
 steps = eng.scalars()["steps"].astype(np.float64)
 per = lambda i: (pc[:, i] / steps).mean()
-npass = per(14); items = per(15)
-print("fill total cyc/step %.0f ; passes/step %.1f ; items/pass %.1f" % (per(0), npass, items / npass))
-print("per pass: (a)+barrier %.0f ; (b)+barrier %.0f" % (per(12) / npass, per(13) / npass))
-print("thread 0 per pass: search+select %.0f ; W,z test + ids load %.0f ; 8 W loads + min %.0f ; update+atomics %.0f" % (
-    per(1) / npass, per(3) / npass, per(5) / npass, per(7) / npass))
+n = per(15)
+print("fill total cyc/step %.0f ; passes(rounds)/step %.1f" % (per(0), n))
+print("per round (thread 0, incl. barrier): a1 %.0f ; a2 %.0f ; b %.0f ; sum %.0f" % (per(12) / n, per(13) / n, per(14) / n, (per(12)+per(13)+per(14))/n))
+print("per round max over threads: b own %.0f ; ids load %.0f ; W loads+min %.0f ; update+atomics %.0f" % (per(1) / n, per(3) / n, per(5) / n, per(7) / n))
