@@ -673,7 +673,6 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     ScanSm sm = scan_layout(dsm, Nq);
     const int *pitID = S.P.i[I_PITID], *stack = S.P.i[I_STACK], *pitDrain = S.P.i[I_PITDRAIN];
-    int *events = S.P.i[I_EVENTS];
     const double *z = S.P.f[F_Z], *W = S.P.f[F_FILLH], *Qg = S.P.f[F_Q], *maxhA = S.P.f[F_MAXH];
     const double *pitVol1 = S.P.f[F_PITVOL];
     double *depo = S.P.f[F_DEPO], *ero = S.P.f[F_ERO], *pdep = S.P.f[F_PDEP], *pitVol = S.P.f[F_PITVOLW];
