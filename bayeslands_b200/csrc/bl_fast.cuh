@@ -892,6 +892,72 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
 #undef STICK
 }
 
+// FLOWalgo.f90:332-388 diffmarine + buildFlux.py:198-247 (see phase_marine_diffusion): the up to 1000 sub-steps run on
+// z / fresh-deposit thickness / rate / coefficient held in shared memory (33 bytes per node); the sub-step count is
+// data dependent (mindt guard), so the loop stays a block-wide sequence of gather pass + min + update.
+template <int KDT>
+__device__ void marine_diffusion(const DevConst &c, Smem &S, unsigned char *dsm, double sea, double timestep)
+{
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    double *zs = (double *)dsm, *sd = zs + Nq, *dmv = sd + Nq, *cf = dmv + Nq;
+    unsigned char *fls = (unsigned char *)(cf + Nq);
+    double *z = S.P.f[F_Z], *cumdiff = S.P.f[F_CUMDIFF], *sumdep = S.P.f[F_DTHICK];
+    const double maxth = 0.1;
+    for (int k = tid; k < N; k += TPB) {                       // diffLinear.sedfluxmarine (diffLinear.py:184-213)
+        const double area = c.area[k], zk = z[k];
+        const double ac = (area > 0.) ? 1. / area : 0.;
+        zs[k] = zk; sd[k] = sumdep[k]; fls[k] = c.flags[k];
+        cf[k] = ac * ((zk >= sea) ? 0. : c.CDr);
+    }
+    __syncthreads();
+    double diffstep = timestep;
+    int it = 0;
+    while (diffstep > 0. && it < 1000) {
+        double maxstep = fmin(c.ms, diffstep);
+        double mind = maxstep;
+        for (int g = tid; g < N; g += TPB) {
+            double acc = 0.;
+            const unsigned char fg = fls[g];
+            const double zg = zs[g];
+            if ((fg & 1) && zg < sea) {
+                const double dg = sd[g], cg = cf[g];
+                Ids<KDT> ids;
+                load_ids<KDT>(c, g, ids);
+#pragma unroll
+                for (int q = 0; q < KDT; ++q) {
+                    const unsigned j = ids.get(q);
+                    if (j == NONE16) continue;
+                    const double zj = zs[j];
+                    bool take;
+                    if (fls[j] & 1) take = (dg > maxth && zg > zj) || (sd[j] > maxth && zg < zj && zj < sea);
+                    else take = (dg > maxth && zg > zj);
+                    if (take) {
+                        double vo, ed;
+                        if (c.ve32) { const float2 ve = *reinterpret_cast<const float2 *>(c.ve32 + ((size_t)g * KDT + q) * 2); vo = ve.x; ed = ve.y; }
+                        else { vo = c.vor[(size_t)q * N + g]; ed = c.edge[(size_t)q * N + g]; }
+                        const double flx = vo * (zj - zg) / ed;
+                        acc = acc + cg * flx;
+                    }
+                }
+                if (acc < 0. && acc * maxstep < -dg) mind = fmin(-dg / acc, mind);
+            }
+            dmv[g] = (fg & 1) ? acc : 0.;
+        }
+        mind = blk_min(mind, S);
+        maxstep = fmin(mind, maxstep);
+        diffstep -= maxstep;
+        for (int k = tid; k < N; k += TPB) {
+            const double d = dmv[k] * maxstep;
+            sd[k] += d; zs[k] += d;
+            if (d != 0.) cumdiff[k] += d;              // x + 0 = x bit for bit (cumdiff is never -0)
+        }
+        __syncthreads();
+        ++it;
+    }
+    for (int k = tid; k < N; k += TPB) { z[k] = zs[k]; sumdep[k] = sd[k]; }
+    __syncthreads();
+}
+
 // buildFlux.py:193-195, :252-272, :292-315 (see phase_apply) with z staged in shared memory for the gather
 template <int KDT>
 __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea, double timestep)
@@ -908,7 +974,7 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
     if (c.CDr > 0.) {            // river-borne marine sediment diffusion works on the global arrays
         for (int k = tid; k < N; k += TPB) { const double sf = sedflux[k]; z[k] += sf; cumdiff[k] += sf; }
         __syncthreads();
-        phase_marine_diffusion(c, S, sea, timestep);
+        marine_diffusion<KDT>(c, S, dsm, sea, timestep);
         for (int k = tid; k < N; k += TPB) { zs[k] = z[k]; fls[k] = c.flags[k]; }
     } else {
 #pragma unroll 4
