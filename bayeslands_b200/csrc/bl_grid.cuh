@@ -174,14 +174,30 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
     const int hx = g.hx, LXP = g.LXP;
     const double eps = g.eps, TH = g.TH, sea = g.sea;
     const unsigned *ring = g.wl + (size_t)c * g.wlcap;
-    for (unsigned long long e = h + warp; e < t; e += nwarps) {
-        const unsigned ent = ring[e & (g.wlcap - 1)];
-        const int p = (int)(ent / (unsigned)g.W0), w = (int)(ent % (unsigned)g.W0);
-        if (!__ldg(g.fill_active + p)) continue;
-        unsigned *L0 = g.l0 + ((size_t)p * 4 + c) * g.W0p + w;
+    // software pipeline over the warp's tasks: the next ring entry is requested before this task's gathers and the next
+    // pending word (read and cleared: nobody else touches colour c's words during its pass) before this task's wake-up
+    // atomics, so a task costs three dependent memory round trips instead of five
+    auto take_word = [&](unsigned ent, int &p, int &w) -> unsigned {
+        p = (int)(ent / (unsigned)g.W0); w = (int)(ent % (unsigned)g.W0);
         unsigned word = 0u;
-        if (lane == 0) { word = *L0; *L0 = 0u; }
-        word = __shfl_sync(0xffffffffu, word, 0);
+        if (__ldg(g.fill_active + p)) {
+            unsigned *L0 = g.l0 + ((size_t)p * 4 + c) * g.W0p + w;
+            if (lane == 0) { word = *L0; if (word) *L0 = 0u; }
+            word = __shfl_sync(0xffffffffu, word, 0);
+        }
+        return word;
+    };
+    unsigned long long e = h + warp;
+    int pN = 0, wN = 0;
+    unsigned wordN = 0u;
+    bool more = e < t;
+    if (more) wordN = take_word(ring[e & (g.wlcap - 1)], pN, wN);
+    while (more) {
+        const int p = pN, w = wN;
+        const unsigned word = wordN;
+        e += nwarps;
+        more = e < t;
+        const unsigned ent2 = more ? ring[e & (g.wlcap - 1)] : 0u;
         int loc = 0, changed = 0;
         double av[8], nwv = 0.;                     // neighbour values in slot order E,NE,N,NW,W,SW,S,SE; the new W
 #pragma unroll
@@ -211,6 +227,7 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
                 if (nw != wk) { W[L] = nw; changed = 1; nwv = nw; }
             }
         }
+        if (more) wordN = take_word(ent2, pN, wN);
         // wake the neighbours a change can move (they are of the other three colours): re-evaluating j alters W(j) only
         // if min_nb W + eps < W(j), and the neighbour whose drop makes that true is the one that wakes j
         const double lim = nwv + eps;
