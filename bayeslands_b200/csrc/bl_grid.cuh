@@ -402,22 +402,28 @@ __global__ void __launch_bounds__(256) k_discharge(GConst g)
         if (s == 8) break;
         const int Ir = I + c_di[s], Jr = J + c_dj[s];
         const size_t R = (size_t)Jr * g.LXP + Ir;
-        __threadfence();
-        const unsigned sh = 8u * (unsigned)(R & 3);
-        const unsigned old = atomicAdd(cnt + (R >> 2), 1u << sh);
         unsigned mask = don[R];
-        if ((int)((old >> sh) & 0xFFu) + 1 != __popc(mask)) break;   // somebody else will finish R
-        __threadfence();
-        acc = is_ghost(g, Ir, Jr) ? 0. : q0i;
-        while (mask) {                                        // donors in descending mesh id
-            int best = -1, bid = -1;
-            for (unsigned mm = mask; mm; mm &= mm - 1) {
-                const int o = __ffs(mm) - 1;
-                const int id = mesh_id(g, Ir + c_di[o], Jr + c_dj[o]);
-                if (id > bid) { bid = id; best = o; }
+        const double qr = is_ghost(g, Ir, Jr) ? 0. : q0i;
+        if ((mask & (mask - 1u)) == 0u) {
+            // R's only donor: no rendezvous needed, carry the value on in a register (most of a river)
+            acc = qr + acc;
+        } else {
+            __threadfence();
+            const unsigned sh = 8u * (unsigned)(R & 3);
+            const unsigned old = atomicAdd(cnt + (R >> 2), 1u << sh);
+            if ((int)((old >> sh) & 0xFFu) + 1 != __popc(mask)) break;   // somebody else will finish R
+            __threadfence();
+            acc = qr;
+            while (mask) {                                        // donors in descending mesh id
+                int best = -1, bid = -1;
+                for (unsigned mm = mask; mm; mm &= mm - 1) {
+                    const int o = __ffs(mm) - 1;
+                    const int id = mesh_id(g, Ir + c_di[o], Jr + c_dj[o]);
+                    if (id > bid) { bid = id; best = o; }
+                }
+                acc = acc + __ldcg(Q + (size_t)(Jr + c_dj[best]) * g.LXP + (Ir + c_di[best]));
+                mask &= ~(1u << best);
             }
-            acc = acc + __ldcg(Q + (size_t)(Jr + c_dj[best]) * g.LXP + (Ir + c_di[best]));
-            mask &= ~(1u << best);
         }
         I = Ir; J = Jr; L = R;
     }
