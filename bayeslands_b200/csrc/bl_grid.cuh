@@ -396,13 +396,14 @@ __global__ void __launch_bounds__(256) k_discharge(GConst g)
     if (don[L] != 0) return;                                  // only leaves start a walk
     const double q0i = g.area * g.rain[p];                    // rain is 0 on ghost nodes (model.py:278-279)
     double acc = is_ghost(g, I, J) ? 0. : q0i;
+    int s = rcv[L];
     for (;;) {
         Q[L] = acc;
-        const int s = rcv[L];
         if (s == 8) break;
         const int Ir = I + c_di[s], Jr = J + c_dj[s];
         const size_t R = (size_t)Jr * g.LXP + Ir;
         unsigned mask = don[R];
+        const int sr = rcv[R];                                    // requested together with the mask: one round trip per hop
         const double qr = is_ghost(g, Ir, Jr) ? 0. : q0i;
         if ((mask & (mask - 1u)) == 0u) {
             // R's only donor: no rendezvous needed, carry the value on in a register (most of a river)
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(256) k_discharge(GConst g)
                 mask &= ~(1u << best);
             }
         }
-        I = Ir; J = Jr; L = R;
+        I = Ir; J = Jr; L = R; s = sr;
     }
 }
 
