@@ -340,25 +340,50 @@ __global__ void k_fill_begin(GConst g)
 }
 
 // ---- receivers on the filled surface (sfd.c:55-111) ---------------------------------------------------------
+// Each warp owns 32 columns and walks SROWS rows upwards with a 3 x 3 register window: one coalesced load per node, the
+// left / right columns come from the neighbouring lanes (the two edge lanes fetch theirs).
+constexpr int SROWS = 16;
+__device__ __forceinline__ void row3(const double *A, const GConst &g, int I, int J, int lane, double fill, double &l, double &c, double &r)
+{
+    const bool jok = (J >= 0 && J < g.LY);
+    const double v = (jok && I < g.LX) ? A[(size_t)J * g.LXP + I] : fill;
+    l = __shfl_up_sync(0xffffffffu, v, 1);
+    r = __shfl_down_sync(0xffffffffu, v, 1);
+    if (lane == 0) l = (jok && I >= 1 && I - 1 < g.LX) ? A[(size_t)J * g.LXP + I - 1] : fill;
+    if (lane == 31) r = (jok && I + 1 < g.LX) ? A[(size_t)J * g.LXP + I + 1] : fill;
+    c = v;
+}
 __global__ void __launch_bounds__(256) k_sfd(GConst g)
 {
     const int p = blockIdx.z;
     if (!g.running[p]) return;
-    const int I = blockIdx.x * 32 + threadIdx.x, J = blockIdx.y * 8 + threadIdx.y;
-    if (I >= g.LX || J >= g.LY) return;
-    const size_t L = (size_t)J * g.LXP + I, o = (size_t)p * g.NLP + L;
+    const int lane = threadIdx.x, I = (blockIdx.x * 8 + threadIdx.y) * 32 + lane, J0 = blockIdx.y * SROWS;
+    if (I - lane >= g.LX) return;                                   // the whole warp is outside the lattice
     const double *W = g.W + (size_t)p * g.NLP;
-    double wl = W[L];
-    if (g.fdbg) g.fdbg[o] = wl;
-    int low = 8;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-        const int I2 = I + c_di[s], J2 = J + c_dj[s];
-        if (I2 < 0 || J2 < 0 || I2 >= g.LX || J2 >= g.LY) continue;
-        const double wj = W[(size_t)J2 * g.LXP + I2];
-        if (wj < wl) { low = s; wl = wj; }
+    const double INF = 1.e300;                                      // a missing neighbour is never lower
+    double pl, pc, pr, cl, cc, cr, nl, nc, nr;
+    row3(W, g, I, J0 - 1, lane, INF, pl, pc, pr);
+    row3(W, g, I, J0, lane, INF, cl, cc, cr);
+#pragma unroll 4
+    for (int J = J0; J < J0 + SROWS; ++J) {
+        row3(W, g, I, J + 1, lane, INF, nl, nc, nr);
+        if (I < g.LX && J < g.LY) {
+            const size_t o = (size_t)p * g.NLP + (size_t)J * g.LXP + I;
+            if (g.fdbg) g.fdbg[o] = cc;
+            double wl = cc;
+            int low = 8;                                            // slot order E,NE,N,NW,W,SW,S,SE, strict <, first wins
+            if (cr < wl) { low = 0; wl = cr; }
+            if (nr < wl) { low = 1; wl = nr; }
+            if (nc < wl) { low = 2; wl = nc; }
+            if (nl < wl) { low = 3; wl = nl; }
+            if (cl < wl) { low = 4; wl = cl; }
+            if (pl < wl) { low = 5; wl = pl; }
+            if (pc < wl) { low = 6; wl = pc; }
+            if (pr < wl) { low = 7; wl = pr; }
+            g.rcv[o] = (unsigned char)low;
+        }
+        pl = cl; pc = cc; pr = cr; cl = nl; cc = nc; cr = nr;
     }
-    g.rcv[o] = (unsigned char)low;
 }
 
 // donor mask (which neighbours drain into me) + arrival counters
@@ -853,7 +878,7 @@ int grid_one_step(bl_grid *ctx, double *out_pts, double *out_sse, double *out_el
         most = std::max<long long>(most, ctx->h_counters[2]);
     }
     ctx->last_sweeps = most + 1;   // the next step's first chunk: landscapes change slowly
-    grid::k_sfd<<<g2, b2, 0, st>>>(g);
+    grid::k_sfd<<<dim3((unsigned)((g.LX + 255) / 256), (unsigned)((g.LY + grid::SROWS - 1) / grid::SROWS), (unsigned)B), b2, 0, st>>>(g);
     grid::k_donors<<<g2p, b2, 0, st>>>(g);
     grid::k_discharge<<<g2, b2, 0, st>>>(g);
     grid::k_cfl<<<g2, b2, 0, st>>>(g);
