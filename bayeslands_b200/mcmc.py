@@ -208,13 +208,20 @@ class bayeslands_mcmc(object):
                 log(i, rain, erod, lik)
         return dict(pos_rain=pos_rain, pos_erod=pos_erod, pos_likl=pos_likl, accept_ratio=naccept / max(1, S_ - 1) * 100.0)
 
-    def sampler(self):
+    def sampler(self, speculate: Optional[int] = None):
         """Single random-walk Metropolis chain with the reference's draw order and output files
         (`bl_mcmc.py:515-835`): numpy's global stream for the start point, the proposals and the three unused eta
         draws, stdlib `random` for the accept test; `description.txt`, `exp_data.txt` (one `rain erod likl` row per
         sample, `storeParams` :457-480), `prediction_data/mean_pred_{elev,erdp}_<t>.txt` and `mean_pred_erdp_pts.txt`
         (post burn-in running means, :776-815) and `experiment_stats.txt` (:817-833).  Plots are out of scope.
-        Returns (pos_rain, pos_erod, pos_likl, accept_ratio)."""
+        Returns (pos_rain, pos_erod, pos_likl, accept_ratio).
+
+        `speculate=K` evaluates the next K proposals of the chain in one batched launch, assuming they are all rejected
+        (prefetching: a rejection leaves the state, and therefore the following proposal, unchanged); at the first
+        acceptance the rest of the batch is discarded and the chain goes on from the new state with the noise already
+        drawn for those iterations.  Every random draw is made in the sequential order and every evaluation uses the
+        base-shuffle seed of its iteration, so the chain, the files and the RNG states afterwards are identical to the
+        sequential run - only ~1 / acceptance-rate times fewer launches (one chain otherwise keeps one SM busy)."""
         start = time.time()
         samples = self.samples
         fn = self.filename
@@ -252,33 +259,74 @@ class bayeslands_mcmc(object):
         burnsamples = int(samples * self.burn_in)
         num_div = 0
         accept_counter = 0
-        for i in range(samples - 1):
-            p_rain = rain + np.random.normal(0, self.step_rain)
+        K = max(1, min(int(speculate or 1), self.batch))
+        seed0 = self._evals + self.shuffle_seed * 1000003                       # base-shuffle seed of iteration 0
+        nz_r, nz_e, us = [], [], []                                             # noise / uniforms drawn so far, per iteration
+
+        def draw_upto(n):
+            while len(us) < n:
+                nz_r.append(np.random.normal(0, self.step_rain))
+                nz_e.append(np.random.normal(0, self.step_erod))
+                for _ in range(3):
+                    np.random.normal(0, 1.0, 1)              # eta walk draws, consumed and unused (:670-677, F8)
+                us.append(random.uniform(0, 1))
+
+        def propose(j):
+            p_rain = rain + nz_r[j]
             if p_rain < self.rainlimits[0] or p_rain > self.rainlimits[1]:
                 p_rain = rain
-            p_erod = erod + np.random.normal(0, self.step_erod)
+            p_erod = erod + nz_e[j]
             if p_erod < self.erodlimits[0] or p_erod > self.erodlimits[1]:
                 p_erod = erod
-            for _ in range(3):
-                np.random.normal(0, 1.0, 1)                  # eta walk draws, consumed and unused (:670-677, F8)
-            likelihood_proposal, elev, erdp, pts = evaluate(p_rain, p_erod)
-            diff_likelihood = likelihood_proposal - likelihood
-            try:
-                mh_prob = min(1, math.exp(diff_likelihood))
-            except OverflowError:
-                mh_prob = 1
-            u = random.uniform(0, 1)
-            if u < mh_prob:
-                likelihood, rain, erod = likelihood_proposal, p_rain, p_erod
-                pos_rain[i + 1], pos_erod[i + 1], pos_likl[i + 1] = rain, erod, likelihood
-                prev = (elev, erdp, pts)
-                accept_counter += 1
+            return p_rain, p_erod
+
+        i = 0
+        while i < samples - 1:
+            n = min(K, samples - 1 - i)
+            if K == 1:
+                # the sequential order of the reference: draw, evaluate, then the uniform
+                nz_r.append(np.random.normal(0, self.step_rain)); nz_e.append(np.random.normal(0, self.step_erod))
+                for _ in range(3):
+                    np.random.normal(0, 1.0, 1)
+                props = [propose(i)]
+                sse, bpts, belev, berdp = self.blackBox_batch([props[0][0]], [props[0][1]], grids=True, seeds=[seed0 + i])
+                us.append(random.uniform(0, 1))
             else:
-                pos_rain[i + 1], pos_erod[i + 1], pos_likl[i + 1] = pos_rain[i], pos_erod[i], pos_likl[i]
-            store(pos_rain[i + 1], pos_erod[i + 1], pos_likl[i + 1])
-            if i > burnsamples:
-                sum_elev += prev[0]; sum_erdp += prev[1]; sum_pts += prev[2]
-                num_div += 1
+                draw_upto(i + n)
+                props = [propose(i + j) for j in range(n)]
+                sse, bpts, belev, berdp = self.blackBox_batch([q[0] for q in props], [q[1] for q in props], grids=False,
+                                                              seeds=seed0 + i + np.arange(n))
+            liks, _ = log_likelihood(sse, self.G, bpts, self.real_erdp_pts, self.likl_sed)
+            used = n
+            for j in range(n):
+                likelihood_proposal = float(liks[j])
+                diff_likelihood = likelihood_proposal - likelihood
+                try:
+                    mh_prob = min(1, math.exp(diff_likelihood))
+                except OverflowError:
+                    mh_prob = 1
+                it = i + j
+                accepted = us[it] < mh_prob
+                if accepted:
+                    likelihood, rain, erod = likelihood_proposal, props[j][0], props[j][1]
+                    pos_rain[it + 1], pos_erod[it + 1], pos_likl[it + 1] = rain, erod, likelihood
+                    if K == 1:
+                        prev = (belev[0], berdp[0], bpts[0])
+                    else:                                    # prediction grids of the accepted proposal (same seed)
+                        _, p1, e1, d1 = self.blackBox_batch([rain], [erod], grids=True, seeds=[seed0 + it])
+                        prev = (e1[0], d1[0], p1[0])
+                    accept_counter += 1
+                else:
+                    pos_rain[it + 1], pos_erod[it + 1], pos_likl[it + 1] = pos_rain[it], pos_erod[it], pos_likl[it]
+                store(pos_rain[it + 1], pos_erod[it + 1], pos_likl[it + 1])
+                if it > burnsamples:
+                    sum_elev += prev[0]; sum_erdp += prev[1]; sum_pts += prev[2]
+                    num_div += 1
+                if accepted:
+                    used = j + 1                             # the rest of the batch assumed a rejection here
+                    break
+            i += used
+        self._evals = seed0 - self.shuffle_seed * 1000003 + samples - 1
         accept_ratio = accept_counter / (samples * 1.0) * 100
         if fn:
             div = max(num_div, 1)

@@ -170,3 +170,27 @@ def test_sampler_writes_reference_outputs_and_is_seeded(crater_fast, tmp_path):
     g = np.loadtxt(tmp_path / "run0" / "prediction_data" / "mean_pred_elev_15000.txt")
     assert g.shape == (123, 123) and 20.0 < g.mean() < 120.0
     assert 0.0 <= out[0][3] <= 100.0
+
+
+def test_speculative_sampler_is_the_same_chain(crater_fast, tmp_path):
+    """sampler(speculate=K) evaluates K proposals ahead assuming rejections: the chain, the files it writes and the state
+    of both RNG streams afterwards must be identical to the sequential sampler's."""
+    import filecmp
+    import os
+    res, states = [], []
+    for rep, K in enumerate((None, 16)):
+        mc = _mc(crater_fast, 16, samples=60)
+        mc.filename = str(tmp_path / ("run%d" % rep))
+        np.random.seed(5); random.seed(6)
+        res.append(mc.sampler(speculate=K))
+        states.append((np.random.get_state()[1].copy(), np.random.get_state()[2], random.getstate()))
+        launches = mc.engine.launches
+        res[-1] = res[-1] + (launches,)
+    a, b = res
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+    assert 0 < a[3] < 100.0, "the chain must contain acceptances and rejections for the test to mean anything"
+    assert np.array_equal(states[0][0], states[1][0]) and states[0][1] == states[1][1] and states[0][2] == states[1][2]
+    for f in ("exp_data.txt", os.path.join("prediction_data", "mean_pred_elev_15000.txt"),
+              os.path.join("prediction_data", "mean_pred_erdp_pts.txt")):
+        assert filecmp.cmp(tmp_path / "run0" / f, tmp_path / "run1" / f, shallow=False), f
+    assert b[4] < a[4]                                        # fewer launches

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--config", default="crater_fast")
     ap.add_argument("--samples", type=int, default=1000)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--speculate", type=int, default=0, help="evaluate this many proposals ahead per launch (same chain)")
     a = ap.parse_args()
     d, inp, m, simtime, rl, el, coords, likl_sed = bench.load_config(a.config)
 
@@ -44,14 +45,16 @@ def main():
              float(np.ptp(lik[0]))))
     del mc
     np.random.seed(0); random.seed(0)
-    mc = make(1, a.samples, os.path.join(a.out, "chain") if a.out else None)
+    mc = make(max(1, a.speculate), a.samples, os.path.join(a.out, "chain") if a.out else None)
     t0 = time.perf_counter()
-    pos_rain, pos_erod, pos_likl, acc = mc.sampler()
+    pos_rain, pos_erod, pos_likl, acc = mc.sampler(speculate=a.speculate or None)
     dt = time.perf_counter() - t0
     burn = int(0.05 * a.samples)
-    print("single chain, %d samples: %.2f s = %.1f evals/s (batch of 1: one CTA busy); accepted %.1f %%; posterior mean rain %.3f "
-          "erod %.3e; max L %.1f" % (a.samples, dt, (a.samples + 1) / dt, acc, pos_rain[burn:].mean(), pos_erod[burn:].mean(),
-                                     pos_likl.max()))
+    print("single chain, %d samples, %s: %.2f s = %.1f chain iterations/s, %d launches; accepted %.1f %%; posterior mean rain %.3f "
+          "erod %.3e; max L %.1f; chain digest %.10e" % (
+              a.samples, ("speculating %d ahead" % a.speculate) if a.speculate else "sequential (one CTA busy)", dt,
+              (a.samples + 1) / dt, mc.engine.launches, acc, pos_rain[burn:].mean(), pos_erod[burn:].mean(), pos_likl.max(),
+              float(np.sum(pos_rain * 1e3 + pos_erod * 1e7 + pos_likl * 1e-3))))
 
 
 if __name__ == "__main__":
