@@ -343,10 +343,11 @@ __global__ void k_fill_begin(GConst g)
 // Each warp owns 32 columns and walks SROWS rows upwards with a 3 x 3 register window: one coalesced load per node, the
 // left / right columns come from the neighbouring lanes (the two edge lanes fetch theirs).
 constexpr int SROWS = 16;
-__device__ __forceinline__ void row3(const double *A, const GConst &g, int I, int J, int lane, double fill, double &l, double &c, double &r)
+template <typename T>
+__device__ __forceinline__ void row3(const T *A, const GConst &g, int I, int J, int lane, T fill, T &l, T &c, T &r)
 {
     const bool jok = (J >= 0 && J < g.LY);
-    const double v = (jok && I < g.LX) ? A[(size_t)J * g.LXP + I] : fill;
+    const T v = (jok && I < g.LX) ? A[(size_t)J * g.LXP + I] : fill;
     l = __shfl_up_sync(0xffffffffu, v, 1);
     r = __shfl_down_sync(0xffffffffu, v, 1);
     if (lane == 0) l = (jok && I >= 1 && I - 1 < g.LX) ? A[(size_t)J * g.LXP + I - 1] : fill;
@@ -359,7 +360,9 @@ __global__ void __launch_bounds__(256) k_sfd(GConst g)
     if (!g.running[p]) return;
     const int lane = threadIdx.x, I = (blockIdx.x * 8 + threadIdx.y) * 32 + lane, J0 = blockIdx.y * SROWS;
     if (I - lane >= g.LX) return;                                   // the whole warp is outside the lattice
-    const double *W = g.W + (size_t)p * g.NLP;
+    const double *__restrict__ W = g.W + (size_t)p * g.NLP;
+    unsigned char *__restrict__ rcvp = g.rcv + (size_t)p * g.NLP;
+    double *__restrict__ fdbg = g.fdbg ? g.fdbg + (size_t)p * g.NLP : nullptr;
     const double INF = 1.e300;                                      // a missing neighbour is never lower
     double pl, pc, pr, cl, cc, cr, nl, nc, nr;
     row3(W, g, I, J0 - 1, lane, INF, pl, pc, pr);
@@ -368,8 +371,8 @@ __global__ void __launch_bounds__(256) k_sfd(GConst g)
     for (int J = J0; J < J0 + SROWS; ++J) {
         row3(W, g, I, J + 1, lane, INF, nl, nc, nr);
         if (I < g.LX && J < g.LY) {
-            const size_t o = (size_t)p * g.NLP + (size_t)J * g.LXP + I;
-            if (g.fdbg) g.fdbg[o] = cc;
+            const size_t o = (size_t)J * g.LXP + I;
+            if (fdbg) fdbg[o] = cc;
             double wl = cc;
             int low = 8;                                            // slot order E,NE,N,NW,W,SW,S,SE, strict <, first wins
             if (cr < wl) { low = 0; wl = cr; }
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(256) k_sfd(GConst g)
             if (pl < wl) { low = 5; wl = pl; }
             if (pc < wl) { low = 6; wl = pc; }
             if (pr < wl) { low = 7; wl = pr; }
-            g.rcv[o] = (unsigned char)low;
+            rcvp[o] = (unsigned char)low;
         }
         pl = cl; pc = cc; pr = cr; cl = nl; cc = nc; cr = nr;
     }
@@ -391,20 +394,44 @@ __global__ void __launch_bounds__(256) k_donors(GConst g)
 {
     const int p = blockIdx.z;
     if (!g.running[p]) return;
-    const int I = blockIdx.x * 32 + threadIdx.x, J = blockIdx.y * 8 + threadIdx.y;
-    if (I >= g.LXP || J >= g.LY) return;
-    const size_t L = (size_t)J * g.LXP + I, o = (size_t)p * g.NLP + L;
-    if ((I & 3) == 0) g.cnt[o >> 2] = 0u;
-    if (I >= g.LX) return;
-    const unsigned char *rcv = g.rcv + (size_t)p * g.NLP;
-    unsigned m = 0u;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-        const int I2 = I + c_di[s], J2 = J + c_dj[s];
-        if (I2 < 0 || J2 < 0 || I2 >= g.LX || J2 >= g.LY) continue;
-        if (rcv[(size_t)J2 * g.LXP + I2] == ((s + 4) & 7)) m |= 1u << s;
+    const int lane = threadIdx.x, I = (blockIdx.x * 8 + threadIdx.y) * 32 + lane, J0 = blockIdx.y * SROWS;
+    if (I - lane >= g.LXP) return;
+    const int NONE = 9;                                             // a missing neighbour drains nowhere
+    const unsigned char *R = g.rcv + (size_t)p * g.NLP;
+    int pl, pc, pr, cl, cc, cr, nl, nc, nr;
+    auto row = [&](int J, int &l, int &c, int &r) {
+        const bool jok = (J >= 0 && J < g.LY);
+        const int v = (jok && I < g.LX) ? (int)R[(size_t)J * g.LXP + I] : NONE;
+        l = __shfl_up_sync(0xffffffffu, v, 1);
+        r = __shfl_down_sync(0xffffffffu, v, 1);
+        if (lane == 0) l = (jok && I >= 1 && I - 1 < g.LX) ? (int)R[(size_t)J * g.LXP + I - 1] : NONE;
+        if (lane == 31) r = (jok && I + 1 < g.LX) ? (int)R[(size_t)J * g.LXP + I + 1] : NONE;
+        c = v;
+    };
+    row(J0 - 1, pl, pc, pr);
+    row(J0, cl, cc, cr);
+#pragma unroll 4
+    for (int J = J0; J < J0 + SROWS; ++J) {
+        row(J + 1, nl, nc, nr);
+        if (I < g.LXP && J < g.LY) {
+            const size_t o = (size_t)p * g.NLP + (size_t)J * g.LXP + I;
+            if ((I & 3) == 0) g.cnt[o >> 2] = 0u;
+            if (I < g.LX) {
+                // neighbour in slot s drains into me when its receiver slot is the opposite one, (s + 4) & 7
+                unsigned m = 0u;
+                if (cr == 4) m |= 1u;        // E
+                if (nr == 5) m |= 2u;        // NE
+                if (nc == 6) m |= 4u;        // N
+                if (nl == 7) m |= 8u;        // NW
+                if (cl == 0) m |= 16u;       // W
+                if (pl == 1) m |= 32u;       // SW
+                if (pc == 2) m |= 64u;       // S
+                if (pr == 3) m |= 128u;      // SE
+                g.don[o] = (unsigned char)m;
+            }
+        }
+        pl = cl; pc = cc; pr = cr; cl = nl; cc = nc; cr = nr;
     }
-    g.don[o] = (unsigned char)m;
 }
 
 // discharge (FLOWalgo.f90:53-81; compute_flow flowNetwork.py:418-443): wait-free tree accumulation
@@ -879,7 +906,7 @@ int grid_one_step(bl_grid *ctx, double *out_pts, double *out_sse, double *out_el
     }
     ctx->last_sweeps = most + 1;   // the next step's first chunk: landscapes change slowly
     grid::k_sfd<<<dim3((unsigned)((g.LX + 255) / 256), (unsigned)((g.LY + grid::SROWS - 1) / grid::SROWS), (unsigned)B), b2, 0, st>>>(g);
-    grid::k_donors<<<g2p, b2, 0, st>>>(g);
+    grid::k_donors<<<dim3((unsigned)((g.LXP + 255) / 256), (unsigned)((g.LY + grid::SROWS - 1) / grid::SROWS), (unsigned)B), b2, 0, st>>>(g);
     grid::k_discharge<<<g2, b2, 0, st>>>(g);
     grid::k_cfl<<<g2, b2, 0, st>>>(g);
     grid::k_dt<<<(B + 127) / 128, 128, 0, st>>>(g);
