@@ -36,6 +36,7 @@ class GridEngine:
         self.tdev = torch.device("cuda", self.device)
         self.LY, self.LX = lat.shape
         self.G = self.LY * self.LX
+        self.grid_ny, self.grid_nx = self.LY, self.LX          # the output grid of interpolateArray is the lattice itself
         k = self._keep = dict(z0=np.ascontiguousarray(lat.z0, dtype=np.float64),
                               flags=np.ascontiguousarray(lat.flags, dtype=np.uint8),
                               parent=np.ascontiguousarray(lat.parent, dtype=np.int32))
@@ -94,7 +95,9 @@ class GridEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
 
-    def reset(self, rain, erod):
+    def reset(self, rain, erod, seeds=None):
+        """`seeds` is accepted for interface parity with `Engine.reset` and ignored: no stack order is built here, so the
+        base shuffle (flowNetwork.py:316) has nothing to act on."""
         def to_dev(x, buf):
             if isinstance(x, torch.Tensor):
                 buf.copy_(x.to(dtype=torch.float64), non_blocking=True)

@@ -49,7 +49,7 @@ class bayeslands_mcmc(object):
     def __init__(self, muted, simtime, samples, real_elev, real_erdp, real_erdp_pts, erdp_coords, filename,
                  xmlinput, erodlimits, rainlimits, mlimit, nlimit, run_nb, likl_sed, batch: int = 1,
                  device: int = 0, dem_xyz: Optional[np.ndarray] = None, sealevel: Optional[np.ndarray] = None,
-                 base_dir: Optional[str] = None, mesh=None, shuffle_seed: int = 0):
+                 base_dir: Optional[str] = None, mesh=None, shuffle_seed: int = 0, engine=None):
         self.filename = filename
         self.input = xmlinput
         self.real_elev = np.asarray(real_elev, dtype=np.float64)
@@ -73,16 +73,23 @@ class bayeslands_mcmc(object):
         self.burn_in = 0.05
         # ---- built once instead of per proposal
         self.inp = xmlinput if isinstance(xmlinput, config.Input) else config.parse_xml(xmlinput, base_dir=base_dir)
-        if mesh is None:
-            if dem_xyz is None:
-                dem_xyz = np.loadtxt(self.inp.demfile)
-            mesh = meshmod.build_from_dem(dem_xyz, self.inp.btype, self.inp.Afactor)
-        if sealevel is None and self.inp.seafile is not None:
-            sealevel = np.loadtxt(self.inp.seafile)
-        self.mesh = mesh
-        self.batch = int(batch)
-        self.engine = Engine(mesh, self.inp, self.batch, device=device, real_elev=self.real_elev,
-                             erdp_coords=self.erdp_coords, sealevel=sealevel)
+        if engine is not None:
+            # a ready engine, e.g. a `grid_engine.GridEngine` for a regular lattice too large for one CTA; it must have been
+            # built with the same real_elev / erdp_coords (it computes the SSE and the point series on the device)
+            self.mesh = engine
+            self.batch = int(engine.B)
+            self.engine = engine
+        else:
+            if mesh is None:
+                if dem_xyz is None:
+                    dem_xyz = np.loadtxt(self.inp.demfile)
+                mesh = meshmod.build_from_dem(dem_xyz, self.inp.btype, self.inp.Afactor)
+            if sealevel is None and self.inp.seafile is not None:
+                sealevel = np.loadtxt(self.inp.seafile)
+            self.mesh = mesh
+            self.batch = int(batch)
+            self.engine = Engine(mesh, self.inp, self.batch, device=device, real_elev=self.real_elev,
+                                 erdp_coords=self.erdp_coords, sealevel=sealevel)
         self.G = self.engine.G
         self.shuffle_seed = int(shuffle_seed)
         self._evals = 0

@@ -151,3 +151,37 @@ def test_lattice_full_size_properties():
     assert np.all((cd - ch)[inner] <= 1e-12)
     del eng
     torch.cuda.empty_cache()
+
+
+def test_mcmc_front_end_on_the_lattice_engine():
+    """bayeslands_mcmc(engine=GridEngine): likelihood_batch and the (speculative) sampler over a regular-grid landscape,
+    likelihoods equal to the oracle's (bl_mcmc.py:482-513 on the lattice-shaped grids)."""
+    import random
+    from bayeslands_b200.grid_engine import GridEngine
+    from bayeslands_b200.mcmc import bayeslands_mcmc
+    from oracle import oracle
+    T = 20000.0
+    m, inp, disp, lat = synthetic(24, 20, T=T)
+    ext = lat.ext
+    truth = oracle.OracleModel(m, inp, seed=1, disp=disp)
+    truth.reset(1.5, 5e-6, seed=1)
+    truth.run_to_time(T)
+    real = truth.z[ext] + 0.3 * np.random.default_rng(3).standard_normal(ext.shape)
+    coords = [[5, 7], [10, 12], [15, 3]]
+    eng = GridEngine(lat, inp, 6, real_elev=real, erdp_coords=coords)
+    real_pts = np.zeros((4, 3))
+    mc = bayeslands_mcmc(True, T, 30, real, None, real_pts, coords, None, inp, [3e-6, 7e-6], [0.5, 2.5], [0.4, 0.6], [0.9, 1.1],
+                         "lat", False, engine=eng)
+    rain = np.array([0.7, 1.2, 1.5, 1.9, 2.2, 2.4]); erod = np.array([3.5e-6, 4e-6, 5e-6, 5.5e-6, 6e-6, 6.5e-6])
+    lik, _ = mc.likelihood_batch(rain, erod)
+    for b in range(6):
+        om = oracle.OracleModel(m, inp, seed=1, disp=disp)
+        om.reset(rain[b], erod[b], seed=1)
+        om.run_to_time(T)
+        want, _ = oracle.likelihood(om.z[ext], real, np.zeros((4, 3)), real_pts, False)
+        assert abs(lik[b] - want) <= 1e-9 * abs(want), (b, lik[b], want)
+    out = []
+    for K in (None, 6):
+        np.random.seed(1); random.seed(2)
+        out.append(mc.sampler(speculate=K))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][2], out[1][2]) and out[0][3] == out[1][3]
