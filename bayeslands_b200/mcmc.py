@@ -223,7 +223,8 @@ class bayeslands_mcmc(object):
         (post burn-in running means, :776-815) and `experiment_stats.txt` (:817-833).  Plots are out of scope.
         Returns (pos_rain, pos_erod, pos_likl, accept_ratio).
 
-        `speculate=K` evaluates the next K proposals of the chain in one batched launch, assuming they are all rejected
+        `speculate=K` (default: the engine's batch size; 1 = strictly sequential evaluation) evaluates the next K proposals
+        of the chain in one batched launch, assuming they are all rejected
         (prefetching: a rejection leaves the state, and therefore the following proposal, unchanged); at the first
         acceptance the rest of the batch is discarded and the chain goes on from the new state with the noise already
         drawn for those iterations.  Every random draw is made in the sequential order and every evaluation uses the
@@ -266,7 +267,7 @@ class bayeslands_mcmc(object):
         burnsamples = int(samples * self.burn_in)
         num_div = 0
         accept_counter = 0
-        K = max(1, min(int(speculate or 1), self.batch))
+        K = max(1, min(int(self.batch if speculate is None else speculate), self.batch))
         seed0 = self._evals + self.shuffle_seed * 1000003                       # base-shuffle seed of iteration 0
         nz_r, nz_e, us = [], [], []                                             # noise / uniforms drawn so far, per iteration
 

@@ -178,7 +178,7 @@ def test_speculative_sampler_is_the_same_chain(crater_fast, tmp_path):
     import filecmp
     import os
     res, states = [], []
-    for rep, K in enumerate((None, 16)):
+    for rep, K in enumerate((1, 16)):
         mc = _mc(crater_fast, 16, samples=60)
         mc.filename = str(tmp_path / ("run%d" % rep))
         np.random.seed(5); random.seed(6)

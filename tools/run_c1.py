@@ -47,7 +47,7 @@ def main():
     np.random.seed(0); random.seed(0)
     mc = make(max(1, a.speculate), a.samples, os.path.join(a.out, "chain") if a.out else None)
     t0 = time.perf_counter()
-    pos_rain, pos_erod, pos_likl, acc = mc.sampler(speculate=a.speculate or None)
+    pos_rain, pos_erod, pos_likl, acc = mc.sampler(speculate=a.speculate or 1)
     dt = time.perf_counter() - t0
     burn = int(0.05 * a.samples)
     print("single chain, %d samples, %s: %.2f s = %.1f chain iterations/s, %d launches; accepted %.1f %%; posterior mean rain %.3f "
