@@ -172,47 +172,70 @@ class bayeslands_mcmc(object):
         return [likelihood, pred_elev_vec, pred_erdp_vec, pred_erdp_pts_vec]
 
     # ---- accept/reject core of sampler (bl_mcmc.py:633-704, :747-755) -------------------------------
-    def sampler_chains(self, nchains: Optional[int] = None, np_seed: int = 0, py_seed: int = 0, log=None):
-        """`nchains` independent random-walk Metropolis chains advanced in lock step, one batched forward
-        evaluation per iteration.  Chain c draws from its own numpy RandomState(np_seed + c) and
-        random.Random(py_seed + c) in the reference's order per iteration: normal(rain), normal(erod),
-        3 x normal(size=1) for the eta walk (consumed, unused - F8), then uniform for the accept test.
+    def sampler_chains(self, nchains: Optional[int] = None, np_seed: int = 0, py_seed: int = 0, log=None,
+                       speculate: Optional[int] = None):
+        """`nchains` independent random-walk Metropolis chains, batched forward evaluations.  Chain c draws from its own
+        numpy RandomState(np_seed + c) and random.Random(py_seed + c) in the reference's order per iteration:
+        normal(rain), normal(erod), 3 x normal(size=1) for the eta walk (consumed, unused - F8), then uniform for the
+        accept test.  `speculate=K` (default batch // nchains) evaluates the next K proposals of every chain per launch
+        assuming rejections, as `sampler` does; every evaluation keeps the base-shuffle seed of its (iteration, chain), so
+        the chains are identical for any K.  `log(i, rain, erod, lik)` is called per iteration only when K = 1.
         Returns dict(pos_rain, pos_erod, pos_likl [samples, nchains], accept_ratio[nchains])."""
         C_ = int(nchains or self.batch)
         S_ = self.samples
+        K = max(1, int(speculate if speculate is not None else self.batch // C_))
+        K = max(1, min(K, self.batch // C_))
         rs = [np.random.RandomState(np_seed + c) for c in range(C_)]
         pr = [random.Random(py_seed + c) for c in range(C_)]
         rain = np.array([r.uniform(self.rainlimits[0], self.rainlimits[1]) for r in rs])
         erod = np.array([r.uniform(self.erodlimits[0], self.erodlimits[1]) for r in rs])
         lik, _ = self.likelihood_batch(rain, erod)      # the reference evaluates the start twice (:569, :610)
+        seed0 = self._evals + self.shuffle_seed * 1000003          # seed of (iteration 0, chain 0); (i, c) -> seed0 + i*C + c
         pos_rain = np.zeros((S_, C_)); pos_erod = np.zeros((S_, C_)); pos_likl = np.zeros((S_, C_))
         pos_rain[0], pos_erod[0], pos_likl[0] = rain, erod, lik
         naccept = np.zeros(C_, dtype=np.int64)
-        for i in range(S_ - 1):
-            p_rain = rain.copy(); p_erod = erod.copy()
-            for c in range(C_):
-                v = rain[c] + rs[c].normal(0, self.step_rain)
-                if not (v < self.rainlimits[0] or v > self.rainlimits[1]):
-                    p_rain[c] = v
-                v = erod[c] + rs[c].normal(0, self.step_erod)
-                if not (v < self.erodlimits[0] or v > self.erodlimits[1]):
-                    p_erod[c] = v
+        noise = [[] for _ in range(C_)]                             # per chain: (d_rain, d_erod, u) per iteration drawn so far
+        it = np.zeros(C_, dtype=np.int64)                           # next iteration of every chain
+
+        def draw_upto(c, n):
+            while len(noise[c]) < n:
+                dr = rs[c].normal(0, self.step_rain); de = rs[c].normal(0, self.step_erod)
                 for _ in range(3):          # eta random walk draws (bl_mcmc.py:670-677): consumed, never used (F8)
                     rs[c].normal(0, 1.0, 1)
-            lik_p, _ = self.likelihood_batch(p_rain, p_erod)
+                noise[c].append((dr, de, pr[c].uniform(0, 1)))
+
+        while np.any(it < S_ - 1):
+            pr_, pe_, owner = [], [], []
             for c in range(C_):
-                diff = lik_p[c] - lik[c]
+                n = int(min(K, S_ - 1 - it[c]))
+                draw_upto(c, int(it[c]) + n)
+                for j in range(n):
+                    dr, de, _ = noise[c][int(it[c]) + j]
+                    v = rain[c] + dr
+                    p_r = rain[c] if (v < self.rainlimits[0] or v > self.rainlimits[1]) else v
+                    v = erod[c] + de
+                    p_e = erod[c] if (v < self.erodlimits[0] or v > self.erodlimits[1]) else v
+                    pr_.append(p_r); pe_.append(p_e); owner.append((c, int(it[c]) + j))
+            seeds = np.array([seed0 + i * C_ + c for c, i in owner], dtype=np.int64)
+            lik_p, _ = self.likelihood_batch(np.array(pr_), np.array(pe_), seeds=seeds)
+            stopped = np.zeros(C_, dtype=bool)
+            for q, (c, i) in enumerate(owner):
+                if stopped[c]:
+                    continue
+                diff = lik_p[q] - lik[c]
                 try:
                     mh = min(1, math.exp(diff))
                 except OverflowError:
                     mh = 1
-                u = pr[c].uniform(0, 1)
-                if u < mh:
-                    lik[c], rain[c], erod[c] = lik_p[c], p_rain[c], p_erod[c]
+                if noise[c][i][2] < mh:
+                    lik[c], rain[c], erod[c] = lik_p[q], pr_[q], pe_[q]
                     naccept[c] += 1
-            pos_rain[i + 1], pos_erod[i + 1], pos_likl[i + 1] = rain, erod, lik
-            if log is not None:
-                log(i, rain, erod, lik)
+                    stopped[c] = True                      # the rest of this chain's look-ahead assumed a rejection
+                pos_rain[i + 1, c], pos_erod[i + 1, c], pos_likl[i + 1, c] = rain[c], erod[c], lik[c]
+                it[c] = i + 1
+            if log is not None and K == 1:
+                log(int(it.min()) - 1, rain, erod, lik)
+        self._evals = seed0 - self.shuffle_seed * 1000003 + (S_ - 1) * C_
         return dict(pos_rain=pos_rain, pos_erod=pos_erod, pos_likl=pos_likl, accept_ratio=naccept / max(1, S_ - 1) * 100.0)
 
     def sampler(self, speculate: Optional[int] = None):

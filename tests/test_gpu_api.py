@@ -194,3 +194,16 @@ def test_speculative_sampler_is_the_same_chain(crater_fast, tmp_path):
               os.path.join("prediction_data", "mean_pred_erdp_pts.txt")):
         assert filecmp.cmp(tmp_path / "run0" / f, tmp_path / "run1" / f, shallow=False), f
     assert b[4] < a[4]                                        # fewer launches
+
+
+def test_speculative_sampler_chains_are_the_same_chains(crater_fast):
+    """sampler_chains(speculate=K): K proposals ahead per chain and launch; identical chains for any K."""
+    outs = []
+    for K in (1, 8):
+        mc = _mc(crater_fast, 16, samples=40)
+        mc._evals = 0
+        outs.append((mc.sampler_chains(2, np_seed=21, py_seed=22, speculate=K), mc.engine.launches, mc._evals))
+    (a, la, ea), (b, lb, eb) = outs
+    for k in ("pos_rain", "pos_erod", "pos_likl", "accept_ratio"):
+        assert np.array_equal(a[k], b[k]), k
+    assert 0 < a["accept_ratio"].sum() < 200.0 and lb < la and ea == eb
