@@ -69,3 +69,33 @@ def test_mse_minimum_at_true_parameters(crater_fast):
     # the model explains > 90 % of the change from the initial topography
     init = float(np.mean((om.interpolate(m.elevation) - real) ** 2))
     assert mr[2] < 0.1 * init
+
+
+def test_oracle_matches_reference_sfd_vectors(crater_fast):
+    """tests/golden/sfd_reference_vectors.npz holds what the reference's own libUtils/sfd.c returns on the crater_fast
+    mesh (tools/make_golden_sfd.py): the oracle's restatement must reproduce every array bit for bit - also where
+    /root/reference and oracle/_ref do not exist."""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_sfd import surfaces
+    from oracle import oracle
+    d, inp, m = crater_fast
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sfd_reference_vectors.npz"))
+    assert int(g["N"]) == m.N
+    L = oracle.lib()
+    om = oracle.OracleModel(m, inp)
+    c_dp, c_ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    N = m.N
+    for t, (z, fill) in enumerate(surfaces(m)):
+        b = np.zeros(N, dtype=np.int32); r = np.zeros(N, dtype=np.int32)
+        L.or_directions_base(C.byref(om.cm), z.ctypes.data_as(c_dp), b.ctypes.data_as(c_ip), r.ctypes.data_as(c_ip))
+        assert np.array_equal(r, g["rcv1_%d" % t]) and np.array_equal(b, g["base1_%d" % t])
+        mh = np.zeros(N); md = np.zeros(N)
+        L.or_directions(C.byref(om.cm), fill.ctypes.data_as(c_dp), z.ctypes.data_as(c_dp), b.ctypes.data_as(c_ip),
+                        r.ctypes.data_as(c_ip), mh.ctypes.data_as(c_dp), md.ctypes.data_as(c_dp))
+        assert np.array_equal(r, g["rcv_%d" % t]) and np.array_equal(b, g["base_%d" % t])
+        assert np.array_equal(mh, g["maxh_%d" % t]) and np.array_equal(md, g["maxdep_%d" % t])
+        df = np.zeros(N)
+        L.or_diffusion(C.byref(om.cm), z.ctypes.data_as(c_dp), df.ctypes.data_as(c_dp))
+        assert np.array_equal(df, g["diff_%d" % t])

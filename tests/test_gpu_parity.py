@@ -199,3 +199,24 @@ def test_synthetic_uplift_regular_grid_bit_exact(generic, monkeypatch):
             for f in INT_FIELDS + FP_FIELDS:
                 assert np.array_equal(eng.field(f, b), getattr(om, f)), (step, b, f)
             assert sc["tNow"][b] == om.tNow and sc["status"][b] == 0
+
+
+def test_first_step_receivers_match_reference_sfd_vectors(crater_fast):
+    """The real-surface receivers of the first time step are `sfd.directions_base` of the initial elevation: the CUDA
+    path (through the C-ABI) must return exactly what the reference's own sfd.c returned (tests/golden)."""
+    import os
+    from bayeslands_b200.engine import Engine
+    from conftest import ROOT
+    d, inp, m = crater_fast
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sfd_reference_vectors.npz"))
+    for generic in (0, 1):
+        if generic:
+            os.environ["BL_FORCE_GENERIC"] = "1"
+        try:
+            eng = Engine(m, inp, 2)
+            eng.reset(np.array([1.5, 0.5]), np.array([5e-5, 4e-5]), np.array([1, 2], dtype=np.int64))
+            eng.step(15000.0)
+            for b in range(2):
+                assert np.array_equal(eng.field("rcv1", b), g["rcv1_0"]), (generic, b)
+        finally:
+            os.environ.pop("BL_FORCE_GENERIC", None)
