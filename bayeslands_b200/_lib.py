@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbayeslands_b200.so")
+LIB_PATH = os.environ.get("BAYESLANDS_B200_LIB", os.path.join(HERE, "libbayeslands_b200.so"))   # override: profiling builds
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
