@@ -1085,14 +1085,20 @@ __device__ void phase_streampower_serial(const DevConst &c, Smem &S, double erod
 __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
 {
     const int N = c.N, tid = threadIdx.x;
-    const double *z = S.P.f[F_Z], *W = S.P.f[F_FILLH], *pitVol = S.P.f[F_PITVOL];
-    const double *cdepo = S.P.f[F_DEPO], *cero = S.P.f[F_ERO];
+    // distinct per-proposal arrays: __restrict__ lets the streaming loops below keep several nodes' loads in flight
+    const double *__restrict__ z = S.P.f[F_Z], *__restrict__ W = S.P.f[F_FILLH], *__restrict__ pitVol = S.P.f[F_PITVOL];
+    const double *__restrict__ cdepo = S.P.f[F_DEPO], *__restrict__ cero = S.P.f[F_ERO];
     const int *pitID = S.P.i[I_PITID], *pos1 = S.P.i[I_POS1], *ns1 = S.P.i[I_NS], *stack1 = S.P.i[I_STACK1];
-    double *dep = S.P.f[F_SEDIN], *dth = S.P.f[F_DTHICK], *tmpv = S.P.f[F_VAL], *sedflux = S.P.f[F_SEDFLUX];
+    double *__restrict__ dep = S.P.f[F_SEDIN], *__restrict__ dth = S.P.f[F_DTHICK], *tmpv = S.P.f[F_VAL];
+    double *__restrict__ sedflux = S.P.f[F_SEDFLUX];
+    int *__restrict__ kindA = S.P.i[I_KIND];
+    const unsigned char *__restrict__ flagsA = c.flags;
+    const double *__restrict__ areaA = c.area;
     int *land = S.P.i[I_LB], *memb = S.P.i[I_MEMB];
     int marine = 0;
+#pragma unroll 4
     for (int k = tid; k < N; k += TPB) {
-        const bool in = c.flags[k] & 1;
+        const bool in = flagsA[k] & 1;
         double d = in ? cdepo[k] : 0.;
         double th = 0.;
         int island = 0;
@@ -1109,11 +1115,11 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
                 }
             }
             if (zk <= sea) { sumdep = sumdep + d; if (sumdep > 0.) { marine = 1; island = 2; } }
-            if (plain) { th = d / c.area[k]; d = 0.; }
+            if (plain) { th = d / areaA[k]; d = 0.; }
         }
         dep[k] = d;
         dth[k] = th;
-        S.P.i[I_KIND][k] = island;
+        kindA[k] = island;
     }
     marine = __syncthreads_or(marine);
     if (c.depo != 0) {
@@ -1186,17 +1192,19 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
         if (marine) phase_marine_distribution(c, S, sea);     // flowNetwork.py:769-776
         // forced deposition of anything left (flowNetwork.py:782-785)
         int any = 0;
+#pragma unroll 4
         for (int k = tid; k < N; k += TPB) any |= (dep[k] != 0.);
         any = __syncthreads_or(any);
         if (any)
             for (int k = tid; k < N; k += TPB)
-                if (c.flags[k] & 1) dth[k] += dep[k] / c.area[k];
+                if (flagsA[k] & 1) dth[k] += dep[k] / areaA[k];
         __syncthreads();
     }
+#pragma unroll 4
     for (int k = tid; k < N; k += TPB) {
         double sf = 0.;
-        if (c.flags[k] & 1) {
-            const double erosion = cero[k] / c.area[k];
+        if (flagsA[k] & 1) {
+            const double erosion = cero[k] / areaA[k];
             sf = erosion + dth[k];
         }
         sedflux[k] = sf;
