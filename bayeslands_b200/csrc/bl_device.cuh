@@ -23,6 +23,14 @@ struct Smem {
     double dbuf[8];
 };
 
+// diagnostics: thread 0 adds the cycles since the previous tick to slot i of this CTA's phase_cyc row (slots >= 16)
+struct SubTick { long long *p, t; };
+__device__ inline long long sub_clock() { return clock64(); }
+__device__ inline SubTick sub_tick_begin(const DevConst &c) { SubTick s; s.p = c.phase_cyc + (size_t)blockIdx.x * NPHASE; s.t = sub_clock(); return s; }
+// (__syncwarp: lane 0 must be back with its warp before the caller's next warp-synchronous instruction)
+__device__ inline void sub_tick(SubTick &s, int i) { if (threadIdx.x == 0) { const long long t1 = sub_clock(); s.p[i] += t1 - s.t; s.t = t1; } __syncwarp(); }
+__device__ inline void sub_count(SubTick &s, int i, int n) { if (threadIdx.x == 0) s.p[i] += n; __syncwarp(); }
+
 __device__ inline int blk_exscan(int v, int &total, Smem &S)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -84,14 +92,33 @@ __device__ inline double blk_sum(double v, Smem &S)
 template <class Pred>
 __device__ inline int blk_compact(int n, int *out, Pred pred, Smem &S)
 {
-    const int chunk = (n + TPB - 1) / TPB;
-    const int lo = min(n, (int)threadIdx.x * chunk), hi = min(n, lo + chunk);
-    int c = 0;
-    for (int i = lo; i < hi; ++i) c += pred(i) ? 1 : 0;
+    // warp w owns the contiguous range [w * per, (w + 1) * per): lanes read it 32 consecutive elements at a time
+    // (coalesced, independent loads), ballots give the ranks; one block scan over the warp totals orders the warps
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int per = (((n + NWARP - 1) / NWARP) + 31) & ~31;
+    const int lo = w * per, nj = per >> 5;
+    const bool keep = nj <= 64;                  // predicate bits of this lane's elements, one per 32-element group
+    unsigned long long mask = 0ull;
+    int wtot = 0;
+#pragma unroll 4
+    for (int j = 0; j < nj; ++j) {
+        const int i = lo + 32 * j + lane;
+        const bool pr = (i < n) && pred(i);
+        if (pr && keep) mask |= 1ull << j;
+        wtot += __popc(__ballot_sync(0xffffffffu, pr));
+    }
     int total;
-    int off = blk_exscan(c, total, S);
-    for (int i = lo; i < hi; ++i)
-        if (pred(i)) out[off++] = i;
+    int off = blk_exscan(lane == 0 ? wtot : 0, total, S);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (wtot) {
+        for (int j = 0; j < nj; ++j) {
+            const int i = lo + 32 * j + lane;
+            const bool pr = keep ? ((mask >> j) & 1ull) : ((i < n) && pred(i));
+            const unsigned b = __ballot_sync(0xffffffffu, pr);
+            if (pr) out[off + __popc(b & ((1u << lane) - 1u))] = i;
+            off += __popc(b);
+        }
+    }
     __syncthreads();
     return total;
 }
@@ -1095,15 +1122,18 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
     const unsigned char *__restrict__ flagsA = c.flags;
     const double *__restrict__ areaA = c.area;
     int *land = S.P.i[I_LB], *memb = S.P.i[I_MEMB];
-    int marine = 0;
+    int marine = 0, left = 0;
+    SubTick st = sub_tick_begin(c);
+    // every load of a node is issued before the first branch on it, so the unrolled iterations keep one batch of
+    // independent loads in flight (a load under a data-dependent branch costs a memory round trip per branch)
+    if (c.depo != 0) {
 #pragma unroll 4
-    for (int k = tid; k < N; k += TPB) {
-        const bool in = flagsA[k] & 1;
-        double d = in ? cdepo[k] : 0.;
-        double th = 0.;
-        int island = 0;
-        if (c.depo != 0) {
-            const double zk = z[k], fh = W[k], vol = pitVol[k];
+        for (int k = tid; k < N; k += TPB) {
+            const unsigned char fl = flagsA[k];
+            const double cdk = cdepo[k], zk = z[k], fh = W[k], vol = pitVol[k], ar = areaA[k];
+            double d = (fl & 1) ? cdk : 0.;
+            double th = 0.;
+            int island = 0;
             int in_ = 0;
             double sumdep = 0.;
             bool plain = false;
@@ -1115,13 +1145,28 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
                 }
             }
             if (zk <= sea) { sumdep = sumdep + d; if (sumdep > 0.) { marine = 1; island = 2; } }
-            if (plain) { th = d / areaA[k]; d = 0.; }
+            if (plain) { th = d / ar; d = 0.; }
+            dep[k] = d;
+            dth[k] = th;
+            kindA[k] = island;
+            left |= (d != 0. && island != 1);          // land pits hand their load on below: what else is left over?
         }
-        dep[k] = d;
-        dth[k] = th;
-        kindA[k] = island;
+    } else {
+#pragma unroll 4
+        for (int k = tid; k < N; k += TPB) {
+            const unsigned char fl = flagsA[k];
+            const double cdk = cdepo[k];
+            dep[k] = (fl & 1) ? cdk : 0.;
+            dth[k] = 0.;
+            kindA[k] = 0;
+        }
     }
-    marine = __syncthreads_or(marine);
+    {
+        const int both = __syncthreads_or(marine | (left << 1));
+        marine = both & 1;
+        left = (both >> 1) & 1;
+    }
+    int any = 0;
     if (c.depo != 0) {
         const int *isl = S.P.i[I_KIND];
         const int nland = blk_compact(N, land, [&](int i) { return isl[i] == 1; }, S);
@@ -1129,6 +1174,8 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
         // are a contiguous segment of the real-surface stack.  Small basins: one thread gathers + sorts its
         // members; large basins: the block compacts them in id order.
         constexpr int SMALL = 96;
+        sub_tick(st, 16);
+        sub_count(st, 21, nland);
         for (int q = tid; q < nland; q += TPB) {
             const int pit = land[q];
             const int lo = pos1[pit];
@@ -1157,12 +1204,14 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
             for (int i = 0; i < nm; ++i) dth[mb[i]] *= dfrac;
         }
         __syncthreads();
+        sub_tick(st, 17);
         for (int q = 0; q < nland; ++q) {
             const int pit = land[q];
             const int lo = pos1[pit];
             const int nr = ns1[pit];
             const int hi = (nr != NONE_I) ? pos1[nr] : N;
             if (hi - lo <= SMALL) continue;
+            sub_count(st, 20, 1);
             // members in ascending id: mark them (they all lie in the basin's stack segment), compact the bitmap
             unsigned *bm = (unsigned *)S.P.i[I_MARK];
             for (int w = tid; w < (N + 31) / 32; w += TPB) bm[w] = 0u;
@@ -1187,29 +1236,46 @@ __device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
             for (int i = tid; i < nm; i += TPB) dth[memb[i]] *= dfrac;
             __syncthreads();
         }
+        sub_tick(st, 18);
         for (int q = tid; q < nland; q += TPB) dep[land[q]] = 0.;
         __syncthreads();
-        if (marine) phase_marine_distribution(c, S, sea);     // flowNetwork.py:769-776
-        // forced deposition of anything left (flowNetwork.py:782-785)
-        int any = 0;
+        // forced deposition of anything left (flowNetwork.py:782-785).  Without marine deposition the only writes to
+        // dep since the first pass are the zeroed land pits, so "anything left" is already known.
+        any = left;
+        if (marine) {
+            phase_marine_distribution(c, S, sea);     // flowNetwork.py:769-776
+            any = 0;
 #pragma unroll 4
-        for (int k = tid; k < N; k += TPB) any |= (dep[k] != 0.);
-        any = __syncthreads_or(any);
-        if (any)
-            for (int k = tid; k < N; k += TPB)
-                if (flagsA[k] & 1) dth[k] += dep[k] / areaA[k];
-        __syncthreads();
-    }
-#pragma unroll 4
-    for (int k = tid; k < N; k += TPB) {
-        double sf = 0.;
-        if (flagsA[k] & 1) {
-            const double erosion = cero[k] / areaA[k];
-            sf = erosion + dth[k];
+            for (int k = tid; k < N; k += TPB) any |= (dep[k] != 0.);
+            any = __syncthreads_or(any);
         }
-        sedflux[k] = sf;
+    }
+    if (any) {
+#pragma unroll 4
+        for (int k = tid; k < N; k += TPB) {
+            const unsigned char fl = flagsA[k];
+            const double ce = cero[k], ar = areaA[k], dp = dep[k];
+            double th = dth[k];
+            double sf = 0.;
+            if (fl & 1) {
+                th += dp / ar;
+                dth[k] = th;
+                const double erosion = ce / ar;
+                sf = erosion + th;
+            }
+            sedflux[k] = sf;
+        }
+    } else {
+#pragma unroll 4
+        for (int k = tid; k < N; k += TPB) {
+            const unsigned char fl = flagsA[k];
+            const double ce = cero[k], ar = areaA[k], th = dth[k];
+            const double erosion = ce / ar;
+            sedflux[k] = (fl & 1) ? erosion + th : 0.;
+        }
     }
     __syncthreads();
+    sub_tick(st, 19);
 }
 
 // phase: apply ed, hillslope diffusion, boundary, tectonics.  buildFlux.py:193-195, :252-272, :292-315;

@@ -26,7 +26,7 @@ namespace {
 constexpr int NONE_I = -1;
 constexpr unsigned END_U = 0xFFFFFFFFu;
 constexpr int TERM_BIT = 0x40000000;
-constexpr int NPHASE = 16;
+constexpr int NPHASE = 32;
 constexpr int LEVMAX = 63;
 constexpr int DYN_SMEM = 229376; // dynamic shared memory of the fast kernel (224 KB)
 
@@ -116,6 +116,13 @@ constexpr int NWARP = TPB / 32;
 #include "bl_device.cuh"
 #undef BL_MINB
 } // namespace v1024
+namespace v512 {                 // one CTA per SM with twice the registers per thread (128): no spills in the streaming loops
+constexpr int TPB = 512;
+constexpr int NWARP = TPB / 32;
+#define BL_MINB 1
+#include "bl_device.cuh"
+#undef BL_MINB
+} // namespace v512
 namespace v256 {
 constexpr int TPB = 256;
 constexpr int NWARP = TPB / 32;
@@ -386,7 +393,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     c.status = (unsigned *)(ws + L.off_status);
     c.phase_cyc = (long long *)(ws + L.off_phase);
     ctx->tpb = (KDT > 0 && N <= 4096) ? 256 : 1024;
-    if (getenv("BL_TPB")) ctx->tpb = (atoi(getenv("BL_TPB")) == 256) ? 256 : 1024;
+    if (getenv("BL_TPB")) { const int t = atoi(getenv("BL_TPB")); ctx->tpb = (t == 256 || t == 512) ? t : 1024; }
     ctx->device = device; ctx->B = B; ctx->ws = ws; ctx->ws_bytes = L.total;
     ctx->d_stops = (double *)(ws + L.off_stops);
     ctx->d_ckpt = (int *)(ws + L.off_ckpt);
@@ -466,6 +473,13 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
             case 12: LAUNCH(v256, 256, 12, dyn); break;
             case 20: LAUNCH(v256, 256, 20, dyn); break;
             default: LAUNCH(v256, 256, 0, 0); break;
+        }
+    } else if (ctx->tpb == 512) {
+        switch (ctx->c.KDT) {
+            case 8: LAUNCH(v512, 512, 8, dyn); break;
+            case 12: LAUNCH(v512, 512, 12, dyn); break;
+            case 20: LAUNCH(v512, 512, 20, dyn); break;
+            default: LAUNCH(v512, 512, 0, 0); break;
         }
     } else {
         switch (ctx->c.KDT) {

@@ -340,10 +340,14 @@ __device__ void links_stack(const DevConst &c, Smem &S, unsigned char *dsm, cons
     __syncthreads();
     unsigned short *lc16 = (unsigned short *)S.P.i[I_LC], *ps16 = (unsigned short *)S.P.i[I_PS];
     unsigned char *cnt8 = (unsigned char *)S.P.i[I_CNT];
+#pragma unroll 2
     for (int v = tid; v < N; v += TPB) {
-        Ids<KDT> ids;
-        load_ids<KDT>(c, v, ids);
+        // both id rows are fetched up front (the receiver's row depends on shared memory only): two independent
+        // global loads per node in flight instead of one behind the other
+        Ids<KDT> ids, jds;
         const int r = r16[v];
+        load_ids<KDT>(c, v, ids);
+        load_ids<KDT>(c, r, jds);
         int f = NONE16, l = -1, n = 0;
 #pragma unroll
         for (int p = 0; p < KDT; ++p) {
@@ -353,8 +357,6 @@ __device__ void links_stack(const DevConst &c, Smem &S, unsigned char *dsm, cons
         }
         int nx = NONE16, pv = -1;
         if (r != v) {
-            Ids<KDT> jds;
-            load_ids<KDT>(c, r, jds);
 #pragma unroll
             for (int p = 0; p < KDT; ++p) {
                 if (jds.get(p) == NONE16) continue;
@@ -990,6 +992,7 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
         double acc = 0.;
         const unsigned char fg = fls[g];
         const double zg = zs[g];
+        const double c0 = cumdiff[g], h0 = cumhill[g];
         if (fg & 2) {
             Ids<KDT> ids;
             load_ids<KDT>(c, g, ids);
@@ -1027,17 +1030,15 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
         const double ac = (area > 0.) ? 1. / area : 0.;
         double coeff = ac * ((zg >= sea) ? c.CDa : c.CDm);
         if (!(fg & 2)) { coeff = 0.; acc = 0.; }
-        cd[g] = coeff * acc * timestep;
+        const double d = coeff * acc * timestep;
+        cd[g] = d;
+        // the cumulative arrays take the diffusion term here (same thread that added sedflux to cumdiff[g] above)
+        if (fg & 1) { cumdiff[g] = c0 + d; cumhill[g] = h0 + d; }
     }
     __syncthreads();
 #pragma unroll 4
-    for (int k = tid; k < N; k += TPB) {
-        double zn = zs[k];
-        const double d = (fls[k] & 1) ? cd[k] : 0.;
-        const double c0 = cumdiff[k], h0 = cumhill[k];
-        if (fls[k] & 1) { zn += d; cumdiff[k] = c0 + d; cumhill[k] = h0 + d; }
-        zs[k] = zn;
-    }
+    for (int k = tid; k < N; k += TPB)
+        if (fls[k] & 1) zs[k] += cd[k];
     __syncthreads();
     if (c.btype != 0) {
         const double add = (c.btype == 1) ? -0.1 : (c.btype == 2 ? 0. : 100.);

@@ -143,7 +143,7 @@ int bl_get_scalars(bl_ctx *ctx, double *tnow, int64_t *steps, uint32_t *status, 
  * Phase order: fill, sfd, stack1, basins, stack, drainage, discharge, cfl, streampower, newdt(+rerun),
  * erodep, apply; slots 12-15 split streampower on the shared-memory path (event compaction, parallel replay,
  * serial replay, pre-pass + routing). */
-#define BL_NPHASE 16
+#define BL_NPHASE 32
 int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst_host, void *stream);
 /* number of kernel launches issued by this context so far (for bench.py's gpu_launches) */
 int64_t bl_launch_count(const bl_ctx *ctx);

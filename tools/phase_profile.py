@@ -31,3 +31,8 @@ for i, nm in enumerate(_lib.PHASES):
 print("  diag streampower split (cyc/step): prepass+scan %.0f, event compaction %.0f, parallel replay %.0f, serial replay %.0f" % tuple((pc[:,i]/steps).mean() for i in (15,12,13,14)))
 tot = pc[:, :12].sum(1)
 print("  total        %10.0f cyc/step  (%.1f us at 1.965 GHz)" % ((tot / steps).mean(), (tot / steps).mean() / 1965.0))
+
+names = {16: "erodep pass1+compact", 17: "erodep small basins", 18: "erodep large basins", 19: "erodep tail", 20: "#large basins",
+         21: "#land pits"}
+for i in sorted(names):
+    print("  sub %-32s %10.1f /step" % (names[i], (pc[:, i] / steps).mean()))
