@@ -803,11 +803,15 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
             }
         }
     }
+    // the routing is done with sm.kind: it now flags the pits that receive at least one event (most do not)
+    unsigned char *has_ev = sm.kind;
+    for (int v = tid; v < Nq / 4; v += TPB) reinterpret_cast<unsigned *>(has_ev)[v] = 0u;
     __syncthreads();
     for (int e = tid; e < nev; e += TPB) {       // one event per thread: the dependent global lookups run in parallel
         const int donor = stack[N - 1 - ev_donor[e]];
         const int pit = pitID[donor];
         const bool ok = (pit >= 0 && c.area[pit] > 0.);
+        if (ok) has_ev[pit] = 1;
         ev_pit[e] = ok ? (unsigned short)pit : NONE16;
         ev_donor[e] = (unsigned short)donor;
         ev_dep[e] = pdep[donor];
@@ -822,6 +826,7 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
         for (int e = tid; e < nev; e += TPB) { const int pit = ev_pit[e]; if (pit != NONE16 && W[pit] < sea) over = 1; }
     for (int i = tid; i < nbase1; i += TPB) {
         const int pit = base1[i];
+        if (!has_ev[pit]) continue;              // no event: depo[pit] stays as it is
         double dp = depo[pit];
         bool any = false;
         double vol = 0.;
@@ -838,7 +843,7 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
     over = __syncthreads_or(over);
     STICK(13);  // parallel replay
     if (!over) {
-        for (int i = tid; i < nbase1; i += TPB) { const int pit = base1[i]; depo[pit] = S.P.f[F_VAL][pit]; }
+        for (int i = tid; i < nbase1; i += TPB) { const int pit = base1[i]; if (has_ev[pit]) depo[pit] = S.P.f[F_VAL][pit]; }
         __syncthreads();
         return;
     }
