@@ -1,6 +1,7 @@
 // bl_device.cuh - device code of the engine.  Included by bl_engine.cu once per CTA size (inside a namespace
 // that defines TPB / NWARP / BL_MINB): 1024 threads for landscapes that fill an SM's shared memory, 256 threads
-// (several CTAs per SM) for small meshes such as the etopo configs.  No include guard on purpose.
+// (several CTAs per SM) for small meshes such as the etopo configs, 512 threads (128 registers, no spills; BL_TPB=512)
+// as a measured alternative.  No include guard on purpose.
 // ------------------------------------------------------------------------------------------------
 // block primitives
 // ------------------------------------------------------------------------------------------------

@@ -142,7 +142,8 @@ int bl_get_scalars(bl_ctx *ctx, double *tnow, int64_t *steps, uint32_t *status, 
 /* diagnostics: SM clock cycles spent per phase of the time step, [B][BL_NPHASE] int64 to HOST.
  * Phase order: fill, sfd, stack1, basins, stack, drainage, discharge, cfl, streampower, newdt(+rerun),
  * erodep, apply; slots 12-15 split streampower on the shared-memory path (event compaction, parallel replay,
- * serial replay, pre-pass + routing). */
+ * serial replay, pre-pass + routing); slots 16-19 split erodep (first pass + land-pit compaction, small basins,
+ * large basins, tail), 20 / 21 count large basins / land pits; the rest are reserved. */
 #define BL_NPHASE 32
 int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst_host, void *stream);
 /* number of kernel launches issued by this context so far (for bench.py's gpu_launches) */
