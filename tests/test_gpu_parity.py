@@ -158,6 +158,29 @@ def test_crater_generic_path_bit_exact(crater_fast, monkeypatch):
                 assert np.array_equal(eng.field(f, b), getattr(om, f)), (step, b, f)
 
 
+@pytest.mark.parametrize("tpb", [256, 512, 1024])
+def test_crater_every_cta_size_bit_exact(crater_fast, tpb, monkeypatch):
+    """The device code is instantiated once per CTA size (bl_engine.cu: v256 / v512 / v1024); BL_TPB forces one.
+    Block-level primitives (scans, ordered compaction, warp ballots) must give the same bits at every size."""
+    from oracle import oracle
+    monkeypatch.setenv("BL_TPB", str(tpb))
+    d, inp, m = crater_fast
+    eng = _engine(crater_fast, 2)
+    rain = np.array([0.9, 2.2]); erod = np.array([6e-5, 4e-5]); seeds = np.array([8, 9], dtype=np.int64)
+    eng.reset(rain, erod, seeds)
+    oms = [oracle.OracleModel(m, inp, seed=int(s)) for s in seeds]
+    for b, om in enumerate(oms):
+        om.reset(rain[b], erod[b], seed=int(seeds[b]))
+    for step in range(5):
+        eng.step(15000.0)
+        sc = eng.scalars()
+        for b, om in enumerate(oms):
+            om.streamflow(); om.sediment_flux(15000.0)
+            for f in INT_FIELDS + FP_FIELDS:
+                assert np.array_equal(eng.field(f, b), getattr(om, f)), (tpb, step, b, f)
+            assert sc["tNow"][b] == om.tNow and sc["status"][b] == 0
+
+
 @pytest.mark.parametrize("generic", [0, 1])
 def test_synthetic_uplift_regular_grid_bit_exact(generic, monkeypatch):
     """BASELINE config 5 in miniature: regular grid (D8 stencil as the neighbour list), noisy flat start, uplift
