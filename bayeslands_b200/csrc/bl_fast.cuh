@@ -327,7 +327,7 @@ __device__ void fill_sfd(const DevConst &c, Smem &S, unsigned char *dsm, double 
 // updated in place: a word is read and written as one 32-bit access, so any interleaving keeps the
 // invariant "rank = number of enter events from this element up to (excluding) next".
 template <int KDT>
-__device__ void links_stack(const DevConst &c, Smem &S, unsigned char *dsm, const int *rcvg, int *stack, int *pos,
+__device__ __noinline__ void links_stack(const DevConst &c, Smem &S, unsigned char *dsm, const int *rcvg, int *stack, int *pos,
                             int *baselist, int &nbase, bool filled, bool shuffle, unsigned long long seedstep)
 {
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
@@ -574,7 +574,7 @@ constexpr int DEPMAX = 2040;   // bucket offsets kept in static shared memory up
 // + counting sort); buckets are processed from the deepest to the roots with a barrier in between, so when a
 // node is evaluated all its donors (depth + 1) are final and it sums them in the fixed descending-id order.
 // The same buckets serve the sediment routing of streampower().
-__device__ void discharge(const DevConst &c, Smem &S, unsigned char *dsm, double rain)
+__device__ __noinline__ void discharge(const DevConst &c, Smem &S, unsigned char *dsm, double rain)
 {
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     ScanSm sm = scan_layout(dsm, Nq);
