@@ -28,7 +28,9 @@ FIELDS = dict(z=F_Z, cumdiff=F_CUMDIFF, cumhill=F_CUMHILL, fillH=F_FILLH, maxh=F
               ero=F_ERO, depo=F_DEPO, sedflux=F_SEDFLUX, rcv=F_RCV, rcv1=F_RCV1, stack=F_STACK, stack1=F_STACK1,
               pitID=F_PITID, pitDrain=F_PITDRAIN, allDrain=F_ALLDRAIN)
 
-ST_CASCADE_GUARD, ST_MARINE, ST_DRAIN_CYCLE, ST_NAN = 1, 2, 4, 8
+ST_CASCADE_GUARD, ST_DRAIN_CYCLE, ST_NAN = 1, 4, 8
+ST_FATAL = ST_CASCADE_GUARD | ST_NAN      # evaluations whose result must not enter Metropolis
+OPT_FORCE_GENERIC, OPT_NO_L2_PERSIST, OPT_LEAN = 1, 2, 4
 
 
 class BlMesh(C.Structure):
@@ -44,7 +46,9 @@ class BlParams(C.Structure):
                 ("maxDT", C.c_double), ("hill_cfl", C.c_double), ("ms_cfl", C.c_double),
                 ("diffprop", C.c_double), ("diffnb", C.c_int32), ("depo", C.c_int32), ("btype", C.c_int32),
                 ("shuffle_mode", C.c_int32), ("seapos", C.c_double), ("nsea", C.c_int32), ("seat", c_dp),
-                ("seav", c_dp), ("real_elev", c_dp), ("npts", C.c_int32), ("pts_cell", c_ip)]
+                ("seav", c_dp), ("real_elev", c_dp), ("npts", C.c_int32), ("pts_cell", c_ip),
+                ("opt_tpb", C.c_int32), ("opt_flags", C.c_int32), ("opt_grid_group", C.c_int32),
+                ("opt_debug", C.c_int32)]
 
 
 class BlLattice(C.Structure):

@@ -1465,12 +1465,22 @@ bl_run_kernel(const DevConst cpar, int nstops, const double *__restrict__ stops,
                 }
                 if (out_sse && c.real_elev) {
                     sse = blk_sum(sse, S);
-                    if (tid == 0) out_sse[b] = sse;
+                    if (tid == 0) {
+                        out_sse[b] = sse;
+                        if (!isfinite(sse)) atomicOr(&c.status[b], BL_ST_NAN);
+                    }
                 }
             }
             ++ck_seen;
             __syncthreads();
         }
+    }
+    {   // NaN / Inf guard: a non-finite elevation or clock marks the evaluation as failed
+        const double *z = S.P.f[F_Z];
+        int bad = !isfinite(tNow);
+        for (int k = tid; k < c.N; k += TPB) bad |= !isfinite(z[k]);
+        bad = __syncthreads_or(bad);
+        if (tid == 0 && bad) atomicOr(&c.status[b], BL_ST_NAN);
     }
     if (tid == 0) { c.tnow[b] = tNow; c.steps[b] = step; c.lastdt[b] = last_dt; }
 }

@@ -9,129 +9,7 @@
 // are bit-identical to the CPU oracle compiled with -ffp-contract=off.
 //
 // Reference routines restated per phase are cited at each device function (paths under /root/reference).
-#include "bayeslands_b200.h"
-
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include <algorithm>
-#include <string>
-#include <vector>
-
-namespace {
-
-constexpr int NONE_I = -1;
-constexpr unsigned END_U = 0xFFFFFFFFu;
-constexpr int TERM_BIT = 0x40000000;
-constexpr int NPHASE = 32;
-constexpr int LEVMAX = 63;
-constexpr int DYN_SMEM = 229376; // dynamic shared memory of the fast kernel (224 KB)
-
-thread_local std::string g_err;
-
-// ------------------------------------------------------------------------------------------------
-// device-visible constants
-// ------------------------------------------------------------------------------------------------
-struct DevConst {
-    int N, bounds, KD, nlev, G, npts, nsea, B;
-    const int *ngb;             // [KD][N]
-    const unsigned short *ngb16; // [N][KDT] node-major u16 copy for the shared-memory path (0xFFFF = none)
-    int Nq, KDT;                // N rounded up to 64; rows of ngb16
-    const float *ve32;          // [N][KDT][2] (vor, edge) as float pairs when both are float32-representable, else null
-    int lev_contig;             // lev_nodes[i] == bounds + i (colour-major numbering)
-    int dbg;                    // BL_DEBUG experiments (timing only)
-    const double *vor, *edge;   // [KD][N]
-    const double *area, *xy;    // [N], [N][2]
-    const unsigned char *flags; // bit0 borders, bit1 borders2, bit2 indomain
-    const int *parent;          // [bounds]
-    const double *z0, *disp;
-    const int *lev_nodes, *lev_off;
-    const int *grid_idx;
-    const double *grid_w;
-    const int *grid_exact;
-    const double *real_elev;
-    const int *pts_cell;
-    const double *seat, *seav;
-    double m, n, eps, TH, CDa, CDm, CDr, minDT, maxDT, hill, ms, diffprop, seapos;
-    int diffnb, depo, btype, shuffle;
-    char *prop_base;
-    size_t prop_stride;
-    double *rain, *erod;
-    unsigned long long *seed;
-    double *tnow, *lastdt;
-    long long *steps;
-    unsigned *status;
-    long long *phase_cyc; // [B][BL_NPHASE] clock64 cycles per phase (thread 0), diagnostics
-};
-
-enum { F_Z, F_CUMDIFF, F_CUMHILL, F_FILLH, F_MAXH, F_Q, F_SEDIN, F_QS, F_DEPO, F_ERO, F_PITVOL, F_PITVOLW,
-       F_VAL, F_DTHICK, F_E, F_CAPH, F_PDEP, F_SEDFLUX, NF64 };
-enum { I_RCV, I_RCV1, I_STACK, I_STACK1, I_POS, I_POS1, I_PITID, I_PITDRAIN, I_ALLDRAIN, I_FC, I_NS, I_LC,
-       I_PS, I_CNT, I_ROOT1, I_LA, I_LB, I_SUCC, I_SUCC2, I_KIND, I_EVENTS, I_MEMB, I_MARK, NI32 };
-
-__host__ __device__ inline size_t rup(size_t x, size_t a) { return (x + a - 1) / a * a; }
-__host__ __device__ inline int np_of(int N) { return (int)rup((size_t)N + 1, 32); }
-__host__ __device__ inline size_t keys_len(int N)
-{
-    size_t p = 1;
-    while (p < (size_t)N) p <<= 1;
-    return p;
-}
-__host__ __device__ inline size_t prop_bytes(int N)
-{
-    size_t Np = np_of(N);
-    return rup((size_t)NF64 * Np * 8 + (size_t)NI32 * Np * 4 + (size_t)(4 * Np + keys_len(N)) * 8, 256);
-}
-
-struct Prop {
-    double *f[NF64];
-    int *i[NI32];
-    unsigned long long *euA, *euB, *keys;
-};
-
-__device__ inline void prop_init(Prop &P, char *base, int N)
-{
-    size_t Np = np_of(N);
-    double *d = (double *)base;
-    for (int k = 0; k < NF64; ++k) P.f[k] = d + (size_t)k * Np;
-    unsigned long long *u = (unsigned long long *)(d + (size_t)NF64 * Np);
-    P.euA = u;
-    P.euB = u + 2 * Np;
-    P.keys = u + 4 * Np;
-    int *ip = (int *)(P.keys + keys_len(N));
-    for (int k = 0; k < NI32; ++k) P.i[k] = ip + (size_t)k * Np;
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// device code, one instantiation per CTA size
-// ------------------------------------------------------------------------------------------------
-namespace v1024 {
-constexpr int TPB = 1024;
-constexpr int NWARP = TPB / 32;
-#define BL_MINB 1
-#include "bl_device.cuh"
-#undef BL_MINB
-} // namespace v1024
-namespace v512 {                 // one CTA per SM with twice the registers per thread (128): no spills in the streaming loops
-constexpr int TPB = 512;
-constexpr int NWARP = TPB / 32;
-#define BL_MINB 1
-#include "bl_device.cuh"
-#undef BL_MINB
-} // namespace v512
-namespace v256 {
-constexpr int TPB = 256;
-constexpr int NWARP = TPB / 32;
-#define BL_MINB 4
-#include "bl_device.cuh"
-#undef BL_MINB
-} // namespace v256
-
-} // namespace
+#include "bl_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -148,16 +26,21 @@ struct bl_ctx {
     int stops_cap;
     long long launches;
     size_t const_bytes;   // mesh constants at the start of the workspace (kept L2-persistent)
+    int l2_persist;       // bl_params.opt_flags & BL_OPT_NO_L2_PERSIST == 0
+    int dyn_max;          // dynamic shared memory one CTA of the chosen kernel may use (opt-in limit - static)
+    int dyn;              // dynamic shared memory of a launch
+    // stop times / checkpoint ids travel through context-owned pinned slots (no stream synchronisation per launch)
+    static constexpr int NSLOT = 4;
+    char *h_stage;        // [NSLOT][STOPS_CAP * 12] pinned
+    cudaEvent_t slot_ev[NSLOT];
+    int slot;
 };
 
-#define CUDA_OK(x)                                                                      \
-    do {                                                                                \
-        cudaError_t e_ = (x);                                                           \
-        if (e_ != cudaSuccess) {                                                        \
-            g_err = std::string(#x) + ": " + cudaGetErrorString(e_);                    \
-            return BL_ERR_CUDA;                                                         \
-        }                                                                               \
-    } while (0)
+std::string &bl_err_ref()
+{
+    thread_local std::string e;
+    return e;
+}
 
 extern "C" const char *bl_last_error(void) { return g_err.c_str(); }
 extern "C" int bl_version(void) { return 100; }
@@ -182,6 +65,25 @@ int max_degree(const bl_mesh *m)
 }
 
 constexpr int STOPS_CAP = 4096;
+
+// dynamic shared memory the shared-memory device path (bl_fast.cuh) needs for a mesh of Nq (padded) nodes:
+// 17 bytes per node for the scans (value fp64 + links + order + kind) + the event bitmap; the fill keeps W, z, the pending
+// bitmap and the id list of a round; the marine phases of the etopo configs stage 33 bytes per node (marine_diffusion) or
+// the neighbour table as well (marine_distribution) - those fall back to global memory when the CTA cannot have it.
+size_t fast_smem_need(int Nq, int KDT, bool marine)
+{
+    size_t need = (size_t)17 * Nq + Nq / 8 + 256;
+    need = std::max(need, (size_t)16 * Nq + Nq / 8 + 64 + 8192);
+    if (marine) need = std::max(need, std::max((size_t)Nq * (17 + 2 * KDT) + 256, (size_t)33 * Nq + 64));
+    return need;
+}
+
+cudaError_t func_attr(int tpb, int KDT, cudaFuncAttributes *fa)
+{
+    if (tpb == 256) return bl_func_attr_v256(KDT, fa);
+    if (tpb == 512) return bl_func_attr_v512(KDT, fa);
+    return bl_func_attr_v1024(KDT, fa);
+}
 
 Layout make_layout(const bl_mesh *m, const bl_params *p, int B, int KD, int nlev)
 {
@@ -294,9 +196,24 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
             edgeT[(size_t)q * N + i] = m->edge[(size_t)i * BL_KP + q];
         }
     const int Nq = (int)rup((size_t)N, 64);
+    // CTA size and device path.  The shared-memory path needs fast_smem_need() bytes of dynamic shared memory; what a CTA
+    // may use is the device's opt-in limit minus the kernel's static shared memory (queried, not assumed).
+    const int kdt_want = (KD <= 8) ? 8 : (KD <= 12 ? 12 : 20);
+    int tpb = (N <= 4096) ? 256 : 1024;
+    if (p->opt_tpb == 256 || p->opt_tpb == 512 || p->opt_tpb == 1024) tpb = p->opt_tpb;
+    else if (p->opt_tpb != 0) { g_err = "bl_ctx_create: opt_tpb must be 0, 256, 512 or 1024"; return BL_ERR_ARG; }
+    int dyn_max = 0;
+    {
+        int optin = 0;
+        CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        cudaFuncAttributes fa;
+        memset(&fa, 0, sizeof(fa));
+        CUDA_OK(func_attr(tpb, kdt_want, &fa));
+        dyn_max = (optin - (int)fa.sharedSizeBytes) / 1024 * 1024;
+    }
     int KDT = 0;
-    if (N < 32760 && nlev <= LEVMAX && (size_t)17 * Nq + Nq / 8 + 256 <= (size_t)DYN_SMEM) KDT = (KD <= 8) ? 8 : (KD <= 12 ? 12 : 20);
-    if (getenv("BL_FORCE_GENERIC")) KDT = 0;
+    if (N < 32760 && nlev <= LEVMAX && fast_smem_need(Nq, kdt_want, false) <= (size_t)dyn_max) KDT = kdt_want;
+    if (p->opt_flags & BL_OPT_FORCE_GENERIC) KDT = 0;
     const int KDrow = KDT ? KDT : BL_KP;
     std::vector<unsigned short> ngb16((size_t)BL_KP * Nq, 0xFFFFu);
     for (int i = 0; i < N; ++i)
@@ -359,7 +276,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     c.Nq = Nq; c.KDT = KDT;
     c.ve32 = ve_ok ? (const float *)(ws + L.off_ve32) : nullptr;
     c.lev_contig = 1;
-    c.dbg = getenv("BL_DEBUG") ? atoi(getenv("BL_DEBUG")) : 0;
+    c.dbg = p->opt_debug;
     for (size_t i = 0; i < levn.size() && (int)i < N - m->bounds; ++i)
         if (levn[i] != m->bounds + (int)i) { c.lev_contig = 0; break; }
     c.vor = (const double *)(ws + L.off_vor);
@@ -392,8 +309,20 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     c.steps = (long long *)(ws + L.off_steps);
     c.status = (unsigned *)(ws + L.off_status);
     c.phase_cyc = (long long *)(ws + L.off_phase);
-    ctx->tpb = (KDT > 0 && N <= 4096) ? 256 : 1024;
-    if (getenv("BL_TPB")) { const int t = atoi(getenv("BL_TPB")); ctx->tpb = (t == 256 || t == 512) ? t : 1024; }
+    ctx->tpb = (KDT == 0 && p->opt_tpb == 0) ? 1024 : tpb;
+    ctx->l2_persist = (p->opt_flags & BL_OPT_NO_L2_PERSIST) ? 0 : 1;
+    ctx->dyn_max = dyn_max;
+    {   // dynamic shared memory of a launch: what the phases of this configuration need; the marine phases (etopo configs)
+        // stage more when it fits and fall back to their global-memory form otherwise (bl_device.cuh: dsm_bytes tests)
+        const bool marine = (p->CDr > 0. || p->nsea > 0);
+        size_t need = fast_smem_need(Nq, KDT, false);
+        if (marine) need = std::max(need, std::min(fast_smem_need(Nq, KDT, true), (size_t)dyn_max));
+        ctx->dyn = KDT ? (int)std::min((size_t)dyn_max, rup(need, 1024)) : 0;
+        if (KDT && (p->opt_debug & 1)) ctx->dyn = dyn_max;     // experiment: one CTA per SM whatever the mesh size
+    }
+    CUDA_OK(cudaMallocHost((void **)&ctx->h_stage, (size_t)bl_ctx::NSLOT * STOPS_CAP * 12));
+    for (int i = 0; i < bl_ctx::NSLOT; ++i) CUDA_OK(cudaEventCreateWithFlags(&ctx->slot_ev[i], cudaEventDisableTiming));
+    ctx->slot = 0;
     ctx->device = device; ctx->B = B; ctx->ws = ws; ctx->ws_bytes = L.total;
     ctx->d_stops = (double *)(ws + L.off_stops);
     ctx->d_ckpt = (int *)(ws + L.off_ckpt);
@@ -414,6 +343,10 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
 
 extern "C" int bl_ctx_destroy(bl_ctx *ctx)
 {
+    if (ctx) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        for (int i = 0; i < bl_ctx::NSLOT; ++i) if (ctx->slot_ev[i]) cudaEventDestroy(ctx->slot_ev[i]);
+    }
     delete ctx;
     return BL_OK;
 }
@@ -423,10 +356,9 @@ extern "C" int bl_reset(bl_ctx *ctx, const double *rain_dev, const double *erod_
 {
     if (!ctx || !rain_dev || !erod_dev) { g_err = "bl_reset: null argument"; return BL_ERR_ARG; }
     CUDA_OK(cudaSetDevice(ctx->device));
-    v256::bl_reset_kernel<<<ctx->B, 256, 0, (cudaStream_t)stream>>>(ctx->c, rain_dev, erod_dev,
-                                                              (const unsigned long long *)seed_dev, tStart);
+    CUDA_OK(bl_launch_reset_v256(ctx->c, ctx->B, (cudaStream_t)stream, rain_dev, erod_dev,
+                                 (const unsigned long long *)seed_dev, tStart));
     ctx->launches++;
-    CUDA_OK(cudaGetLastError());
     return BL_OK;
 }
 
@@ -435,17 +367,33 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
 {
     if (!ctx || nstops <= 0 || !stops) { g_err = "bl_run: bad arguments"; return BL_ERR_ARG; }
     if (nstops > ctx->stops_cap) { g_err = "bl_run: too many stops"; return BL_ERR_ARG; }
+    if (nck < 0 || nck > BL_NCKPT_MAX) { g_err = "bl_run: nck out of range"; return BL_ERR_ARG; }
     CUDA_OK(cudaSetDevice(ctx->device));
-    std::vector<int> ck(nstops, -1);
-    if (ckpt)
-        for (int i = 0; i < nstops; ++i) {
-            ck[i] = ckpt[i];
-            if (ck[i] >= BL_NCKPT_MAX) { g_err = "bl_run: checkpoint index too large"; return BL_ERR_ARG; }
+    // stage stops / checkpoint ids in the next pinned slot (waits only if that slot's previous copy is still in flight)
+    const int slot = ctx->slot;
+    ctx->slot = (slot + 1) % bl_ctx::NSLOT;
+    CUDA_OK(cudaEventSynchronize(ctx->slot_ev[slot]));
+    double *h_stops = (double *)(ctx->h_stage + (size_t)slot * STOPS_CAP * 12);
+    int *h_ck = (int *)(h_stops + STOPS_CAP);
+    int marked = 0;
+    for (int i = 0; i < nstops; ++i) {
+        h_stops[i] = stops[i];
+        const int k = ckpt ? ckpt[i] : -1;
+        if (k >= BL_NCKPT_MAX) { g_err = "bl_run: checkpoint index too large"; return BL_ERR_ARG; }
+        if (k >= 0) {
+            // grids are written at [(b * nck + <number of checkpoints seen>) * G]: more marked stops than nck, or an id
+            // beyond nck, would write out of bounds (mirrors bl_grid_run)
+            if ((out_elev || out_erdp) && (k >= nck || marked >= nck)) {
+                g_err = "bl_run: more checkpoints than nck grids"; return BL_ERR_ARG;
+            }
+            ++marked;
         }
-    CUDA_OK(cudaMemcpyAsync(ctx->d_stops, stops, (size_t)nstops * 8, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(ctx->d_ckpt, ck.data(), (size_t)nstops * 4, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaStreamSynchronize(st)); // ck is a stack vector
-    if (!getenv("BL_NO_L2_PERSIST")) {
+        h_ck[i] = k;
+    }
+    CUDA_OK(cudaMemcpyAsync(ctx->d_stops, h_stops, (size_t)nstops * 8, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(ctx->d_ckpt, h_ck, (size_t)nstops * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaEventRecord(ctx->slot_ev[slot], st));
+    if (ctx->l2_persist) {
         cudaStreamAttrValue av;
         memset(&av, 0, sizeof(av));
         av.accessPolicyWindow.base_ptr = ctx->ws;
@@ -456,42 +404,14 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
         cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
         cudaGetLastError();
     }
-    // the fast path needs 17 bytes of shared memory per node: small meshes leave room for several CTAs per SM
-    size_t need = (size_t)17 * ctx->c.Nq + ctx->c.Nq / 8 + 256;
-    need = std::max(need, (size_t)16 * ctx->c.Nq + ctx->c.Nq / 8 + 64 + 8192);   // fill: W, z, pending bitmap, id list of a round
-    if (ctx->c.CDr > 0. || ctx->c.nsea > 0) need = std::max(need, (size_t)ctx->c.Nq * (17 + 2 * ctx->c.KDT) + 256);
-    const int dyn = (int)std::min((size_t)DYN_SMEM, rup(need, 1024));
-#define LAUNCH(NS, T, K, DYN)                                                                                   \
-    do {                                                                                                        \
-        if (DYN) CUDA_OK(cudaFuncSetAttribute(NS::bl_run_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN)); \
-        NS::bl_run_kernel<K><<<ctx->B, T, DYN, st>>>(ctx->c, nstops, ctx->d_stops, ctx->d_ckpt, out_pts, out_sse, \
-                                                     out_elev, out_erdp, nck, single, DYN);                     \
-    } while (0)
-    if (ctx->tpb == 256) {
-        switch (ctx->c.KDT) {
-            case 8: LAUNCH(v256, 256, 8, dyn); break;
-            case 12: LAUNCH(v256, 256, 12, dyn); break;
-            case 20: LAUNCH(v256, 256, 20, dyn); break;
-            default: LAUNCH(v256, 256, 0, 0); break;
-        }
-    } else if (ctx->tpb == 512) {
-        switch (ctx->c.KDT) {
-            case 8: LAUNCH(v512, 512, 8, dyn); break;
-            case 12: LAUNCH(v512, 512, 12, dyn); break;
-            case 20: LAUNCH(v512, 512, 20, dyn); break;
-            default: LAUNCH(v512, 512, 0, 0); break;
-        }
-    } else {
-        switch (ctx->c.KDT) {
-            case 8: LAUNCH(v1024, 1024, 8, dyn); break;
-            case 12: LAUNCH(v1024, 1024, 12, dyn); break;
-            case 20: LAUNCH(v1024, 1024, 20, dyn); break;
-            default: LAUNCH(v1024, 1024, 0, 0); break;
-        }
-    }
-#undef LAUNCH
+    RunArgs a;
+    a.nstops = nstops; a.stops = ctx->d_stops; a.ckpt = ctx->d_ckpt;
+    a.out_pts = out_pts; a.out_sse = out_sse; a.out_elev = out_elev; a.out_erdp = out_erdp;
+    a.nck = nck; a.single_step = single;
+    if (ctx->tpb == 256) CUDA_OK(bl_launch_run_v256(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
+    else if (ctx->tpb == 512) CUDA_OK(bl_launch_run_v512(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
+    else CUDA_OK(bl_launch_run_v1024(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
     ctx->launches++;
-    CUDA_OK(cudaGetLastError());
     return BL_OK;
 }
 
@@ -573,4 +493,3 @@ extern "C" int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst, void *stream)
 
 extern "C" int64_t bl_launch_count(const bl_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-#include "bl_grid.cuh"

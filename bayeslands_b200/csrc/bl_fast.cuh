@@ -981,7 +981,9 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
     if (c.CDr > 0.) {            // river-borne marine sediment diffusion works on the global arrays
         for (int k = tid; k < N; k += TPB) { const double sf = sedflux[k]; z[k] += sf; cumdiff[k] += sf; }
         __syncthreads();
-        marine_diffusion<KDT>(c, S, dsm, sea, timestep);
+        // 33 bytes of shared memory per node when the CTA has them, else the global-memory form (same arithmetic)
+        if ((size_t)33 * Nq + 64 <= (size_t)S.dsm_bytes) marine_diffusion<KDT>(c, S, dsm, sea, timestep);
+        else phase_marine_diffusion(c, S, sea, timestep);
         for (int k = tid; k < N; k += TPB) { zs[k] = z[k]; fls[k] = c.flags[k]; }
     } else {
 #pragma unroll 4

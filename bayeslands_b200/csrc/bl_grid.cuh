@@ -685,6 +685,7 @@ __global__ void k_ckpt_final(GConst g, double *out_sse, double *out_pts)
 struct bl_grid {
     grid::GConst g;
     int device, B, debug;
+    int group;                 // proposals per fill group (bl_params.opt_grid_group, default 64)
     long long launches;
     long long last_sweeps;     // sweeps the previous step's fill needed (first chunk size)
     int *h_counters;           // pinned [4]
@@ -842,6 +843,7 @@ extern "C" int bl_grid_create(const bl_lattice *lt, const bl_params *p, int B, i
     ctx->d_ckpt = (int *)(ws + L.ckpt);
     g.stops = ctx->d_stops; g.ckpt = ctx->d_ckpt; g.nstops = 0;
     ctx->device = device; ctx->B = B; ctx->debug = debug; ctx->launches = 0; ctx->last_sweeps = 0;
+    ctx->group = (p->opt_grid_group > 0) ? p->opt_grid_group : 64;
     CUDA_OK(cudaMallocHost((void **)&ctx->h_counters, 4 * sizeof(int)));
     *out = ctx;
     return BL_OK;
@@ -879,7 +881,7 @@ int grid_one_step(bl_grid *ctx, double *out_pts, double *out_sse, double *out_el
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     // Depression filling, a group of proposals at a time: the pending regions of ~64 landscapes (~100 MB of rows) stay in
     // L2 from pass to pass, those of 256 do not (measured: 5.2 ms per proposal-step at B = 256 in one group, 2.75 at 64)
-    static const int group = getenv("BL_GRID_GROUP") ? std::max(1, atoi(getenv("BL_GRID_GROUP"))) : 64;
+    const int group = ctx->group;
     long long most = 0;
     for (int p0 = 0; p0 < B; p0 += group) {
         const int nB = std::min(group, B - p0);

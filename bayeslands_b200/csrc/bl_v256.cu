@@ -1,0 +1,5 @@
+// bl_v256.cu - device code instantiated for four 256-thread CTAs per SM: small meshes such as the etopo configs.
+#define BL_NS v256
+#define BL_TPB 256
+#define BL_MINB 4
+#include "bl_variant.cuh"

@@ -33,7 +33,12 @@ class Engine:
     """One context = one mesh + one parameter set + B proposals resident on `device`."""
 
     def __init__(self, mesh, inp, B: int, device: int = 0, real_elev: Optional[np.ndarray] = None,
-                 erdp_coords: Optional[Sequence] = None, shuffle_mode: int = 1, sealevel=None, disp=None):
+                 erdp_coords: Optional[Sequence] = None, shuffle_mode: int = 1, sealevel=None, disp=None,
+                 tpb: int = 0, force_generic: bool = False, l2_persist: bool = True, lean: bool = False,
+                 debug: int = 0):
+        """Engine options (`bl_params.opt_*`; the library reads no environment variables): `tpb` threads per CTA
+        (0 = automatic), `force_generic` the L2-resident device path, `lean` production mode without the per-stage
+        products kept for `field()`."""
         if not torch.cuda.is_available():
             raise _lib.BlError("bayeslands_b200.Engine needs a CUDA device (no CPU fallback)")
         self.L = _lib.load()
@@ -88,6 +93,10 @@ class Engine:
             k["pts"] = cells
             self.npts = len(cells)
             p.npts, p.pts_cell = self.npts, _ip(cells)
+        p.opt_tpb = int(tpb)
+        p.opt_flags = ((_lib.OPT_FORCE_GENERIC if force_generic else 0) | (0 if l2_persist else _lib.OPT_NO_L2_PERSIST)
+                       | (_lib.OPT_LEAN if lean else 0))
+        p.opt_debug = int(debug)
         self._m, self._p = m, p
         nbytes = self.L.bl_workspace_bytes(C.byref(m), C.byref(p), self.B)
         if nbytes == 0:
@@ -192,6 +201,12 @@ class Engine:
                                          status.ctypes.data_as(C.c_void_p), ldt.ctypes.data_as(C.c_void_p),
                                          self._stream()))
         return dict(tNow=tnow, steps=steps, status=status, last_dt=ldt)
+
+    def status(self) -> np.ndarray:
+        """Per-proposal status bits (`BL_ST_*`) of the evaluations run since the last reset."""
+        st = np.empty(self.B, dtype=np.uint32)
+        _lib.check(self.L.bl_get_scalars(self.ctx, None, None, st.ctypes.data_as(C.c_void_p), None, self._stream()))
+        return st
 
     def phase_cycles(self) -> np.ndarray:
         """[B, BL_NPHASE] SM cycles per phase (see _lib.PHASES), accumulated since reset."""

@@ -25,7 +25,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import config, hostparams, mesh as meshmod
+from . import _lib, config, hostparams, mesh as meshmod
 from .engine import Engine
 
 
@@ -36,12 +36,13 @@ def log_likelihood(sse_elev, G, pts_pred, pts_real, likl_sed, sed_weight=50.0):
     tausq = sse_elev / G
     with np.errstate(divide="ignore", invalid="ignore"):
         lik = -0.5 * G * np.log(2 * math.pi * tausq) - 0.5 * sse_elev / tausq
+        lik = np.where(np.isfinite(sse_elev), lik, -np.inf)        # failed evaluations (status bits) never win
         if likl_sed:
             d2 = np.square(pts_pred[..., 1:, :] - pts_real[1:, :])          # [B, nt-1, npts]
             npts = pts_real.shape[1]
             t2 = d2.sum(axis=-1) / npts                                      # [B, nt-1]
             lp = (-0.5 * npts * np.log(2 * math.pi * t2) - 0.5 * d2.sum(axis=-1) / t2).sum(axis=-1)
-            lik = lik + lp * sed_weight
+            lik = np.where(np.isfinite(lik), lik + lp * sed_weight, -np.inf)
     return lik, tausq
 
 
@@ -128,6 +129,13 @@ class bayeslands_mcmc(object):
         self._h_sse.copy_(sse, non_blocking=True)
         self._h_pts.copy_(pts, non_blocking=True)
         torch.cuda.current_stream(eng.tdev).synchronize()
+        # device status words: an evaluation whose pit cascade hit its iteration guard or that produced a non-finite
+        # surface is wrong - its SSE becomes +inf, i.e. log-likelihood -inf, so Metropolis can never accept it
+        # (a NaN likelihood would be accepted: min(1, exp(nan)) is 1)
+        self.last_status = eng.status()[:n].copy() if hasattr(eng, "status") else np.zeros(n, dtype=np.uint32)
+        failed = (self.last_status & _lib.ST_FATAL) != 0
+        if failed.any():
+            self._h_sse.numpy()[:n][failed] = np.inf
         out_e = out_d = None
         if grids:
             ny, nx = self.mesh.grid_ny, self.mesh.grid_nx

@@ -48,9 +48,8 @@ typedef enum {
 
 /* per-proposal status bits written by the device loop (bl_get_status) */
 #define BL_ST_CASCADE_GUARD 1u   /* pit cascade hit the iteration guard (reference would spin) */
-#define BL_ST_MARINE        2u   /* marine deposition reached (etopo path) but CDr/marine kernels disabled */
 #define BL_ST_DRAIN_CYCLE   4u   /* pit-drainage graph had a cycle: sequential fallback was used */
-#define BL_ST_NAN           8u   /* non-finite elevation produced */
+#define BL_ST_NAN           8u   /* non-finite elevation / time step produced (set at every checkpoint and at the end of a run) */
 
 typedef struct {
     int32_t N;                 /* TIN nodes */
@@ -92,7 +91,16 @@ typedef struct {
     const double *real_elev;   /* [G] observed final topography, host, or NULL */
     int32_t npts;              /* erdp points (<= BL_NPTS_MAX) */
     const int32_t *pts_cell;   /* [npts] flat grid cell index row*nx+col (bl_mcmc.py:156-157) */
+    /* engine options (all 0 = defaults).  Nothing in the library reads environment variables. */
+    int32_t opt_tpb;           /* threads per CTA: 0 automatic, or 256 / 512 / 1024 */
+    int32_t opt_flags;         /* BL_OPT_* bits */
+    int32_t opt_grid_group;    /* lattice engine: proposals per fill group (0 = 64) */
+    int32_t opt_debug;         /* timing experiments only */
 } bl_params;
+
+#define BL_OPT_FORCE_GENERIC 1   /* use the L2-resident device path even if the mesh fits shared memory */
+#define BL_OPT_NO_L2_PERSIST 2   /* do not pin the mesh constants in L2 */
+#define BL_OPT_LEAN          4   /* production mode: skip the stores of per-stage products kept only for bl_get_field */
 
 typedef struct bl_ctx bl_ctx;
 

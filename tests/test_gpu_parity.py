@@ -83,16 +83,15 @@ ETOPO_PROPOSALS = [(1.5, 5e-6), (2.9, 6.9e-6), (0.5, 3e-6), (0.0, 5e-6)]
 
 
 @pytest.mark.parametrize("generic", [0, 1])
-def test_etopo_stepwise_bit_exact(etopo_fast, generic, monkeypatch):
+def test_etopo_stepwise_bit_exact(etopo_fast, generic):
     """etopo path: sea-level curve, 'slope' boundary, marine deposition (marine_distribution), river-borne marine
     diffusion sub-steps, overflow-to-sea fallback - every stage array against the oracle, both device paths."""
     from bayeslands_b200.engine import Engine
     from oracle import oracle
     d, inp, m = etopo_fast
-    if generic:
-        monkeypatch.setenv("BL_FORCE_GENERIC", "1")
     B = len(ETOPO_PROPOSALS)
-    eng = Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=ETOPO_FAST_COORDS, sealevel=d["sealevel"])
+    eng = Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=ETOPO_FAST_COORDS, sealevel=d["sealevel"],
+                 force_generic=bool(generic))
     rain = np.array([p[0] for p in ETOPO_PROPOSALS]); erod = np.array([p[1] for p in ETOPO_PROPOSALS])
     seeds = np.arange(B, dtype=np.int64) + 5
     eng.reset(rain, erod, seeds)
@@ -139,12 +138,11 @@ def test_etopo_full_run_bit_exact(etopo_fast):
             assert np.array_equal(elev[b, ci].reshape(ev[T].shape), ev[T]) and np.array_equal(pts[b, ci], pv[T])
 
 
-def test_crater_generic_path_bit_exact(crater_fast, monkeypatch):
+def test_crater_generic_path_bit_exact(crater_fast):
     """The generic (L2-resident) device path stays bit-exact too: it serves meshes too large for shared memory."""
     from oracle import oracle
-    monkeypatch.setenv("BL_FORCE_GENERIC", "1")
     d, inp, m = crater_fast
-    eng = _engine(crater_fast, 2)
+    eng = _engine(crater_fast, 2, force_generic=True)
     rain = np.array([1.5, 2.7]); erod = np.array([5e-5, 3.3e-5]); seeds = np.array([3, 4], dtype=np.int64)
     eng.reset(rain, erod, seeds)
     oms = [oracle.OracleModel(m, inp, seed=int(s)) for s in seeds]
@@ -159,13 +157,12 @@ def test_crater_generic_path_bit_exact(crater_fast, monkeypatch):
 
 
 @pytest.mark.parametrize("tpb", [256, 512, 1024])
-def test_crater_every_cta_size_bit_exact(crater_fast, tpb, monkeypatch):
-    """The device code is instantiated once per CTA size (bl_engine.cu: v256 / v512 / v1024); BL_TPB forces one.
-    Block-level primitives (scans, ordered compaction, warp ballots) must give the same bits at every size."""
+def test_crater_every_cta_size_bit_exact(crater_fast, tpb):
+    """The device code is instantiated once per CTA size (csrc/bl_v256.cu / bl_v512.cu / bl_v1024.cu); `opt_tpb` forces
+    one.  Block-level primitives (scans, ordered compaction, warp ballots) must give the same bits at every size."""
     from oracle import oracle
-    monkeypatch.setenv("BL_TPB", str(tpb))
     d, inp, m = crater_fast
-    eng = _engine(crater_fast, 2)
+    eng = _engine(crater_fast, 2, tpb=tpb)
     rain = np.array([0.9, 2.2]); erod = np.array([6e-5, 4e-5]); seeds = np.array([8, 9], dtype=np.int64)
     eng.reset(rain, erod, seeds)
     oms = [oracle.OracleModel(m, inp, seed=int(s)) for s in seeds]
@@ -182,7 +179,7 @@ def test_crater_every_cta_size_bit_exact(crater_fast, tpb, monkeypatch):
 
 
 @pytest.mark.parametrize("generic", [0, 1])
-def test_synthetic_uplift_regular_grid_bit_exact(generic, monkeypatch):
+def test_synthetic_uplift_regular_grid_bit_exact(generic):
     """BASELINE config 5 in miniature: regular grid (D8 stencil as the neighbour list), noisy flat start, uplift
     map applied every step (buildFlux.py:312-313), purely erosive (dep = 0), row-major numbering (deep Gauss-Seidel
     dependency levels -> exercises the level schedule of the fill)."""
@@ -191,8 +188,6 @@ def test_synthetic_uplift_regular_grid_bit_exact(generic, monkeypatch):
     from bayeslands_b200.engine import Engine
     from oracle import oracle
     from conftest import ROOT
-    if generic:
-        monkeypatch.setenv("BL_FORCE_GENERIC", "1")
     nx, ny, dx = (24, 18, 100.0) if not generic else (40, 28, 100.0)   # 58 / 94 Gauss-Seidel levels
     rng = np.random.default_rng(1234)
     z0 = 10.0 + rng.uniform(0, 1, (ny, nx))
@@ -209,7 +204,7 @@ def test_synthetic_uplift_regular_grid_bit_exact(generic, monkeypatch):
     assert disp.shape == (m.N,) and disp.max() <= 1.0001e-3 and disp.min() >= 0.0
     B = 3
     rain = np.array([0.6, 1.5, 2.4]); erod = np.array([3.2e-6, 5e-6, 6.8e-6]); seeds = np.array([1, 2, 3], dtype=np.int64)
-    eng = Engine(m, inp, B, disp=disp)
+    eng = Engine(m, inp, B, disp=disp, force_generic=bool(generic))
     eng.reset(rain, erod, seeds)
     oms = [oracle.OracleModel(m, inp, seed=int(s), disp=disp) for s in seeds]
     for b, om in enumerate(oms):
@@ -232,14 +227,9 @@ def test_first_step_receivers_match_reference_sfd_vectors(crater_fast):
     from conftest import ROOT
     d, inp, m = crater_fast
     g = np.load(os.path.join(ROOT, "tests", "golden", "sfd_reference_vectors.npz"))
-    for generic in (0, 1):
-        if generic:
-            os.environ["BL_FORCE_GENERIC"] = "1"
-        try:
-            eng = Engine(m, inp, 2)
-            eng.reset(np.array([1.5, 0.5]), np.array([5e-5, 4e-5]), np.array([1, 2], dtype=np.int64))
-            eng.step(15000.0)
-            for b in range(2):
-                assert np.array_equal(eng.field("rcv1", b), g["rcv1_0"]), (generic, b)
-        finally:
-            os.environ.pop("BL_FORCE_GENERIC", None)
+    for generic in (False, True):
+        eng = Engine(m, inp, 2, force_generic=generic)
+        eng.reset(np.array([1.5, 0.5]), np.array([5e-5, 4e-5]), np.array([1, 2], dtype=np.int64))
+        eng.step(15000.0)
+        for b in range(2):
+            assert np.array_equal(eng.field("rcv1", b), g["rcv1_0"]), (generic, b)
