@@ -30,7 +30,9 @@ struct DevConst {
     int N, bounds, KD, nlev, G, npts, nsea, B;
     const int *ngb;             // [KD][N]
     const unsigned short *ngb16; // [N][KDT] node-major u16 copy for the shared-memory path (0xFFFF = none)
-    int Nq, KDT;                // N rounded up to 64; rows of ngb16
+    const unsigned short *ngb16f; // same rows with empty slots = N: the depression filling keeps W[N] = 2e6 there, so a
+                                 // neighbour gather needs no "is this slot used" test
+    int Nq, KDT;                // N + 1 rounded up to 64; rows of ngb16
     const float *ve32;          // [N][KDT][2] (vor, edge) as float pairs when both are float32-representable, else null
     int lev_contig;             // lev_nodes[i] == bounds + i (colour-major numbering)
     int dbg;                    // BL_DEBUG experiments (timing only)
@@ -128,5 +130,6 @@ struct RunArgs {
                                      const unsigned long long *seed, double tStart);                                     \
     cudaError_t bl_func_attr_##NS(int KDT, cudaFuncAttributes *attr);
 BL_DECL_VARIANT(v1024)
+BL_DECL_VARIANT(v768)
 BL_DECL_VARIANT(v512)
 BL_DECL_VARIANT(v256)

@@ -13,15 +13,18 @@ struct Smem {
     int fl_head[LEVMAX + 1], fl_tail[LEVMAX + 1], fl_base[LEVMAX + 1], fl_mask[LEVMAX + 1];   // per-level worklist rings of the fill
     unsigned char *dsm;        // dynamic shared memory of the fast kernel (nullptr on the generic path)
     unsigned short boff[2048]; // depth-bucket offsets of the tree passes (fast path)
-    static constexpr int FB_WORDS = (NWARP >= 4) ? 128 : 32 * NWARP;   // fill: bitmap words compacted per round
-    unsigned fb_word[FB_WORDS];
-    unsigned short fb_pre[FB_WORDS];
-    int fb_tot[FB_WORDS / 32];
     int dsm_bytes;
     int scan[NWARP + 1];
     double red[NWARP];
     int ibuf[8];
     double dbuf[8];
+    // Scalars of the proposal that live across the whole run.  They are kept here and re-read where needed instead of
+    // being carried in registers: the kernel is capped at 64 registers per thread and this state alone held ~30 of them
+    // through every phase (seen as spills and as S2R re-materialisation inside the inner loops).
+    double tNow, last_dt, rain, erod, sea, tStop, newdt;
+    long long step, tick0;
+    unsigned long long seed;
+    int nbase1, nbase, any_marine;
 };
 
 // diagnostics: thread 0 adds the cycles since the previous tick to slot i of this CTA's phase_cyc row (slots >= 16)
@@ -852,8 +855,9 @@ __device__ double blk_pairwise_sum(const double *a, int n, Smem &S, int *loff, i
 // not fit to the lowest neighbour" walk over the marine deposit nodes, diffnb passes, elevation updated in
 // place.  Kept literal on one thread per proposal (parallelism is across proposals); the per-pass reset of the
 // sediment array is done by the whole block.  Adds the resulting thickness to dth[].
-__device__ void phase_marine_distribution(const DevConst &c, Smem &S, double sea)
+__device__ __noinline__ void phase_marine_distribution(const DevConst &c, Smem &S, double sea)
 {
+    __builtin_assume(__isShared(&c)); __builtin_assume(__isShared(&S));
     const int N = c.N, tid = threadIdx.x;
     const double *z = S.P.f[F_Z];
     double *dep = S.P.f[F_SEDIN], *dth = S.P.f[F_DTHICK];
@@ -1110,8 +1114,9 @@ __device__ void phase_streampower_serial(const DevConst &c, Smem &S, double erod
 
 // phase: erosion / deposition thickness.  flowNetwork.compute_sedflux (flowNetwork.py:721-793) with getids
 // (FLOWalgo.f90:1089-1180) fused.  Result sedflux[] (= ed) in metres.
-__device__ void phase_erodep(const DevConst &c, Smem &S, double sea)
+__device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea)
 {
+    __builtin_assume(__isShared(&c)); __builtin_assume(__isShared(&S));
     const int N = c.N, tid = threadIdx.x;
     // distinct per-proposal arrays: __restrict__ lets the streaming loops below keep several nodes' loads in flight
     const double *__restrict__ z = S.P.f[F_Z], *__restrict__ W = S.P.f[F_FILLH], *__restrict__ pitVol = S.P.f[F_PITVOL];
@@ -1330,49 +1335,50 @@ __device__ void phase_apply(const DevConst &c, Smem &S, double sea, double times
     }
 }
 
-// one time step = buildFlux.streamflow (buildFlux.py:21-100) + sediment_flux (:102-320)
-__device__ void time_step(const DevConst &c, Smem &S, double &tNow, long long &step, double tStop, double rain,
-                          double erod, unsigned long long seed, double &last_dt)
+// one time step = buildFlux.streamflow (buildFlux.py:21-100) + sediment_flux (:102-320).  Proposal scalars (tNow, step,
+// rain, erodibility, seed, tStop) are read from / written to S (see Smem).
+#define BL_TICK(i) do { if (threadIdx.x == 0) { long long *pc_ = S.c.phase_cyc + (size_t)blockIdx.x * NPHASE; \
+                                               const long long t1_ = clock64(); pc_[i] += t1_ - S.tick0; S.tick0 = t1_; } } while (0)
+__device__ void time_step(const DevConst &c, Smem &S)
 {
     const int tid = threadIdx.x;
-    const double sea = sea_level(c, tNow);
-    long long *pc = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
-    long long t0 = clock64();
-#define TICK(i) do { if (tid == 0) { long long t1_ = clock64(); pc[i] += t1_ - t0; t0 = t1_; } } while (0)
-    phase_fill(c, S, sea);
-    TICK(0);
+    if (tid == 0) { S.sea = sea_level(c, S.tNow); S.tick0 = clock64(); }
+    __syncthreads();
+    phase_fill(c, S, S.sea);
+    BL_TICK(0);
     phase_sfd(c, S);
-    TICK(1);
+    BL_TICK(1);
     // real-surface stack (bases ascending), then filled-surface stack (bases shuffled)
     int nbase1, nbase;
     tree_links(c, S.P.i[I_RCV1], S.P.i[I_FC], S.P.i[I_NS], nullptr, nullptr, nullptr);
     phase_stack(c, S, S.P.i[I_RCV1], S.P.i[I_FC], S.P.i[I_NS], S.P.i[I_STACK1], S.P.i[I_POS1], S.P.i[I_LA], nbase1,
                 false, 0ull);
-    TICK(2);
+    if (tid == 0) S.nbase1 = nbase1;     // read after the barriers inside phase_basins
+    BL_TICK(2);
     phase_basins(c, S, S.P.i[I_LA], nbase1);
-    TICK(3);
-    // the filled tree reuses fc; its sibling links go to I_SUCC2 temporarily? no: keep I_NS for the real tree
-    // (basin segments are needed later), filled-tree links live in I_LC/I_PS (+ I_SUCC as next-sibling).
+    BL_TICK(3);
+    // the filled tree keeps I_NS for the real tree (basin segments are needed later); its links live in I_LC / I_PS
+    // (+ I_SUCC as next sibling)
     tree_links(c, S.P.i[I_RCV], S.P.i[I_FC], S.P.i[I_SUCC], S.P.i[I_LC], S.P.i[I_PS], S.P.i[I_CNT]);
     phase_stack(c, S, S.P.i[I_RCV], S.P.i[I_FC], S.P.i[I_SUCC], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase,
-                c.shuffle != 0, mix64(seed + (unsigned long long)step));
-    TICK(4);
-    phase_drainage(c, S, S.P.i[I_LA], nbase1, sea);
-    TICK(5);
-    phase_discharge(c, S, rain);
-    TICK(6);
+                c.shuffle != 0, mix64(S.seed + (unsigned long long)S.step));
+    BL_TICK(4);
+    phase_drainage(c, S, S.P.i[I_LA], S.nbase1, S.sea);
+    BL_TICK(5);
+    phase_discharge(c, S, S.rain);
+    BL_TICK(6);
     // CFL and time step (buildFlux.py:169-177)
-    const double flowcfl = phase_cfl(c, S, erod);
+    const double flowcfl = phase_cfl(c, S, S.erod);
     double cfl = fmin(flowcfl, c.hill);
     cfl = py2_floorish(cfl);
-    cfl = fmin(cfl, tStop - tNow);
+    cfl = fmin(cfl, S.tStop - S.tNow);
     cfl = fmax(c.minDT, cfl);
     cfl = fmin(c.maxDT, cfl);
     // flowNetwork.compute_sedflux (flowNetwork.py:579-719)
     double newdt = cfl;
-    TICK(7);
-    phase_streampower(c, S, erod, sea, newdt);
-    TICK(8);
+    BL_TICK(7);
+    phase_streampower(c, S, S.erod, S.sea, newdt);
+    BL_TICK(8);
     {
         const int N = c.N;
         const double *cdepo = S.P.f[F_DEPO], *cero = S.P.f[F_ERO], *pitVol = S.P.f[F_PITVOL];
@@ -1390,17 +1396,15 @@ __device__ void time_step(const DevConst &c, Smem &S, double &tNow, long long &s
         if (nb) { minperc = blk_min(minperc, S); newdt = cfl * minperc; }
         newdt = py2_floorish(newdt);
         newdt = fmax(c.minDT, newdt);
-        if (newdt < cfl) phase_streampower(c, S, erod, sea, newdt);
+        if (newdt < cfl) phase_streampower(c, S, S.erod, S.sea, newdt);
     }
-    TICK(9);
-    phase_erodep(c, S, sea);
-    TICK(10);
-    phase_apply(c, S, sea, newdt);
-    TICK(11);
-#undef TICK
-    tNow += newdt;
-    last_dt = newdt;
-    ++step;
+    BL_TICK(9);
+    phase_erodep(c, S, S.sea);
+    BL_TICK(10);
+    phase_apply(c, S, S.sea, newdt);
+    BL_TICK(11);
+    if (tid == 0) { S.tNow += newdt; S.last_dt = newdt; S.step += 1; }
+    __syncthreads();
 }
 
 #include "bl_fast.cuh"
@@ -1436,17 +1440,19 @@ bl_run_kernel(const DevConst cpar, int nstops, const double *__restrict__ stops,
     for (int i = tid; i <= c.nlev && i <= LEVMAX; i += TPB) S.lev_off[i] = c.lev_off[i];
     if (tid < 8) S.ibuf[tid] = 0;
     __syncthreads();
-    double tNow = c.tnow[b];
-    long long step = c.steps[b];
-    double last_dt = c.lastdt[b];
-    const double rain = c.rain[b], erod = c.erod[b];
-    const unsigned long long seed = c.seed ? c.seed[b] : 0ull;
+    if (tid == 0) {
+        S.tNow = c.tnow[b]; S.step = c.steps[b]; S.last_dt = c.lastdt[b];
+        S.rain = c.rain[b]; S.erod = c.erod[b]; S.seed = c.seed ? c.seed[b] : 0ull;
+    }
+    __syncthreads();
     int ck_seen = 0;
     for (int s = 0; s < nstops; ++s) {
-        const double tStop = stops[s];
-        while (tNow < tStop) {
-            if (KDT > 0) fast::time_step<(KDT > 0 ? KDT : 8)>(c, S, dsm, tNow, step, tStop, rain, erod, seed, last_dt);
-            else time_step(c, S, tNow, step, tStop, rain, erod, seed, last_dt);
+        __syncthreads();                    // every thread is done with the previous stop's loop condition
+        if (tid == 0) S.tStop = stops[s];
+        __syncthreads();
+        while (S.tNow < S.tStop) {
+            if (KDT > 0) fast::time_step<(KDT > 0 ? KDT : 8)>(c, S, dsm);
+            else time_step(c, S);
             if (single_step) break;
         }
         const int ck = ckpt ? ckpt[s] : -1;
@@ -1477,12 +1483,12 @@ bl_run_kernel(const DevConst cpar, int nstops, const double *__restrict__ stops,
     }
     {   // NaN / Inf guard: a non-finite elevation or clock marks the evaluation as failed
         const double *z = S.P.f[F_Z];
-        int bad = !isfinite(tNow);
+        int bad = !isfinite(S.tNow);
         for (int k = tid; k < c.N; k += TPB) bad |= !isfinite(z[k]);
         bad = __syncthreads_or(bad);
         if (tid == 0 && bad) atomicOr(&c.status[b], BL_ST_NAN);
     }
-    if (tid == 0) { c.tnow[b] = tNow; c.steps[b] = step; c.lastdt[b] = last_dt; }
+    if (tid == 0) { c.tnow[b] = S.tNow; c.steps[b] = S.step; c.lastdt[b] = S.last_dt; }
 }
 
 __global__ void bl_reset_kernel(const DevConst c, const double *rain, const double *erod,

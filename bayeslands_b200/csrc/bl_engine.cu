@@ -47,7 +47,7 @@ extern "C" int bl_version(void) { return 100; }
 
 namespace {
 struct Layout {
-    size_t off_ve32, off_ngb16, off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
+    size_t off_ve32, off_ngb16, off_ngb16f, off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
         off_levo, off_gidx, off_gw, off_gex, off_real, off_pts, off_seat, off_seav, off_rain, off_erod, off_seed,
         off_tnow, off_lastdt, off_steps, off_status, off_phase, off_stops, off_ckpt, off_prop, total;
     int KD, nlev;
@@ -68,12 +68,12 @@ constexpr int STOPS_CAP = 4096;
 
 // dynamic shared memory the shared-memory device path (bl_fast.cuh) needs for a mesh of Nq (padded) nodes:
 // 17 bytes per node for the scans (value fp64 + links + order + kind) + the event bitmap; the fill keeps W, z, the pending
-// bitmap and the id list of a round; the marine phases of the etopo configs stage 33 bytes per node (marine_diffusion) or
+// flags and the per-warp id rings; the marine phases of the etopo configs stage 33 bytes per node (marine_diffusion) or
 // the neighbour table as well (marine_distribution) - those fall back to global memory when the CTA cannot have it.
 size_t fast_smem_need(int Nq, int KDT, bool marine)
 {
     size_t need = (size_t)17 * Nq + Nq / 8 + 256;
-    need = std::max(need, (size_t)16 * Nq + Nq / 8 + 64 + 8192);
+    need = std::max(need, (size_t)17 * Nq + 32 * 128 + 64);        // fill: W, z, pending flags, per-warp slot lists
     if (marine) need = std::max(need, std::max((size_t)Nq * (17 + 2 * KDT) + 256, (size_t)33 * Nq + 64));
     return need;
 }
@@ -82,6 +82,7 @@ cudaError_t func_attr(int tpb, int KDT, cudaFuncAttributes *fa)
 {
     if (tpb == 256) return bl_func_attr_v256(KDT, fa);
     if (tpb == 512) return bl_func_attr_v512(KDT, fa);
+    if (tpb == 768) return bl_func_attr_v768(KDT, fa);
     return bl_func_attr_v1024(KDT, fa);
 }
 
@@ -92,8 +93,9 @@ Layout make_layout(const bl_mesh *m, const bl_params *p, int B, int KD, int nlev
     const size_t N = m->N;
     auto take = [&](size_t bytes) { size_t r = o; o = rup(o + bytes, 256); return r; };
     L.off_ngb = take((size_t)KD * N * 4);
-    L.off_ngb16 = take((size_t)BL_KP * rup(N, 64) * 2);
-    L.off_ve32 = take((size_t)BL_KP * rup(N, 64) * 8);
+    L.off_ngb16 = take((size_t)BL_KP * rup(N + 1, 64) * 2);
+    L.off_ngb16f = take((size_t)BL_KP * rup(N + 1, 64) * 2);
+    L.off_ve32 = take((size_t)BL_KP * rup(N + 1, 64) * 8);
     L.off_vor = take((size_t)KD * N * 8);
     L.off_edge = take((size_t)KD * N * 8);
     L.off_area = take(N * 8);
@@ -195,13 +197,13 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
             vorT[(size_t)q * N + i] = m->vor[(size_t)i * BL_KP + q];
             edgeT[(size_t)q * N + i] = m->edge[(size_t)i * BL_KP + q];
         }
-    const int Nq = (int)rup((size_t)N, 64);
+    const int Nq = (int)rup((size_t)N + 1, 64);     // one spare slot: the fill's dummy neighbour (see DevConst::ngb16f)
     // CTA size and device path.  The shared-memory path needs fast_smem_need() bytes of dynamic shared memory; what a CTA
     // may use is the device's opt-in limit minus the kernel's static shared memory (queried, not assumed).
     const int kdt_want = (KD <= 8) ? 8 : (KD <= 12 ? 12 : 20);
     int tpb = (N <= 4096) ? 256 : 1024;
-    if (p->opt_tpb == 256 || p->opt_tpb == 512 || p->opt_tpb == 1024) tpb = p->opt_tpb;
-    else if (p->opt_tpb != 0) { g_err = "bl_ctx_create: opt_tpb must be 0, 256, 512 or 1024"; return BL_ERR_ARG; }
+    if (p->opt_tpb == 256 || p->opt_tpb == 512 || p->opt_tpb == 768 || p->opt_tpb == 1024) tpb = p->opt_tpb;
+    else if (p->opt_tpb != 0) { g_err = "bl_ctx_create: opt_tpb must be 0, 256, 512, 768 or 1024"; return BL_ERR_ARG; }
     int dyn_max = 0;
     {
         int optin = 0;
@@ -222,6 +224,14 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
             if (j < 0) break;
             ngb16[(size_t)i * KDrow + q] = (unsigned short)j;
         }
+    std::vector<unsigned short> ngb16f((size_t)BL_KP * Nq, (unsigned short)N);
+    if (KDT)
+        for (int i = 0; i < N; ++i)
+            for (int q = 0; q < KD; ++q) {
+                int j = m->ngb[(size_t)i * BL_KP + q];
+                if (j < 0) break;
+                ngb16f[(size_t)i * KDrow + q] = (unsigned short)j;
+            }
     std::vector<float> ve32((size_t)BL_KP * Nq * 2, 0.f);
     bool ve_ok = KDT > 0;
     for (int i = 0; i < N && ve_ok; ++i)
@@ -247,6 +257,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
 #define UP(off, src, bytes) CUDA_OK(cudaMemcpy(ws + (off), (src), (bytes), cudaMemcpyHostToDevice))
     UP(L.off_ngb, ngbT.data(), ngbT.size() * 4);
     UP(L.off_ngb16, ngb16.data(), ngb16.size() * 2);
+    UP(L.off_ngb16f, ngb16f.data(), ngb16f.size() * 2);
     UP(L.off_ve32, ve32.data(), ve32.size() * 4);
     UP(L.off_vor, vorT.data(), vorT.size() * 8);
     UP(L.off_edge, edgeT.data(), edgeT.size() * 8);
@@ -273,6 +284,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     c.N = N; c.bounds = m->bounds; c.KD = KD; c.nlev = nlev; c.G = m->G; c.npts = p->npts; c.nsea = p->nsea; c.B = B;
     c.ngb = (const int *)(ws + L.off_ngb);
     c.ngb16 = (const unsigned short *)(ws + L.off_ngb16);
+    c.ngb16f = (const unsigned short *)(ws + L.off_ngb16f);
     c.Nq = Nq; c.KDT = KDT;
     c.ve32 = ve_ok ? (const float *)(ws + L.off_ve32) : nullptr;
     c.lev_contig = 1;
@@ -410,6 +422,7 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
     a.nck = nck; a.single_step = single;
     if (ctx->tpb == 256) CUDA_OK(bl_launch_run_v256(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
     else if (ctx->tpb == 512) CUDA_OK(bl_launch_run_v512(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
+    else if (ctx->tpb == 768) CUDA_OK(bl_launch_run_v768(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
     else CUDA_OK(bl_launch_run_v1024(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
     ctx->launches++;
     return BL_OK;
@@ -457,9 +470,11 @@ extern "C" int bl_get_field(bl_ctx *ctx, int field, int proposal, void *dst, voi
         case BL_F_PITID: ii = I_PITID; break;
         case BL_F_PITDRAIN: ii = I_PITDRAIN; break;
         case BL_F_ALLDRAIN: ii = I_ALLDRAIN; break;
+        case 100: src = u + 4 * Np; bytes = (size_t)N * 8; break;     // diagnostics: the key scratch (trace builds)
         default: g_err = "bl_get_field: unknown field"; return BL_ERR_ARG;
     }
-    if (fi >= 0) { src = d + (size_t)fi * Np; bytes = (size_t)N * 8; }
+    if (src) { }
+    else if (fi >= 0) { src = d + (size_t)fi * Np; bytes = (size_t)N * 8; }
     else { src = ip + (size_t)ii * Np; bytes = (size_t)N * 4; }
     CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));

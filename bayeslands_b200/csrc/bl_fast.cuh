@@ -12,6 +12,12 @@
 
 namespace fast {
 
+// The phases are separate (__noinline__) functions so that each gets its own register allocation under the kernel's
+// 64-register cap; BL_ASSUME_SHARED tells the compiler that Smem / DevConst / the dynamic buffer live in shared memory,
+// so that their accesses stay LDS / STS with 32-bit addresses although the pointers arrive as generic ones.
+#define BL_ASSUME_SHARED(c, S, dsm) do { __builtin_assume(__isShared(&(c))); __builtin_assume(__isShared(&(S))); \
+                                         __builtin_assume(__isShared(dsm)); } while (0)
+
 constexpr unsigned short NONE16 = 0xFFFFu;
 constexpr unsigned END16 = 0xFFFFu;
 
@@ -43,8 +49,9 @@ __device__ __forceinline__ void none_ids(Ids<KDT> &ids)
 
 // sfd.c:55-153 on W / z held in shared memory ([Nq] each at the start of dsm): receivers on both surfaces
 template <int KDT>
-__device__ void fill_receivers(const DevConst &c, Smem &S, unsigned char *dsm, double sea, int &any_marine)
+__device__ __noinline__ void fill_receivers(const DevConst &c, Smem &S, unsigned char *dsm, double sea, int &any_marine)
 {
+    BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     double *W = (double *)dsm, *zs = W + Nq;
     // receivers on both surfaces
@@ -78,131 +85,190 @@ __device__ void fill_receivers(const DevConst &c, Smem &S, unsigned char *dsm, d
     any_marine = __syncthreads_or(mar);
 }
 
-// ---- depression filling, bitmap worklists (levels contiguous in node id) -------------------------------
-// Same literal Gauss-Seidel sweep as below, for meshes whose level-l nodes are the id range
-// [bounds + lev_off[l], bounds + lev_off[l+1]) (mesh.py numbers them so).  The pending set is one bit per node;
-// a changed node just ORs its neighbours' bits (no lists, no level lookup).  At a level's turn the level's
-// bitmap words are compacted block-wide (popc + prefix sums) and thread t evaluates the t-th pending node, so
-// the work of a spatially clustered front is spread over all warps.  W and z both stay in shared memory; the only
-// global access in the sweep is the node's packed neighbour ids.
-template <int KDT>
-__device__ void fill_bitmap(const DevConst &c, Smem &S, unsigned char *dsm, double sea)
+// ---- shared-memory accessors with explicit 32-bit addresses ------------------------------------------------
+// The latency-critical loops address shared memory through 32-bit window offsets (one __cvta_generic_to_shared per
+// buffer, plain integer arithmetic afterwards) and predicated stores: measured in situ, a dependent instruction costs
+// ~8 cycles and a branch / re-convergence pair ~40, so what matters in a round with a few hundred active lanes is the
+// number of instructions on the dependent chain, not the amount of work.
+__device__ __forceinline__ unsigned s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(unsigned a)
 {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2(unsigned a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned a)
+{
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8_if(bool p, unsigned a, unsigned v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.u8 [%1], %2;\n\t}" ::"r"((unsigned)p), "r"(a), "r"(v) : "memory");
+}
+
+// ---- depression filling, per-warp worklists (levels contiguous in node id) --------------------------------
+// Same literal Gauss-Seidel sweep as below, for meshes whose level-l nodes are the id range
+// [bounds + lev_off[l], bounds + lev_off[l+1]) (mesh.py numbers them so).  A round (one level of one sweep) evaluates a
+// thin front - a few hundred pending nodes out of ~3 000 - so its cost is the LENGTH of the dependent instruction chain
+// between two block barriers, not the amount of work.  Hence:
+//  * the pending set is one BYTE per node: a changed node wakes its neighbours with plain stores (no atomics; concurrent
+//    wakers store the same value), and nodes of other levels are the only flags a round writes besides clearing its own;
+//  * no block-wide compaction: half of the warps sweep, each owning 8 groups of 32 ids out of every 256 * NWF (dealt
+//    round-robin, so a front confined to one region of the landscape still spreads over all of them); a lane reads the 8
+//    flags of 8 consecutive ids as one 64-bit word, eight ballots pack the warp's pending ids into a byte list of its
+//    own, lanes evaluate them 32 at a time: straight-line code, no exchange between warps, ONE block barrier per round;
+//  * the evaluation issues every load it may need up front (neighbour ids, then all neighbour values through safe
+//    addresses), selects afterwards and stores under predicates: nothing sits behind a data-dependent branch.
+// W and z both stay in shared memory; the only global access in the sweep is the node's packed neighbour ids.
+template <int KDT>
+__device__ __forceinline__ void fill_eval(const unsigned short *__restrict__ ngb16f, int k, unsigned aW, unsigned aZ,
+                                          unsigned aP, double sea, double eps, double TH, int &loc)
+{
+    Ids<KDT> ids;        // empty slots hold the dummy node N, whose W is 2e6 (DevConst::ngb16f): no slot tests below
+    {
+        const uint2 *src = reinterpret_cast<const uint2 *>(ngb16f + (size_t)k * KDT);   // the longest latency: issued first
+#pragma unroll
+        for (int q = 0; q < KDT / 4; ++q) { const uint2 v = __ldg(src + q); ids.w[2 * q] = v.x; ids.w[2 * q + 1] = v.y; }
+    }
+    const unsigned ak = aW + 8u * (unsigned)k;
+    const double wk = lds_f64(ak), zk = lds_f64(aZ + 8u * (unsigned)k);
+    // min over the neighbours (exact: any association gives the same bits); four loads in flight at a time keep the
+    // evaluation within the register budget (a spill costs an L2 round trip: the L1 is carved out for shared memory)
+    double hmin = 2.e6;
+#pragma unroll
+    for (int p0 = 0; p0 < KDT; p0 += 4) {
+        double h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = lds_f64(aW + 8u * ids.get(p0 + u));
+        hmin = fmin(hmin, fmin(fmin(h[0], h[1]), fmin(h[2], h[3])));
+    }
+    // PDalgo.f90:51-79 without branches (same arithmetic, same comparisons):
+    //   if (W > z) { if (z >= he) W = z; else if (W > he) { W = he; if capped W = floor + TH else change = true } }
+    const double he = hmin + eps;
+    const bool wet = wk > zk, dry = zk >= he, lower = wk > he;
+    const double floor_ = (zk >= sea) ? zk : sea;
+    const bool capped = (he - floor_) > TH;
+    const double nlow = capped ? floor_ + TH : he;
+    const double nw = wet ? (dry ? zk : (lower ? nlow : wk)) : wk;
+    if (wet && !dry && lower && !capped) loc = 1;
+    if (nw != wk) {
+        sts_f64(ak, nw);
+        // wake only the neighbours this change can move: re-evaluating j alters W(j) only if
+        // min_nb W + eps < W(j), and the neighbour that brings the minimum down below W(j) - eps is the
+        // one that wakes j (W(j) is re-read: other levels do not change during this pass).  Flags of ghost nodes
+        // and of the dummy node may get set too: no level ever reads them.
+        const double lim = nw + eps;
+        double wj[KDT];
+#pragma unroll
+        for (int p = 0; p < KDT; ++p) wj[p] = lds_f64(aW + 8u * ids.get(p));
+#pragma unroll
+        for (int p = 0; p < KDT; ++p) sts_u8_if(wj[p] > lim, aP + ids.get(p), 1u);
+    }
+}
+
+template <int KDT>
+__device__ __noinline__ void fill_bitmap(const DevConst &c, Smem &S, unsigned char *dsm, double sea)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x, nb = c.bounds;
     const int lane = tid & 31, warp = tid >> 5;
-    double *W = (double *)dsm, *zs = W + Nq;
-    unsigned *bits = (unsigned *)(zs + Nq);                   // [Nq/32 + 1]
-    unsigned short *flist = (unsigned short *)(dsm + (size_t)16 * Nq + Nq / 8 + 64);   // [CHW * 32] pending ids of a round
-    const double *z = S.P.f[F_Z];
-    for (int i = tid; i < N; i += TPB) { const double zi = z[i]; zs[i] = zi; W[i] = (i < nb) ? zi : 1.e6; }
-    for (int i = tid; i <= Nq / 32; i += TPB) {               // every interior node starts pending
-        const int lo = i * 32;
-        unsigned m = 0xFFFFFFFFu;
-        if (lo + 32 <= nb || lo >= N) m = 0u;
-        else {
-            if (lo < nb) m &= ~((1u << (nb - lo)) - 1u);
-            if (lo + 32 > N) m &= (1u << (N - lo)) - 1u;
-        }
-        bits[i] = m;
+    // Half of the warps sweep, 8 flags per lane: a thin front then gives each sweeping warp ~20 pending ids, i.e. one
+    // evaluation pass with most lanes busy.
+    constexpr int NWF = (NWARP >= 2) ? NWARP / 2 : 1;
+    {
+        double *W = (double *)dsm, *zs = W + Nq;
+        unsigned char *pend = (unsigned char *)(zs + Nq);                      // [Nq] pending flags (8-byte aligned)
+        const double *z = S.P.f[F_Z];
+        for (int i = tid; i < N; i += TPB) { const double zi = z[i]; zs[i] = zi; W[i] = (i < nb) ? zi : 1.e6; }
+        for (int i = tid; i < Nq; i += TPB) pend[i] = (i >= nb && i < N) ? 1 : 0;   // every interior node starts pending
+        if (tid == 0) W[N] = 2.e6;                                              // the dummy neighbour of empty slots
     }
     __syncthreads();
+    const unsigned aW = s32(dsm), aZ = aW + 8u * (unsigned)Nq, aP = aZ + 8u * (unsigned)Nq;
+    const unsigned aL = aW + 17u * (unsigned)Nq + (unsigned)warp * 256u;       // [NWF][256] pending slots of this warp
+    const unsigned short *ngb16f = c.ngb16f;
     const double eps = c.eps, TH = c.TH;
-    constexpr int CHW = Smem::FB_WORDS;                        // bitmap words compacted per round
+    const int nlev = c.nlev;
+    const unsigned lt = (1u << lane) - 1u;
+    // slot s = 8 * lane + byte of this warp's 256 ids of a batch: id = base + ((lane >> 2) * NWF + warp) * 32 + (lane & 3) * 8 + byte
+    const int lane_off = ((lane >> 2) * NWF + warp) * 32 + (lane & 3) * 8;
+#ifdef BL_FILL_TRACE
+    // trace build only (tools/fill_trace.py): clocks of warps 0 and 5 along each round (whole-warp reads, lane 0 stores)
+    unsigned long long *trc = S.P.keys + 8 + (warp == 5 ? 8000 : 0);
+    int tri = 0;
+    const bool trw = (warp == 0 || warp == 5) && lane == 0;
+#define TRC(x) do { const long long v_ = (long long)(x); if (trw && tri < 7990) trc[tri] = (unsigned long long)v_; ++tri; } while (0)
+#else
+#define TRC(x) do { } while (0)
+#endif
     int change = 1;
     while (change) {
         int loc = 0;
-        for (int l = 0; l < c.nlev; ++l) {
-            const int n0 = nb + S.lev_off[l], n1 = nb + S.lev_off[l + 1];     // node id range of the level
-            const int wf = n0 >> 5, wl = (n1 - 1) >> 5;
-            for (int wbase = wf; wbase <= wl; wbase += CHW) {
-                // (a) warps 0..CHW/32-1: one word per lane -> count, prefix within the warp, consume the bits
-                if (warp < CHW / 32) {
-                    const int wi = wbase + tid;
-                    unsigned word = 0u;
-                    if (wi <= wl) {
-                        const int lo = wi * 32;
-                        unsigned m = 0xFFFFFFFFu;
-                        if (lo < n0) m &= ~((1u << (n0 - lo)) - 1u);
-                        if (lo + 32 > n1) m &= (1u << (n1 - lo)) - 1u;
-                        word = bits[wi] & m;
-                        if (word) atomicAnd(&bits[wi], ~word);
-                    }
-                    int inc = __popc(word);
-                    const int cnt = inc;
+        for (int l = 0; l < nlev; ++l) {
+            TRC(clock64());
+            if (warp < NWF) {
+                const int n0 = nb + S.lev_off[l], n1 = nb + S.lev_off[l + 1];     // node id range of the level
+#ifdef BL_FILL_TRACE
+                int offsum = 0;
+#endif
+                for (int base = n0 & ~7; base < n1; base += 256 * NWF) {
+                    const int k0 = base + lane_off;
+                    uint2 w2 = lds_v2(aP + (unsigned)min(k0, Nq - 8));
+                    if (k0 >= n1) w2 = make_uint2(0u, 0u);
+                    // ids outside [n0, n1) in the boundary words belong to other levels: not ours to take
+                    bool pb[8];
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                    S.fb_word[tid] = word;
-                    S.fb_pre[tid] = (unsigned short)(inc - cnt);
-                    if (lane == 31) S.fb_tot[warp] = inc;
+                    for (int q = 0; q < 8; ++q)
+                        pb[q] = (((q < 4 ? w2.x : w2.y) >> (8 * (q & 3))) & 0xFFu) != 0u && (unsigned)(k0 + q - n0) < (unsigned)(n1 - n0);
+                    unsigned mb[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) mb[q] = __ballot_sync(0xffffffffu, pb[q]);
+                    int off = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        sts_u8_if(pb[q], aP + (unsigned)(k0 + q), 0u);
+                        sts_u8_if(pb[q], aL + (unsigned)(off + __popc(mb[q] & lt)), (unsigned)(8 * lane + q));
+                        off += __popc(mb[q]);
+                    }
+                    __syncwarp();
+                    TRC(clock64());
+                    for (int i = lane; i < off; i += 32) {
+                        const int s = (int)lds_u8(aL + (unsigned)i);
+                        const int ln = s >> 3;
+                        fill_eval<KDT>(ngb16f, base + ((ln >> 2) * NWF + warp) * 32 + (ln & 3) * 8 + (s & 7), aW, aZ, aP, sea, eps, TH,
+                                       loc);
+                    }
+                    __syncwarp();
+#ifdef BL_FILL_TRACE
+                    offsum += off;
+#endif
                 }
-                __syncthreads();
-                // (a2) every thread expands one nibble of one word into the round's id list (8 threads per word)
-                int tot = 0, cum[CHW / 32];
-#pragma unroll
-                for (int q = 0; q < CHW / 32; ++q) { cum[q] = tot; tot += S.fb_tot[q]; }
-                if (tot == 0) { __syncthreads(); continue; }            // uniform: nothing pending in this round (fb_tot is reused)
-                for (int it = tid; it < CHW * 8; it += TPB) {
-                    const int wq = it >> 3, sub = it & 7;
-                    const unsigned word = S.fb_word[wq];
-                    unsigned nib = (word >> (4 * sub)) & 15u;
-                    if (nib) {
-                        int cq = 0;                                     // (a runtime index into cum[] would put it in local memory)
-#pragma unroll
-                        for (int u = 1; u < CHW / 32; ++u) if ((wq >> 5) >= u) cq = cum[u];
-                        int pos = cq + (int)S.fb_pre[wq] + __popc(word & ((1u << (4 * sub)) - 1u));
-                        const int base = (wbase + wq) * 32 + 4 * sub;
-                        if (nib & 1u) flist[pos++] = (unsigned short)base;
-                        if (nib & 2u) flist[pos++] = (unsigned short)(base + 1);
-                        if (nib & 4u) flist[pos++] = (unsigned short)(base + 2);
-                        if (nib & 8u) flist[pos] = (unsigned short)(base + 3);
-                    }
-                }
-                __syncthreads();
-                // (b) thread t takes the t-th pending node of the round
-                for (int t = tid; t < tot; t += TPB) {
-                    const int k = flist[t];
-                    const double wk = W[k], zk = zs[k];
-                    if (!(wk > zk)) continue;
-                    Ids<KDT> ids;
-                    load_ids<KDT>(c, k, ids);
-                    double hm[KDT];
-#pragma unroll
-                    for (int p = 0; p < KDT; ++p) hm[p] = (ids.get(p) != NONE16) ? W[ids.get(p)] : 2.e6;
-                    double hmin;
-                    if (KDT == 8) {      // min is exact: any association gives the same bits
-                        hmin = fmin(fmin(fmin(hm[0], hm[1]), fmin(hm[2], hm[3])), fmin(fmin(hm[4], hm[5]), fmin(hm[6], hm[7])));
-                    } else {
-                        hmin = 2.e6;
-#pragma unroll
-                        for (int p = 0; p < KDT; ++p) hmin = fmin(hmin, hm[p]);
-                    }
-                    hmin = fmin(hmin, 2.e6);
-                    const double he = hmin + eps;
-                    double nw = wk;
-                    if (zk >= he) nw = zk;
-                    else if (wk > he) {
-                        nw = he;
-                        if (zk >= sea) { if (nw - zk > TH) nw = zk + TH; else loc = 1; }
-                        else           { if (nw - sea > TH) nw = sea + TH; else loc = 1; }
-                    }
-                    if (nw != wk) {
-                        W[k] = nw;
-                        // wake only the neighbours this change can move: re-evaluating j alters W(j) only if
-                        // min_nb W + eps < W(j), and the neighbour that brings the minimum down below W(j) - eps is the
-                        // one that wakes j (hm[p] is W(j) now: other levels do not change during this pass)
-                        const double lim = nw + eps;
-#pragma unroll
-                        for (int p = 0; p < KDT; ++p) {
-                            const unsigned j = ids.get(p);
-                            if (j != NONE16 && (int)j >= nb && hm[p] > lim) atomicOr(&bits[j >> 5], 1u << (j & 31));
-                        }
-                    }
-                }
-                __syncthreads();
+#ifdef BL_FILL_TRACE
+                TRC(clock64());
+                TRC(offsum);
+#endif
             }
+            if (l + 1 < nlev) __syncthreads();
+#ifdef BL_FILL_TRACE
+            else __syncthreads();
+#endif
+            TRC(clock64());
         }
         change = __syncthreads_or(loc);
     }
+#ifdef BL_FILL_TRACE
+    if (trw) trc[-8 + (warp == 5 ? 1 : 0)] = (unsigned long long)tri;
+#endif
+#undef TRC
 }
 
 // ---- depression filling + receivers ---------------------------------------------------------------
@@ -330,6 +396,7 @@ template <int KDT>
 __device__ __noinline__ void links_stack(const DevConst &c, Smem &S, unsigned char *dsm, const int *rcvg, int *stack, int *pos,
                             int *baselist, int &nbase, bool filled, bool shuffle, unsigned long long seedstep)
 {
+    BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     unsigned *eu = (unsigned *)dsm;                                  // [2*Nq]
     unsigned short *r16 = (unsigned short *)(dsm + (size_t)8 * Nq);  // [Nq]
@@ -376,6 +443,7 @@ __device__ __noinline__ void links_stack(const DevConst &c, Smem &S, unsigned ch
         }
     }
     nbase = blk_compact(N, baselist, [&](int i) { return r16[i] == i; }, S);
+    if (tid == 0) { if (filled) S.nbase = nbase; else S.nbase1 = nbase; }     // read by the later phases (barriers follow)
     if (shuffle && nbase > 1) {
         int n2 = 1;
         while (n2 < nbase) n2 <<= 1;
@@ -424,8 +492,9 @@ __device__ __noinline__ void links_stack(const DevConst &c, Smem &S, unsigned ch
 }
 
 // ---- pit ids and volumes (FLOWalgo.f90:130-165) ------------------------------------------------------
-__device__ void basins(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1)
+__device__ __noinline__ void basins(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1)
 {
+    BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     unsigned short *root16 = (unsigned short *)dsm;          // [Nq]
     double *val = (double *)(dsm + (size_t)8 * Nq);          // [Nq]
@@ -484,9 +553,10 @@ __device__ inline int pit_walk16(const unsigned short *r16, const unsigned short
     }
 }
 
-__device__ void drainage(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1, double sea,
-                         int any_marine)
+__device__ __noinline__ void drainage(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1, double sea,
+                                      int any_marine)
 {
+    BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     unsigned short *r16 = (unsigned short *)dsm, *pid16 = r16 + Nq;
     const int *rcv = S.P.i[I_RCV], *pitID = S.P.i[I_PITID];
@@ -576,6 +646,7 @@ constexpr int DEPMAX = 2040;   // bucket offsets kept in static shared memory up
 // The same buckets serve the sediment routing of streampower().
 __device__ __noinline__ void discharge(const DevConst &c, Smem &S, unsigned char *dsm, double rain)
 {
+    BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     ScanSm sm = scan_layout(dsm, Nq);
     const unsigned short *lc16 = (const unsigned short *)S.P.i[I_LC], *ps16 = (const unsigned short *)S.P.i[I_PS];
@@ -646,8 +717,9 @@ __device__ __noinline__ void discharge(const DevConst &c, Smem &S, unsigned char
     for (int v = tid; v < N; v += TPB) Q[v] = sm.vals[v];
 }
 
-__device__ double flow_cfl(const DevConst &c, Smem &S, unsigned char *dsm, double erod)
+__device__ __noinline__ double flow_cfl(const DevConst &c, Smem &S, unsigned char *dsm, double erod)
 {
+    BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq;
     ScanSm sm = scan_layout(dsm, Nq);
     const double *W = S.P.f[F_FILLH];
@@ -669,9 +741,10 @@ __device__ double flow_cfl(const DevConst &c, Smem &S, unsigned char *dsm, doubl
 }
 
 // FLOWalgo.f90:583-1044 (see phase_streampower).  `first`: Q is still in sm.vals (straight after discharge).
-__device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, double erod, double sea, double dt,
-                            bool first, const int *base1, int nbase1)
+__device__ __noinline__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, double erod, double sea, double dt,
+                                         bool first, const int *base1, int nbase1)
 {
+    BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     ScanSm sm = scan_layout(dsm, Nq);
     const int *pitID = S.P.i[I_PITID], *stack = S.P.i[I_STACK], *pitDrain = S.P.i[I_PITDRAIN];
@@ -903,8 +976,9 @@ __device__ void streampower(const DevConst &c, Smem &S, unsigned char *dsm, doub
 // z / fresh-deposit thickness / rate / coefficient held in shared memory (33 bytes per node); the sub-step count is
 // data dependent (mindt guard), so the loop stays a block-wide sequence of gather pass + min + update.
 template <int KDT>
-__device__ void marine_diffusion(const DevConst &c, Smem &S, unsigned char *dsm, double sea, double timestep)
+__device__ __noinline__ void marine_diffusion(const DevConst &c, Smem &S, unsigned char *dsm, double sea, double timestep)
 {
+    BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     double *zs = (double *)dsm, *sd = zs + Nq, *dmv = sd + Nq, *cf = dmv + Nq;
     unsigned char *fls = (unsigned char *)(cf + Nq);
@@ -967,8 +1041,9 @@ __device__ void marine_diffusion(const DevConst &c, Smem &S, unsigned char *dsm,
 
 // buildFlux.py:193-195, :252-272, :292-315 (see phase_apply) with z staged in shared memory for the gather
 template <int KDT>
-__device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea, double timestep)
+__device__ __noinline__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea, double timestep)
 {
+    BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
     double *__restrict__ zs = (double *)dsm;
     double *__restrict__ cd = zs + Nq;
@@ -1067,44 +1142,53 @@ __device__ void apply(const DevConst &c, Smem &S, unsigned char *dsm, double sea
 }
 
 template <int KDT>
-__device__ void time_step(const DevConst &c, Smem &S, unsigned char *dsm, double &tNow, long long &step, double tStop,
-                          double rain, double erod, unsigned long long seed, double &last_dt)
+__device__ void time_step(const DevConst &c, Smem &S, unsigned char *dsm)
 {
     const int tid = threadIdx.x;
-    const double sea = sea_level(c, tNow);
-    long long *pc = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
-    long long t0 = clock64();
-#define TICK(i) do { if (tid == 0) { long long t1_ = clock64(); pc[i] += t1_ - t0; t0 = t1_; } } while (0)
-    int any_marine;
-    fill_sfd<KDT>(c, S, dsm, sea, any_marine);
-    if (tid == 0) S.ibuf[1] = any_marine;
-    TICK(0);
-    int nbase1, nbase;
-    links_stack<KDT>(c, S, dsm, S.P.i[I_RCV1], S.P.i[I_STACK1], S.P.i[I_POS1], S.P.i[I_LA], nbase1, false, false, 0ull);
-    TICK(2);
-    basins(c, S, dsm, S.P.i[I_LA], nbase1);
-    TICK(3);
-    links_stack<KDT>(c, S, dsm, S.P.i[I_RCV], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase, true, c.shuffle != 0,
-                     mix64(seed + (unsigned long long)step));
-    TICK(4);
-    drainage(c, S, dsm, S.P.i[I_LA], nbase1, sea, any_marine);
-    TICK(5);
-    discharge(c, S, dsm, rain);
-    TICK(6);
-    const double flowcfl = flow_cfl(c, S, dsm, erod);
-    double cfl = fmin(flowcfl, c.hill);
-    cfl = py2_floorish(cfl);
-    cfl = fmin(cfl, tStop - tNow);
-    cfl = fmax(c.minDT, cfl);
-    cfl = fmin(c.maxDT, cfl);
-    double newdt = cfl;
-    TICK(7);
-    streampower(c, S, dsm, erod, sea, newdt, true, S.P.i[I_LA], nbase1);
-    TICK(8);
+    if (tid == 0) { S.sea = sea_level(c, S.tNow); S.tick0 = clock64(); }
+    __syncthreads();
+    {
+        int any_marine;
+        fill_sfd<KDT>(c, S, dsm, S.sea, any_marine);
+        if (tid == 0) { S.ibuf[1] = any_marine; S.any_marine = any_marine; }
+    }
+    BL_TICK(0);
+    {
+        int nbase1;
+        links_stack<KDT>(c, S, dsm, S.P.i[I_RCV1], S.P.i[I_STACK1], S.P.i[I_POS1], S.P.i[I_LA], nbase1, false, false, 0ull);
+    }
+    BL_TICK(2);
+    basins(c, S, dsm, S.P.i[I_LA], S.nbase1);
+    BL_TICK(3);
+    {
+        int nbase;
+        links_stack<KDT>(c, S, dsm, S.P.i[I_RCV], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase, true, c.shuffle != 0,
+                         mix64(S.seed + (unsigned long long)S.step));
+    }
+    BL_TICK(4);
+    drainage(c, S, dsm, S.P.i[I_LA], S.nbase1, S.sea, S.any_marine);
+    BL_TICK(5);
+    discharge(c, S, dsm, S.rain);
+    BL_TICK(6);
+    {
+        const double flowcfl = flow_cfl(c, S, dsm, S.erod);
+        double cfl = fmin(flowcfl, c.hill);
+        cfl = py2_floorish(cfl);
+        cfl = fmin(cfl, S.tStop - S.tNow);
+        cfl = fmax(c.minDT, cfl);
+        cfl = fmin(c.maxDT, cfl);
+        if (tid == 0) { S.dbuf[2] = cfl; S.newdt = cfl; }
+        __syncthreads();
+    }
+    BL_TICK(7);
+    streampower(c, S, dsm, S.erod, S.sea, S.newdt, true, S.P.i[I_LA], S.nbase1);
+    BL_TICK(8);
     {
         // getid1 (FLOWalgo.f90:1047-1086): pitVol > 0 only at basin roots, so only those can qualify
         const double *cdepo = S.P.f[F_DEPO], *cero = S.P.f[F_ERO], *pitVol = S.P.f[F_PITVOL];
         const int *pitID = S.P.i[I_PITID], *alld = S.P.i[I_ALLDRAIN], *base1 = S.P.i[I_LA];
+        const int nbase1 = S.nbase1;
+        const double cfl = S.dbuf[2];
         int nb = 0;
         double minperc = 1.e300;
         for (int i = tid; i < nbase1; i += TPB) {
@@ -1116,20 +1200,21 @@ __device__ void time_step(const DevConst &c, Smem &S, unsigned char *dsm, double
             if (in1 && in2 && (c.flags[k] & 4)) { nb = 1; minperc = fmin(minperc, pitVol[k] / sumvol); }
         }
         nb = __syncthreads_or(nb);
+        double newdt = cfl;
         if (nb) { minperc = blk_min(minperc, S); newdt = cfl * minperc; }
         newdt = py2_floorish(newdt);
         newdt = fmax(c.minDT, newdt);
-        if (newdt < cfl) streampower(c, S, dsm, erod, sea, newdt, false, S.P.i[I_LA], nbase1);
+        if (tid == 0) S.newdt = newdt;
+        __syncthreads();
+        if (newdt < cfl) streampower(c, S, dsm, S.erod, S.sea, S.newdt, false, S.P.i[I_LA], S.nbase1);
     }
-    TICK(9);
-    phase_erodep(c, S, sea);
-    TICK(10);
-    apply<KDT>(c, S, dsm, sea, newdt);
-    TICK(11);
-#undef TICK
-    tNow += newdt;
-    last_dt = newdt;
-    ++step;
+    BL_TICK(9);
+    phase_erodep(c, S, S.sea);
+    BL_TICK(10);
+    apply<KDT>(c, S, dsm, S.sea, S.newdt);
+    BL_TICK(11);
+    if (tid == 0) { S.tNow += S.newdt; S.last_dt = S.newdt; S.step += 1; }
+    __syncthreads();
 }
 
 } // namespace fast

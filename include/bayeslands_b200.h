@@ -92,7 +92,7 @@ typedef struct {
     int32_t npts;              /* erdp points (<= BL_NPTS_MAX) */
     const int32_t *pts_cell;   /* [npts] flat grid cell index row*nx+col (bl_mcmc.py:156-157) */
     /* engine options (all 0 = defaults).  Nothing in the library reads environment variables. */
-    int32_t opt_tpb;           /* threads per CTA: 0 automatic, or 256 / 512 / 1024 */
+    int32_t opt_tpb;           /* threads per CTA: 0 automatic, or 256 / 512 / 768 / 1024 */
     int32_t opt_flags;         /* BL_OPT_* bits */
     int32_t opt_grid_group;    /* lattice engine: proposals per fill group (0 = 64) */
     int32_t opt_debug;         /* timing experiments only */

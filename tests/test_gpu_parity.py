@@ -156,7 +156,7 @@ def test_crater_generic_path_bit_exact(crater_fast):
                 assert np.array_equal(eng.field(f, b), getattr(om, f)), (step, b, f)
 
 
-@pytest.mark.parametrize("tpb", [256, 512, 1024])
+@pytest.mark.parametrize("tpb", [256, 512, 768, 1024])
 def test_crater_every_cta_size_bit_exact(crater_fast, tpb):
     """The device code is instantiated once per CTA size (csrc/bl_v256.cu / bl_v512.cu / bl_v1024.cu); `opt_tpb` forces
     one.  Block-level primitives (scans, ordered compaction, warp ballots) must give the same bits at every size."""

@@ -9,8 +9,11 @@ import torch
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "crater_fast"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 148
+TPB = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+DBG = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 d, inp, m, simtime, rl, el, coords, likl_sed = bench.load_config(cfg)
-eng = Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=coords, sealevel=d["sealevel"] if "sealevel" in d else None)
+eng = Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=coords, sealevel=d["sealevel"] if "sealevel" in d else None,
+             tpb=TPB, debug=DBG)
 r, e, s = bench.proposals(0, 0, B, rl, el)
 from bayeslands_b200 import hostparams
 for it in range(2):
@@ -24,7 +27,7 @@ for it in range(2):
 pc = eng.phase_cycles().astype(np.float64)
 steps = eng.scalars()["steps"]
 tot = pc.sum(1)
-print("config", cfg, "B", B, "wall ms", dt * 1e3, "mean steps", steps.mean())
+print("config", cfg, "B", B, "tpb", TPB, "debug", DBG, "evals/s %.1f" % (B / dt), "wall ms", dt * 1e3, "mean steps", steps.mean())
 print("mean cycles/step per phase:")
 for i, nm in enumerate(_lib.PHASES):
     print("  %-12s %10.0f cyc  %5.1f%%" % (nm, (pc[:, i] / steps).mean(), 100 * pc[:, i].sum() / tot.sum()))
@@ -36,3 +39,7 @@ names = {16: "erodep pass1+compact", 17: "erodep small basins", 18: "erodep larg
          21: "#land pits"}
 for i in sorted(names):
     print("  sub %-32s %10.1f /step" % (names[i], (pc[:, i] / steps).mean()))
+
+if DBG & 4:
+    print("  fill diag (warp 0, cyc/step): scan %.0f, eval %.0f, barrier %.0f; rounds/step %.1f, evals/step (CTA) %.0f, eval passes/step (warp 0) %.1f"
+          % tuple((pc[:, i] / steps).mean() for i in (22, 23, 24, 25, 26, 27)))
