@@ -59,6 +59,8 @@ class BlLattice(C.Structure):
 
 EXPORTS = ("bl_last_error", "bl_version", "bl_workspace_bytes", "bl_ctx_create", "bl_ctx_destroy", "bl_reset",
            "bl_run", "bl_step", "bl_get_field", "bl_get_scalars", "bl_get_phase_cycles", "bl_launch_count",
+           "bl_fill", "bl_sfd", "bl_stack", "bl_discharge", "bl_basins", "bl_drainage", "bl_streampower", "bl_diffuse",
+           "bl_interp",
            "bl_grid_workspace_bytes", "bl_grid_create", "bl_grid_destroy", "bl_grid_reset", "bl_grid_run",
            "bl_grid_step", "bl_grid_get_field", "bl_grid_get_scalars", "bl_grid_launch_count")
 
@@ -97,6 +99,16 @@ def load():
     L.bl_get_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bl_launch_count.restype = C.c_int64
     L.bl_launch_count.argtypes = [C.c_void_p]
+    vp, dbl, i32, u64, i64 = C.c_void_p, C.c_double, C.c_int, C.c_uint64, C.c_int64
+    L.bl_fill.argtypes = [vp, vp, dbl, vp, vp]
+    L.bl_sfd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bl_stack.argtypes = [vp, vp, i32, u64, i64, vp, vp, vp, vp]
+    L.bl_discharge.argtypes = [vp, vp, dbl, vp, vp]
+    L.bl_basins.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.bl_drainage.argtypes = [vp, vp, vp, vp, vp, dbl, vp, vp, vp]
+    L.bl_streampower.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, dbl, i32, u64, i64, vp, vp, vp]
+    L.bl_diffuse.argtypes = [vp, vp, vp, vp]
+    L.bl_interp.argtypes = [vp, vp, vp, vp]
     L.bl_grid_workspace_bytes.restype = C.c_size_t
     L.bl_grid_workspace_bytes.argtypes = [C.POINTER(BlLattice), C.c_int, C.c_int]
     L.bl_grid_create.argtypes = [C.POINTER(BlLattice), C.POINTER(BlParams), C.c_int, C.c_int, C.c_void_p, C.c_size_t,

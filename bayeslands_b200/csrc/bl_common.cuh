@@ -123,6 +123,20 @@ struct RunArgs {
     int nck, single_step;
 };
 
+// arguments of one per-stage launch (bl_stage_kernel in bl_device.cuh)
+enum { BL_STAGE_FILL = 1, BL_STAGE_SFD, BL_STAGE_STACK, BL_STAGE_DISCHARGE, BL_STAGE_BASINS, BL_STAGE_DRAINAGE,
+       BL_STAGE_STREAMPOWER, BL_STAGE_DIFFUSE, BL_STAGE_INTERP };
+struct StageArgs {
+    int stage, shuffle;
+    double sea, rain, erod, dt;
+    unsigned long long seed;
+    long long step;
+    const double *q_in;      // streampower: caller's discharge
+    double *diff_out;        // diffuse: raw flux
+    const double *v_in;      // interp: nodal values
+    double *grid_out;        // interp: [G]
+};
+
 // per-CTA-size device TUs (bl_v1024.cu, bl_v512.cu, bl_v256.cu): launchers with external linkage
 #define BL_DECL_VARIANT(NS)                                                                                              \
     cudaError_t bl_launch_run_##NS(int KDT, const DevConst &c, int B, int dyn, cudaStream_t st, const RunArgs &a);       \
@@ -130,6 +144,8 @@ struct RunArgs {
                                      const unsigned long long *seed, double tStart);                                     \
     cudaError_t bl_func_attr_##NS(int KDT, cudaFuncAttributes *attr);
 BL_DECL_VARIANT(v1024)
+cudaError_t bl_launch_stage_v1024(int KDT, const DevConst &c, int dyn, cudaStream_t st, const StageArgs &a);
+cudaError_t bl_launch_stage_v256(int KDT, const DevConst &c, int dyn, cudaStream_t st, const StageArgs &a);
 BL_DECL_VARIANT(v768)
 BL_DECL_VARIANT(v512)
 BL_DECL_VARIANT(v256)

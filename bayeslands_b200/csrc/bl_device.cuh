@@ -25,6 +25,7 @@ struct Smem {
     long long step, tick0;
     unsigned long long seed;
     int nbase1, nbase, any_marine;
+    double *diff_out;          // per-stage entry point bl_diffuse: raw diffusion flux of sfd.diffusion (null in a run)
 };
 
 // diagnostics: thread 0 adds the cycles since the previous tick to slot i of this CTA's phase_cyc row (slots >= 16)
@@ -1313,6 +1314,7 @@ __device__ void phase_apply(const DevConst &c, Smem &S, double sea, double times
         const double ac = (area > 0.) ? 1. / area : 0.;
         double coeff = ac * ((z[g] >= sea) ? c.CDa : c.CDm);
         if (!(fg & 2)) { coeff = 0.; acc = 0.; }
+        if (S.diff_out) S.diff_out[g] = acc;
         cd[g] = coeff * acc * timestep;
     }
     __syncthreads();
@@ -1434,6 +1436,7 @@ bl_run_kernel(const DevConst cpar, int nstops, const double *__restrict__ stops,
         prop_init(S.P, cpar.prop_base + (size_t)b * cpar.prop_stride, cpar.N);
         S.dsm = (KDT > 0) ? dsm : nullptr;
         S.dsm_bytes = (KDT > 0) ? dyn_bytes : 0;
+        S.diff_out = nullptr;
     }
     __syncthreads();
     const DevConst &c = S.c;
@@ -1490,6 +1493,149 @@ bl_run_kernel(const DevConst cpar, int nstops, const double *__restrict__ stops,
     }
     if (tid == 0) { c.tnow[b] = S.tNow; c.steps[b] = S.step; c.lastdt[b] = S.last_dt; }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Per-stage entry points (bl_fill, bl_sfd, bl_stack, ... in bayeslands_b200.h): ONE routine of the time
+// step on proposal slot 0, with the same device functions the fused step uses (shared-memory path when the context
+// selected it, generic path otherwise).  The host copies the caller's arrays into / out of the slot.
+// ------------------------------------------------------------------------------------------------
+#ifdef BL_WITH_STAGE
+template <int KDT>
+__global__ void __launch_bounds__(TPB, BL_MINB)
+bl_stage_kernel(const DevConst cpar, const StageArgs a, int dyn_bytes)
+{
+    __shared__ Smem S;
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        S.c = cpar;
+        prop_init(S.P, cpar.prop_base, cpar.N);
+        S.dsm = (KDT > 0) ? dsm : nullptr;
+        S.dsm_bytes = (KDT > 0) ? dyn_bytes : 0;
+        S.diff_out = nullptr;
+        S.sea = a.sea; S.rain = a.rain; S.erod = a.erod; S.tNow = 0.; S.tStop = 0.; S.step = a.step; S.seed = a.seed;
+        S.tick0 = clock64();
+    }
+    __syncthreads();
+    const DevConst &c = S.c;
+    for (int i = tid; i <= c.nlev && i <= LEVMAX; i += TPB) S.lev_off[i] = c.lev_off[i];
+    if (tid < 8) S.ibuf[tid] = 0;
+    __syncthreads();
+    const int N = c.N;
+    constexpr int K = (KDT > 0) ? KDT : 8;
+    const double *z = S.P.f[F_Z], *W = S.P.f[F_FILLH];
+    // helpers: "some node lies under the sea" (S.ibuf[1]) and the real-surface base list = {i : pitID[i] == i}
+    auto any_marine = [&]() { int m = 0; for (int k = tid; k < N; k += TPB) m |= (W[k] < a.sea); return __syncthreads_or(m); };
+    switch (a.stage) {
+        case BL_STAGE_FILL: {                      // pdstack.pitfilling(elev, 0, sealevel) -> fillH (+ receivers on the fast path)
+            if (KDT > 0) { int am; fast::fill_sfd<K>(c, S, dsm, a.sea, am); }
+            else phase_fill(c, S, a.sea);
+            break;
+        }
+        case BL_STAGE_SFD: {                       // sfd.directions(fillH, elev) + sfd.directions_base(elev) -> rcv, rcv1, maxh
+            if (KDT > 0) {
+                double *Ws = (double *)dsm, *zs = Ws + c.Nq;
+                for (int i = tid; i < N; i += TPB) { Ws[i] = W[i]; zs[i] = z[i]; }
+                __syncthreads();
+                int am;
+                fast::fill_receivers<K>(c, S, dsm, a.sea, am);
+            } else phase_sfd(c, S);
+            __syncthreads();
+            // pyMaxDep (sfd.c:88-90, :109): largest rise to a neighbour; not used by the path (slp_cr = 0), stage output only
+            double *maxdep = S.P.f[F_CAPH];
+            for (int g = tid; g < N; g += TPB) {
+                double dd = 0.;
+                for (int p = 0; p < c.KD; ++p) {
+                    const int j = c.ngb[(size_t)p * N + g];
+                    if (j < 0) break;
+                    const double dh = z[j] - z[g];
+                    if (dh > dd) dd = dh;
+                }
+                maxdep[g] = dd;
+            }
+            break;
+        }
+        case BL_STAGE_STACK: {                     // fstack.build(base, receivers, delta) -> stack (bases ascending or shuffled)
+            int nbase;
+            const unsigned long long ss = mix64(a.seed + (unsigned long long)a.step);
+            if (KDT > 0) fast::links_stack<K>(c, S, dsm, S.P.i[I_RCV], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase, true, a.shuffle != 0, ss);
+            else {
+                tree_links(c, S.P.i[I_RCV], S.P.i[I_FC], S.P.i[I_SUCC], S.P.i[I_LC], S.P.i[I_PS], S.P.i[I_CNT]);
+                phase_stack(c, S, S.P.i[I_RCV], S.P.i[I_FC], S.P.i[I_SUCC], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase, a.shuffle != 0, ss);
+            }
+            if (tid == 0) S.P.i[I_MARK][0] = nbase;
+            break;
+        }
+        case BL_STAGE_DISCHARGE: {                 // flowcompute.discharge(stack, receivers, elev, area * rain) -> Q
+            if (KDT > 0) {
+                int nbase;
+                fast::links_stack<K>(c, S, dsm, S.P.i[I_RCV], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase, true, false, 0ull);
+                fast::discharge(c, S, dsm, a.rain);
+            } else {
+                tree_links(c, S.P.i[I_RCV], S.P.i[I_FC], S.P.i[I_SUCC], S.P.i[I_LC], S.P.i[I_PS], S.P.i[I_CNT]);
+                phase_discharge(c, S, a.rain);
+            }
+            break;
+        }
+        case BL_STAGE_BASINS: {                    // flowcompute.basinparameters(stack1, receivers1, elev, fillH, area) -> pitID, pitVolume
+            int nbase1;
+            if (KDT > 0) {
+                fast::links_stack<K>(c, S, dsm, S.P.i[I_RCV1], S.P.i[I_STACK1], S.P.i[I_POS1], S.P.i[I_LA], nbase1, false, false, 0ull);
+                fast::basins(c, S, dsm, S.P.i[I_LA], nbase1);
+            } else {
+                tree_links(c, S.P.i[I_RCV1], S.P.i[I_FC], S.P.i[I_NS], nullptr, nullptr, nullptr);
+                phase_stack(c, S, S.P.i[I_RCV1], S.P.i[I_FC], S.P.i[I_NS], S.P.i[I_STACK1], S.P.i[I_POS1], S.P.i[I_LA], nbase1, false, 0ull);
+                phase_basins(c, S, S.P.i[I_LA], nbase1);
+            }
+            break;
+        }
+        case BL_STAGE_DRAINAGE: {                  // flowcompute.basindrainage / basindrainageall -> pitDrain, allDrain
+            const int *pitID = S.P.i[I_PITID];
+            const int nbase1 = blk_compact(N, S.P.i[I_LA], [&](int i) { return pitID[i] == i; }, S);
+            const int am = any_marine();
+            if (KDT > 0) fast::drainage(c, S, dsm, S.P.i[I_LA], nbase1, a.sea, am);
+            else phase_drainage(c, S, S.P.i[I_LA], nbase1, a.sea);
+            break;
+        }
+        case BL_STAGE_STREAMPOWER: {               // flowcompute.streampower(stack, receivers, pitID, pitVolume, pitDrain, ...) -> cdepo, cero
+            const int *pitID = S.P.i[I_PITID];
+            const int nbase1 = blk_compact(N, S.P.i[I_LA], [&](int i) { return pitID[i] == i; }, S);
+            const int am = any_marine();
+            if (tid == 0) S.ibuf[1] = am;
+            int nbase;
+            const unsigned long long ss = mix64(a.seed + (unsigned long long)a.step);
+            if (KDT > 0) {
+                fast::links_stack<K>(c, S, dsm, S.P.i[I_RCV], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase, true, a.shuffle != 0, ss);
+                fast::discharge(c, S, dsm, 0.);     // builds the depth buckets of the routing; its Q is replaced by the caller's
+                __syncthreads();
+                for (int k = tid; k < N; k += TPB) S.P.f[F_Q][k] = a.q_in[k];
+                __syncthreads();
+                fast::streampower(c, S, dsm, a.erod, a.sea, a.dt, false, S.P.i[I_LA], nbase1);
+            } else {
+                tree_links(c, S.P.i[I_RCV], S.P.i[I_FC], S.P.i[I_SUCC], S.P.i[I_LC], S.P.i[I_PS], S.P.i[I_CNT]);
+                phase_stack(c, S, S.P.i[I_RCV], S.P.i[I_FC], S.P.i[I_SUCC], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase, a.shuffle != 0, ss);
+                for (int k = tid; k < N; k += TPB) S.P.f[F_Q][k] = a.q_in[k];
+                __syncthreads();
+                phase_streampower(c, S, a.erod, a.sea, a.dt);
+            }
+            break;
+        }
+        case BL_STAGE_DIFFUSE: {                   // sfd.diffusion(elev, borders2, ...) -> raw flux (hook in apply / phase_apply)
+            for (int k = tid; k < N; k += TPB) S.P.f[F_SEDFLUX][k] = 0.;
+            if (tid == 0) S.diff_out = a.diff_out;
+            __syncthreads();
+            if (KDT > 0) fast::apply<K>(c, S, dsm, a.sea, 0.);
+            else phase_apply(c, S, a.sea, 0.);
+            break;
+        }
+        case BL_STAGE_INTERP: {                    // bl_mcmc.interpolateArray on the mesh-constant k = 3 table
+            for (int g = tid; g < c.G; g += TPB) a.grid_out[g] = interp_cell(c, a.v_in, g);
+            break;
+        }
+        default: break;
+    }
+}
+#endif
 
 __global__ void bl_reset_kernel(const DevConst c, const double *rain, const double *erod,
                                 const unsigned long long *seed, double tStart)

@@ -506,5 +506,203 @@ extern "C" int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst, void *stream)
     return BL_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// per-stage entry points on caller-owned device arrays: proposal slot 0 is the scratch landscape
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Slot0 {
+    double *f[NF64];
+    int *i[NI32];
+};
+Slot0 slot0(const bl_ctx *ctx)
+{
+    Slot0 s;
+    const size_t Np = np_of(ctx->c.N);
+    double *d = (double *)ctx->c.prop_base;
+    for (int k = 0; k < NF64; ++k) s.f[k] = d + (size_t)k * Np;
+    unsigned long long *u = (unsigned long long *)(d + (size_t)NF64 * Np);
+    int *ip = (int *)(u + 4 * Np + keys_len(ctx->c.N));
+    for (int k = 0; k < NI32; ++k) s.i[k] = ip + (size_t)k * Np;
+    return s;
+}
+int stage_launch(bl_ctx *ctx, const StageArgs &a, cudaStream_t st)
+{
+    // the 256-thread unit serves the contexts that run 256-thread CTAs, the 1024-thread unit all others
+    if (ctx->tpb == 256) CUDA_OK(bl_launch_stage_v256(ctx->c.KDT, ctx->c, ctx->dyn, st, a));
+    else {
+        int dyn = ctx->dyn;
+        if (ctx->c.KDT && ctx->tpb != 1024) {      // dyn_max was derived for another unit's static shared memory
+            cudaFuncAttributes fa;
+            memset(&fa, 0, sizeof(fa));
+            int optin = 0;
+            CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+            CUDA_OK(bl_func_attr_v1024(ctx->c.KDT, &fa));
+            dyn = std::min(dyn, (optin - (int)fa.sharedSizeBytes) / 1024 * 1024);
+        }
+        CUDA_OK(bl_launch_stage_v1024(ctx->c.KDT, ctx->c, dyn, st, a));
+    }
+    ctx->launches++;
+    return BL_OK;
+}
+StageArgs stage_args(int stage)
+{
+    StageArgs a;
+    memset(&a, 0, sizeof(a));
+    a.stage = stage;
+    a.sea = -1.e6;
+    return a;
+}
+#define D2D(dst, src, bytes) CUDA_OK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToDevice, st))
+#define STAGE_PROLOGUE(name)                                                                 \
+    if (!ctx) { g_err = name ": null context"; return BL_ERR_ARG; }                          \
+    CUDA_OK(cudaSetDevice(ctx->device));                                                     \
+    cudaStream_t st = (cudaStream_t)stream;                                                  \
+    const size_t N = (size_t)ctx->c.N;                                                       \
+    Slot0 s = slot0(ctx);                                                                    \
+    (void)N; (void)s
+} // namespace
+
+extern "C" int bl_fill(bl_ctx *ctx, const double *elev, double sealevel, double *fillH, void *stream)
+{
+    STAGE_PROLOGUE("bl_fill");
+    if (!elev || !fillH) { g_err = "bl_fill: null argument"; return BL_ERR_ARG; }
+    D2D(s.f[F_Z], elev, N * 8);
+    StageArgs a = stage_args(BL_STAGE_FILL);
+    a.sea = sealevel;
+    if (int rc = stage_launch(ctx, a, st)) return rc;
+    D2D(fillH, s.f[F_FILLH], N * 8);
+    return BL_OK;
+}
+
+extern "C" int bl_sfd(bl_ctx *ctx, const double *fillH, const double *elev, int32_t *base, int32_t *rcv, double *maxh,
+                      double *maxdep, void *stream)
+{
+    STAGE_PROLOGUE("bl_sfd");
+    if (!elev || !rcv) { g_err = "bl_sfd: null argument"; return BL_ERR_ARG; }
+    D2D(s.f[F_Z], elev, N * 8);
+    D2D(s.f[F_FILLH], fillH ? fillH : elev, N * 8);
+    StageArgs a = stage_args(BL_STAGE_SFD);
+    if (int rc = stage_launch(ctx, a, st)) return rc;
+    // receivers on the first array given: fillH (sfd.directions) or, without it, elev (sfd.directions_base)
+    D2D(rcv, fillH ? s.i[I_RCV] : s.i[I_RCV1], N * 4);
+    if (maxh) D2D(maxh, s.f[F_MAXH], N * 8);
+    if (maxdep) D2D(maxdep, s.f[F_CAPH], N * 8);
+    if (base) {
+        // pyBase: the self-receivers, -1 elsewhere (sfd.c:99-101)
+        std::vector<int> h(N);
+        CUDA_OK(cudaMemcpyAsync(h.data(), fillH ? s.i[I_RCV] : s.i[I_RCV1], N * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < N; ++i) h[i] = (h[i] == (int)i) ? (int)i : -1;
+        CUDA_OK(cudaMemcpyAsync(base, h.data(), N * 4, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    }
+    return BL_OK;
+}
+
+extern "C" int bl_stack(bl_ctx *ctx, const int32_t *rcv, int shuffle, uint64_t seed, int64_t step, int32_t *stack,
+                        int32_t *base_out, int32_t *nbase_out, void *stream)
+{
+    STAGE_PROLOGUE("bl_stack");
+    if (!rcv || !stack) { g_err = "bl_stack: null argument"; return BL_ERR_ARG; }
+    D2D(s.i[I_RCV], rcv, N * 4);
+    StageArgs a = stage_args(BL_STAGE_STACK);
+    a.shuffle = shuffle; a.seed = seed; a.step = step;
+    if (int rc = stage_launch(ctx, a, st)) return rc;
+    D2D(stack, s.i[I_STACK], N * 4);
+    if (base_out) D2D(base_out, s.i[I_LB], N * 4);
+    if (nbase_out) D2D(nbase_out, s.i[I_MARK], 4);
+    return BL_OK;
+}
+
+extern "C" int bl_discharge(bl_ctx *ctx, const int32_t *rcv, double rain, double *Q, void *stream)
+{
+    STAGE_PROLOGUE("bl_discharge");
+    if (!rcv || !Q) { g_err = "bl_discharge: null argument"; return BL_ERR_ARG; }
+    D2D(s.i[I_RCV], rcv, N * 4);
+    StageArgs a = stage_args(BL_STAGE_DISCHARGE);
+    a.rain = rain;
+    if (int rc = stage_launch(ctx, a, st)) return rc;
+    D2D(Q, s.f[F_Q], N * 8);
+    return BL_OK;
+}
+
+extern "C" int bl_basins(bl_ctx *ctx, const int32_t *rcv1, const double *elev, const double *fillH, int32_t *pitID,
+                         double *pitVol, void *stream)
+{
+    STAGE_PROLOGUE("bl_basins");
+    if (!rcv1 || !elev || !fillH || !pitID || !pitVol) { g_err = "bl_basins: null argument"; return BL_ERR_ARG; }
+    D2D(s.i[I_RCV1], rcv1, N * 4);
+    D2D(s.f[F_Z], elev, N * 8);
+    D2D(s.f[F_FILLH], fillH, N * 8);
+    StageArgs a = stage_args(BL_STAGE_BASINS);
+    if (int rc = stage_launch(ctx, a, st)) return rc;
+    D2D(pitID, s.i[I_PITID], N * 4);
+    D2D(pitVol, s.f[F_PITVOL], N * 8);
+    return BL_OK;
+}
+
+extern "C" int bl_drainage(bl_ctx *ctx, const int32_t *pitID, const double *pitVol, const int32_t *rcv, const double *fillH,
+                           double sealevel, int32_t *pitDrain, int32_t *allDrain, void *stream)
+{
+    STAGE_PROLOGUE("bl_drainage");
+    if (!pitID || !pitVol || !rcv || !fillH || !pitDrain || !allDrain) { g_err = "bl_drainage: null argument"; return BL_ERR_ARG; }
+    D2D(s.i[I_PITID], pitID, N * 4);
+    D2D(s.f[F_PITVOL], pitVol, N * 8);
+    D2D(s.i[I_RCV], rcv, N * 4);
+    D2D(s.f[F_FILLH], fillH, N * 8);
+    StageArgs a = stage_args(BL_STAGE_DRAINAGE);
+    a.sea = sealevel;
+    if (int rc = stage_launch(ctx, a, st)) return rc;
+    D2D(pitDrain, s.i[I_PITDRAIN], N * 4);
+    D2D(allDrain, s.i[I_ALLDRAIN], N * 4);
+    return BL_OK;
+}
+
+extern "C" int bl_streampower(bl_ctx *ctx, const int32_t *rcv, const int32_t *pitID, const double *pitVol,
+                              const int32_t *pitDrain, const double *maxh, const double *Q, const double *fillH,
+                              const double *elev, double erod, double sealevel, double dt, int shuffle, uint64_t seed,
+                              int64_t step, double *depo, double *ero, void *stream)
+{
+    STAGE_PROLOGUE("bl_streampower");
+    if (!rcv || !pitID || !pitVol || !pitDrain || !maxh || !Q || !fillH || !elev || !depo || !ero) {
+        g_err = "bl_streampower: null argument"; return BL_ERR_ARG;
+    }
+    D2D(s.i[I_RCV], rcv, N * 4);
+    D2D(s.i[I_PITID], pitID, N * 4);
+    D2D(s.f[F_PITVOL], pitVol, N * 8);
+    D2D(s.i[I_PITDRAIN], pitDrain, N * 4);
+    D2D(s.f[F_MAXH], maxh, N * 8);
+    D2D(s.f[F_FILLH], fillH, N * 8);
+    D2D(s.f[F_Z], elev, N * 8);
+    StageArgs a = stage_args(BL_STAGE_STREAMPOWER);
+    a.erod = erod; a.sea = sealevel; a.dt = dt; a.shuffle = shuffle; a.seed = seed; a.step = step; a.q_in = Q;
+    if (int rc = stage_launch(ctx, a, st)) return rc;
+    D2D(depo, s.f[F_DEPO], N * 8);
+    D2D(ero, s.f[F_ERO], N * 8);
+    return BL_OK;
+}
+
+extern "C" int bl_diffuse(bl_ctx *ctx, const double *elev, double *diff, void *stream)
+{
+    STAGE_PROLOGUE("bl_diffuse");
+    if (!elev || !diff) { g_err = "bl_diffuse: null argument"; return BL_ERR_ARG; }
+    D2D(s.f[F_Z], elev, N * 8);
+    CUDA_OK(cudaMemsetAsync(s.f[F_CUMDIFF], 0, N * 8, st));
+    CUDA_OK(cudaMemsetAsync(s.f[F_CUMHILL], 0, N * 8, st));
+    StageArgs a = stage_args(BL_STAGE_DIFFUSE);
+    a.diff_out = diff;
+    return stage_launch(ctx, a, st);
+}
+
+extern "C" int bl_interp(bl_ctx *ctx, const double *v, double *grid, void *stream)
+{
+    STAGE_PROLOGUE("bl_interp");
+    if (!v || !grid || ctx->c.G <= 0) { g_err = "bl_interp: null argument or no grid table"; return BL_ERR_ARG; }
+    StageArgs a = stage_args(BL_STAGE_INTERP);
+    a.v_in = v; a.grid_out = grid;
+    return stage_launch(ctx, a, st);
+}
+
 extern "C" int64_t bl_launch_count(const bl_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

@@ -1112,6 +1112,7 @@ __device__ __noinline__ void apply(const DevConst &c, Smem &S, unsigned char *ds
         const double ac = (area > 0.) ? 1. / area : 0.;
         double coeff = ac * ((zg >= sea) ? c.CDa : c.CDm);
         if (!(fg & 2)) { coeff = 0.; acc = 0.; }
+        if (S.diff_out) S.diff_out[g] = acc;
         const double d = coeff * acc * timestep;
         cd[g] = d;
         // the cumulative arrays take the diffusion term here (same thread that added sedflux to cumdiff[g] above)

@@ -34,6 +34,28 @@ cudaError_t BL_CAT(bl_launch_run_, BL_NS)(int KDT, const DevConst &c, int B, int
     return cudaGetLastError();
 }
 
+#ifdef BL_WITH_STAGE
+cudaError_t BL_CAT(bl_launch_stage_, BL_NS)(int KDT, const DevConst &c, int dyn, cudaStream_t st, const StageArgs &a)
+{
+#define LAUNCH(K, DYN)                                                                                                  \
+    do {                                                                                                                \
+        if (DYN) {                                                                                                      \
+            cudaError_t e = cudaFuncSetAttribute(BL_NS::bl_stage_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN); \
+            if (e != cudaSuccess) return e;                                                                             \
+        }                                                                                                               \
+        BL_NS::bl_stage_kernel<K><<<1, BL_TPB, DYN, st>>>(c, a, DYN);                                                   \
+    } while (0)
+    switch (KDT) {
+        case 8: LAUNCH(8, dyn); break;
+        case 12: LAUNCH(12, dyn); break;
+        case 20: LAUNCH(20, dyn); break;
+        default: LAUNCH(0, 0); break;
+    }
+#undef LAUNCH
+    return cudaGetLastError();
+}
+#endif
+
 cudaError_t BL_CAT(bl_launch_reset_, BL_NS)(const DevConst &c, int B, cudaStream_t st, const double *rain, const double *erod,
                                             const unsigned long long *seed, double tStart)
 {

@@ -187,6 +187,89 @@ class Engine:
         """Exactly one time step for every proposal (per-stage parity entry point)."""
         _lib.check(self.L.bl_step(self.ctx, float(tStop), self._stream()))
 
+    # ---- per-stage entry points (SURVEY.md 8b): caller arrays in, fresh arrays out, like the f2py routines ----------
+    def _dev(self, a, dt):
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(self.tdev)
+
+    def _ptr(self, t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def pitfilling(self, elev, sealevel):
+        """`PDalgo.pdstack.pitfilling(elev, 0, sealevel)` (elevationTIN.py:304) -> fillH."""
+        z = self._dev(elev, torch.float64); out = torch.empty_like(z)
+        _lib.check(self.L.bl_fill(self.ctx, self._ptr(z), float(sealevel), self._ptr(out), self._stream()))
+        return out.cpu().numpy()
+
+    def directions(self, fillH, elev):
+        """`sfd.directions(fillH, elev, ...)` (flowNetwork.py:310) -> base, receivers, maxh, maxdep."""
+        w = self._dev(fillH, torch.float64); z = self._dev(elev, torch.float64)
+        base = torch.empty(self.N, dtype=torch.int32, device=self.tdev); rcv = torch.empty_like(base)
+        maxh = torch.empty_like(z); maxdep = torch.empty_like(z)
+        _lib.check(self.L.bl_sfd(self.ctx, self._ptr(w), self._ptr(z), self._ptr(base), self._ptr(rcv), self._ptr(maxh),
+                                 self._ptr(maxdep), self._stream()))
+        return base.cpu().numpy(), rcv.cpu().numpy(), maxh.cpu().numpy(), maxdep.cpu().numpy()
+
+    def directions_base(self, elev):
+        """`sfd.directions_base(elev, ...)` (flowNetwork.py:298) -> base1, receivers1."""
+        z = self._dev(elev, torch.float64)
+        base = torch.empty(self.N, dtype=torch.int32, device=self.tdev); rcv = torch.empty_like(base)
+        _lib.check(self.L.bl_sfd(self.ctx, None, self._ptr(z), self._ptr(base), self._ptr(rcv), None, None, self._stream()))
+        return base.cpu().numpy(), rcv.cpu().numpy()
+
+    def stack_build(self, receivers, shuffle=0, seed=0, step=0):
+        """`FLWnetwork.fstack.build` (flowNetwork.py:393) -> stack, ordered bases."""
+        r = self._dev(receivers, torch.int32)
+        stack = torch.empty_like(r); base = torch.empty_like(r); nb = torch.zeros(1, dtype=torch.int32, device=self.tdev)
+        _lib.check(self.L.bl_stack(self.ctx, self._ptr(r), int(shuffle), int(seed), int(step), self._ptr(stack), self._ptr(base),
+                                   self._ptr(nb), self._stream()))
+        return stack.cpu().numpy(), base.cpu().numpy()[:int(nb.item())]
+
+    def discharge(self, receivers, rain):
+        """`flowcompute.discharge` with the uniform-rain source `area * rain` (flowNetwork.py:418-443) -> Q."""
+        r = self._dev(receivers, torch.int32); q = torch.empty(self.N, dtype=torch.float64, device=self.tdev)
+        _lib.check(self.L.bl_discharge(self.ctx, self._ptr(r), float(rain), self._ptr(q), self._stream()))
+        return q.cpu().numpy()
+
+    def basinparameters(self, receivers1, elev, fillH):
+        """`flowcompute.basinparameters` (flowNetwork.py:549) -> pitID, pitVolume."""
+        r = self._dev(receivers1, torch.int32); z = self._dev(elev, torch.float64); w = self._dev(fillH, torch.float64)
+        pid = torch.empty_like(r); vol = torch.empty_like(z)
+        _lib.check(self.L.bl_basins(self.ctx, self._ptr(r), self._ptr(z), self._ptr(w), self._ptr(pid), self._ptr(vol), self._stream()))
+        return pid.cpu().numpy(), vol.cpu().numpy()
+
+    def basindrainage(self, pitID, pitVolume, receivers, fillH, sealevel):
+        """`flowcompute.basindrainage` + `basindrainageall` (flowNetwork.py:558-568) -> pitDrain, allDrain."""
+        pid = self._dev(pitID, torch.int32); vol = self._dev(pitVolume, torch.float64)
+        r = self._dev(receivers, torch.int32); w = self._dev(fillH, torch.float64)
+        d1 = torch.empty_like(r); d2 = torch.empty_like(r)
+        _lib.check(self.L.bl_drainage(self.ctx, self._ptr(pid), self._ptr(vol), self._ptr(r), self._ptr(w), float(sealevel),
+                                      self._ptr(d1), self._ptr(d2), self._stream()))
+        return d1.cpu().numpy(), d2.cpu().numpy()
+
+    def streampower(self, receivers, pitID, pitVolume, pitDrain, maxh, Q, fillH, elev, erod, sealevel, dt, shuffle=0,
+                    seed=0, step=0):
+        """`flowcompute.streampower` (flowNetwork.py:656) -> cdepo, cero (m^3)."""
+        r = self._dev(receivers, torch.int32); pid = self._dev(pitID, torch.int32); vol = self._dev(pitVolume, torch.float64)
+        pdr = self._dev(pitDrain, torch.int32); mh = self._dev(maxh, torch.float64); q = self._dev(Q, torch.float64)
+        w = self._dev(fillH, torch.float64); z = self._dev(elev, torch.float64)
+        depo = torch.empty_like(z); ero = torch.empty_like(z)
+        _lib.check(self.L.bl_streampower(self.ctx, self._ptr(r), self._ptr(pid), self._ptr(vol), self._ptr(pdr), self._ptr(mh), self._ptr(q),
+                                         self._ptr(w), self._ptr(z), float(erod), float(sealevel), float(dt), int(shuffle), int(seed),
+                                         int(step), self._ptr(depo), self._ptr(ero), self._stream()))
+        return depo.cpu().numpy(), ero.cpu().numpy()
+
+    def diffusion(self, elev):
+        """`sfd.diffusion(elev, borders2, ...)` (flowNetwork.py:148) -> diffusion flux."""
+        z = self._dev(elev, torch.float64); out = torch.empty_like(z)
+        _lib.check(self.L.bl_diffuse(self.ctx, self._ptr(z), self._ptr(out), self._stream()))
+        return out.cpu().numpy()
+
+    def interpolate(self, v):
+        """`bl_mcmc.interpolateArray` (bl_mcmc.py:167-215) on the mesh-constant table -> (ny, nx) grid."""
+        x = self._dev(v, torch.float64); out = torch.empty(self.G, dtype=torch.float64, device=self.tdev)
+        _lib.check(self.L.bl_interp(self.ctx, self._ptr(x), self._ptr(out), self._stream()))
+        return out.cpu().numpy().reshape(self.mesh.grid_ny, self.mesh.grid_nx)
+
     # ---- inspection ---------------------------------------------------------------------------------
     def field(self, name: str, proposal: int = 0) -> np.ndarray:
         fid = _lib.FIELDS[name]

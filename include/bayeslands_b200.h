@@ -157,6 +157,54 @@ int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst_host, void *stream);
 /* number of kernel launches issued by this context so far (for bench.py's gpu_launches) */
 int64_t bl_launch_count(const bl_ctx *ctx);
 
+/* ---- per-stage entry points on caller-owned DEVICE arrays ------------------------------------------
+ * One routine of the time step per call, in the argument order of the f2py signature it replaces, executed by the SAME
+ * device function the fused step (bl_run) uses - the shared-memory path or the generic path, whichever the context
+ * selected.  Every array is a device pointer of length N (mesh constants come from the context, as the reference keeps
+ * them in module state: libUtils/PDclass.f90:15-34).  Proposal slot 0 of the context is the scratch landscape: its
+ * state is overwritten (use a context of its own, or bl_reset afterwards).  Calls are asynchronous on `stream`.
+ *
+ *   reference call site (flow/flowNetwork.py, surface/elevationTIN.py)                          entry point
+ *   fillH = pdstack.pitfilling(elev, allFill = 0, sealevel)          elevationTIN.py:304         bl_fill
+ *   base, rcv, maxh, maxdep = sfd.directions(fillH, elev, ngb, edges, dist, gids)  :310         bl_sfd(fillH, elev, ...)
+ *   base1, rcv1 = sfd.directions_base(elev, ngb, edges, dist, gids)  flowNetwork.py:298         bl_sfd(NULL, elev, ...)
+ *   donors, stack = fstack.build(base, receivers, delta)             :393 / :412                bl_stack
+ *   Q, lay = flowcompute.discharge(stack, receivers, elev, area * rain)  :440                   bl_discharge
+ *   pitID, pitVolume = flowcompute.basinparameters(stack1, rcv1, elev, fillH, area)  :549       bl_basins
+ *   pitDrain = flowcompute.basindrainage(order, pitID, rcv, pIDs, fillH, sea)  :566             bl_drainage
+ *   allDrain = flowcompute.basindrainageall(order, pitID, rcv, pIDs)  :568                      bl_drainage
+ *   cdepo, cero, sedload = flowcompute.streampower(stack, rcv, pitID, pitVolume, pitDrain, xy, area, maxh, maxdep,
+ *                          Q, fillH, elev, rivqs, K, actlay, perc_dep, slp_cr, sea, dt, borders)  :656   bl_streampower
+ *   diff = sfd.diffusion(elev, borders2, ngb, edges, dist, gids)     :148                        bl_diffuse
+ *   zreg = interpolateArray(coords, z)                               bl_mcmc.py:167-215          bl_interp
+ */
+int bl_fill(bl_ctx *ctx, const double *elev, double sealevel, double *fillH, void *stream);
+/* fillH != NULL: receivers on fillH, maxh / maxdep from elev (sfd.c:55-111); fillH == NULL: receivers on elev (sfd.c:113-153).
+ * base[i] = i for self-receivers, -1 elsewhere; base / maxh / maxdep may be NULL.  (A non-NULL base synchronises.) */
+int bl_sfd(bl_ctx *ctx, const double *fillH, const double *elev, int32_t *base, int32_t *rcv, double *maxh, double *maxdep,
+           void *stream);
+/* Pre-order DFS stack of the receiver forest (FLWnetwork.f90:21-71, FLOWstack.f90:24-40).  The base order is the
+ * reference's: ascending ids (shuffle = 0, flowNetwork.py:302-303) or shuffled (shuffle = 1, :316, counter-hash of
+ * (seed, step): DESIGN.md 5).  base_out [N] receives the ordered bases, nbase_out [1] their number; both may be NULL. */
+int bl_stack(bl_ctx *ctx, const int32_t *rcv, int shuffle, uint64_t seed, int64_t step, int32_t *stack, int32_t *base_out,
+             int32_t *nbase_out, void *stream);
+/* Q = area * rain (0 on ghost nodes) accumulated down the receiver tree in reverse stack order (FLOWalgo.f90:53-81). */
+int bl_discharge(bl_ctx *ctx, const int32_t *rcv, double rain, double *Q, void *stream);
+int bl_basins(bl_ctx *ctx, const int32_t *rcv1, const double *elev, const double *fillH, int32_t *pitID, double *pitVol,
+              void *stream);
+/* Both drainage maps of compute_parameters_depression (flowNetwork.py:558-577); the pit order is derived inside. */
+int bl_drainage(bl_ctx *ctx, const int32_t *pitID, const double *pitVol, const int32_t *rcv, const double *fillH,
+                double sealevel, int32_t *pitDrain, int32_t *allDrain, void *stream);
+/* Single rock, detachment limited (the configuration every BASELINE config reaches).  The stack the cascade follows
+ * is built from rcv with the base order (shuffle, seed, step) as in bl_stack.  Outputs: cdepo, cero in m^3. */
+int bl_streampower(bl_ctx *ctx, const int32_t *rcv, const int32_t *pitID, const double *pitVol, const int32_t *pitDrain,
+                   const double *maxh, const double *Q, const double *fillH, const double *elev, double erod,
+                   double sealevel, double dt, int shuffle, uint64_t seed, int64_t step, double *depo, double *ero,
+                   void *stream);
+int bl_diffuse(bl_ctx *ctx, const double *elev, double *diff, void *stream);
+/* v [N] nodal values -> grid [G] on the context's k = 3 table. */
+int bl_interp(bl_ctx *ctx, const double *v, double *grid, void *stream);
+
 /* ---- lattice engine: regular D8 lattice too large for one CTA (BASELINE config 5) -------------
  * Same reference path as above for the purely erosive configuration (flow.depo = 0, constant sea level): every
  * phase of the time step is a grid-wide kernel batched over all proposals.  Nodes are the (ny+2) x (nx+2) lattice

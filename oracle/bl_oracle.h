@@ -6,9 +6,13 @@
  *
  * PARITY STATUS: the reference ships no unit tests and cannot be executed here (Python 2 + gfortran +
  * Triangle).  Pinned against the reference itself: sfd.c routines (compiled from
- * /root/reference into oracle/_ref, bit-exact) and the shipped end-to-end data (likelihood formula,
- * likelihood-surface argmax, MSE at truth).  Everything else (Fortran routines) is a line-by-line
- * restatement whose per-kernel bit-level parity is UNPINNED by reference tests ("parity unpinned").
+ * /root/reference into oracle/_ref, bit-exact; golden vectors in tests/golden) and the shipped end-to-end data
+ * (likelihood formula, likelihood-surface argmax, MSE at truth, per-cell deviation of the shipped sweeps).
+ * Pinned by hand-derived fixtures (tests/micro.py, derivations in tests/golden/README.md): fillPD incl. the capped
+ * early stop and its order dependence, fstack.build, basinparameters, basindrainage(all) incl. a de-dup hit, discharge,
+ * streampower incl. the two-pit overflow cascade, the land-pit proportional fill, the CFL time step.
+ * "parity unpinned" (line-by-line restatements with no fixture of their own): flowcfl's slope exponent branch (n != 1),
+ * getid1's newdt re-run, diffmarine, marine_distribution, the marine branch of the pit cascade (FLOWalgo.f90:979-991).
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  */

@@ -232,6 +232,38 @@ class OracleModel:
             return self.L.or_run_to(C.byref(self.cm), C.byref(self.cp), self.st, len(stops), _dp(stops))
         return 0
 
+    # ---- single routines on explicit arrays (micro-fixtures, per-stage parity tests) --------
+    def streampower_routine(self, stack, rcv, pitID, pitVol, pitDrain, maxh, Q, fillH, z, erod, sea, dt):
+        """`flowcompute.streampower` (FLOWalgo.f90:583-1044) -> cdepo, cero."""
+        N = self.N
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        stack, rcv, pitID, pitDrain = i32(stack), i32(rcv), i32(pitID), i32(pitDrain)
+        pitVol, maxh, Q, fillH, z = f64(pitVol), f64(maxh), f64(Q), f64(fillH), f64(z)
+        maxdep = np.zeros(N); depo = np.zeros(N); ero = np.zeros(N); sedfl = np.zeros(N); pv = np.zeros(N)
+        self.L.or_streampower.restype = C.c_int
+        self.L.or_streampower.argtypes = [C.POINTER(_Mesh), C.POINTER(_Params), C.c_int, c_ip, c_ip, c_ip, c_dp, c_ip, c_dp, c_dp,
+                                          c_dp, c_dp, c_dp, C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp]
+        self.L.or_streampower(C.byref(self.cm), C.byref(self.cp), N, _ip(stack), _ip(rcv), _ip(pitID), _dp(pitVol), _ip(pitDrain),
+                              _dp(maxh), _dp(maxdep), _dp(Q), _dp(fillH), _dp(z), float(erod), float(sea), float(dt), _dp(depo),
+                              _dp(ero), _dp(sedfl), _dp(pv))
+        return depo, ero
+
+    def basindrainage_routine(self, pitID, pitVol, rcv, fillH, sea):
+        """`compute_parameters_depression` drainage part (flowNetwork.py:558-568): pit order + basindrainage(all)."""
+        N = len(pitID)
+        pitID = np.ascontiguousarray(pitID, dtype=np.int32); rcv = np.ascontiguousarray(rcv, dtype=np.int32)
+        fillH = np.ascontiguousarray(fillH, dtype=np.float64)
+        pIDs = np.ascontiguousarray(np.where(np.asarray(pitVol) >= 0.0)[0], dtype=np.int32)
+        order = np.ascontiguousarray(np.argsort(fillH[pIDs], kind="stable")[::-1], dtype=np.int32)
+        d1 = np.zeros(N, dtype=np.int32); d2 = np.zeros(N, dtype=np.int32)
+        ch = np.zeros(max(1, len(pIDs)), dtype=np.int32)
+        self.L.or_basindrainage.argtypes = [C.c_int, c_ip, c_ip, c_ip, c_ip, c_dp, C.c_double, C.c_int, c_ip, c_ip]
+        self.L.or_basindrainageall.argtypes = [C.c_int, c_ip, c_ip, c_ip, c_ip, C.c_int, c_ip, c_ip]
+        self.L.or_basindrainage(len(pIDs), _ip(order), _ip(pitID), _ip(rcv), _ip(pIDs), _dp(fillH), float(sea), N, _ip(d1), _ip(ch))
+        self.L.or_basindrainageall(len(pIDs), _ip(order), _ip(pitID), _ip(rcv), _ip(pIDs), N, _ip(d2), _ip(ch))
+        return d1, d2
+
     # ---- bl_mcmc.blackBox / interpolateArray (bl_mcmc.py:97-215) --------------------------
     def interpolate(self, v):
         m = self.mesh

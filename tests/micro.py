@@ -1,0 +1,200 @@
+"""Hand-derivable micro-fixtures for the routines the reference keeps in Fortran (no gfortran here: SURVEY.md F1).
+
+A *chain mesh* is a 1-D landscape: ghost node 0 at the left end, ghost node 1 at the right end (boundsPt = 2), interior
+nodes in between, each adjacent to its left and right neighbour only (neighbour order: left, right).  Cells are
+100 m x 100 m (area 1e4 m^2, Voronoi and Delaunay edge lengths 100 m), so every quantity of a time step can be
+followed by hand.  `order[p]` gives the node id at position p = 1 .. L-1 (the sweep order of fillPD is the id order).
+
+The expected values and their derivations are in tests/golden/README.md; both the CPU oracle and the CUDA path (per-stage
+entry points and bl_step) are checked against them (tests/test_oracle.py, tests/test_gpu_stages.py).
+"""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DX = 100.0
+
+
+def chain_mesh(z_by_pos, order=None, btype="fixed"):
+    """z_by_pos: elevations at positions 0 .. L (positions 0 and L are the ghost nodes).  Returns MeshArrays."""
+    from bayeslands_b200 import mesh as M
+    z_by_pos = np.asarray(z_by_pos, dtype=np.float64)
+    L = len(z_by_pos) - 1
+    N = L + 1
+    if order is None:
+        order = list(range(2, N))                  # ids ascend from left to right
+    ids = np.empty(L + 1, dtype=np.int64)          # id at position p
+    ids[0], ids[L] = 0, 1
+    ids[1:L] = order
+    assert sorted(ids.tolist()) == list(range(N))
+    pos = np.empty(N, dtype=np.int64)
+    pos[ids] = np.arange(L + 1)
+    ngb = np.full((N, M.KP), -2, dtype=np.int32)
+    edge = np.zeros((N, M.KP)); vor = np.zeros((N, M.KP))
+    for k in range(N):
+        p = pos[k]
+        q = 0
+        for pp in (p - 1, p + 1):
+            if 0 <= pp <= L:
+                ngb[k, q] = ids[pp]; edge[k, q] = DX; vor[k, q] = DX
+                q += 1
+    area = np.where(np.arange(N) < 2, 0.0, DX * DX)
+    xy = np.column_stack((pos * DX, np.zeros(N)))
+    fv = M.FVmesh(node_coords=xy, neighbours=ngb, edge_length=edge, vor_edges=vor, control_volumes=area)
+    regX = np.arange(1, L) * DX
+    rg = M.RecGrid(regX=regX, regY=np.array([0.0]), regZ=np.zeros((L - 1, 1)), resEdges=DX, areaDel=DX * DX, nx=L - 1, ny=1,
+                   rnx=L - 1, rny=1, boundsPt=2, edgesPt=0)
+    borders = (area > 0).astype(np.int32)
+    borders2 = borders.copy()
+    borders2[ids[1]] = 0; borders2[ids[L - 1]] = 0           # the DEM perimeter is excluded from hillslope diffusion
+    parent = np.array([ids[1], ids[L - 1]], dtype=np.int32)
+    elev = z_by_pos[pos]
+    m = M.MeshArrays(recGrid=rg, FVmesh=fv, elevation=elev.copy(), parentIDs=parent, borders=borders, borders2=borders2,
+                     insideIDs=np.where(borders > 0)[0], btype=btype, grid_nx=1, grid_ny=1,
+                     grid_idx=np.array([[2, 2, 2]], dtype=np.int32), grid_w=np.array([[1.0, 1.0, 1.0]]),
+                     grid_exact=np.array([1], dtype=np.int32), hillslope_min_edge2=DX * DX)
+    m.extra["pos"] = pos
+    m.extra["ids"] = ids
+    return m
+
+
+def inputs(fillmax=15.0, dep=1, caerial=0.0, cmarine=0.0, tend=5000.0):
+    """Input of Examples/crater_fast with the given knobs (no hillslope creep by default, so a step is fluvial only)."""
+    from bayeslands_b200 import config
+    xml = str(np.load(os.path.join(ROOT, "data", "crater_fast.npz"))["xml"])
+    xml = xml.replace("<fillmax>15.</fillmax>", "<fillmax>%r</fillmax>" % float(fillmax))
+    xml = xml.replace("<caerial>2.e-2</caerial>", "<caerial>%r</caerial>" % float(caerial))
+    xml = xml.replace("<cmarine>5.e-2</cmarine>", "<cmarine>%r</cmarine>" % float(cmarine))
+    xml = xml.replace("<end>15000.</end>", "<end>%r</end>" % float(tend)).replace("<rend>15000.</rend>", "<rend>%r</rend>" % float(tend))
+    inp = config.parse_xml(xml)
+    assert inp.fillmax == float(fillmax) and inp.CDa == float(caerial)
+    if not dep:
+        inp.depo = 0
+    return inp
+
+
+# ---------------------------------------------------------------------------------------------------
+# F1  capped lake: the sweep order changes the answer and the loop stops one sweep early (PDalgo.f90:58-79)
+# positions:      0(g0)  1     2     3     4    5(g1)
+F1_Z = [0.0, 20.0, 0.0, -10.0, 30.0, 50.0]
+EPS, TH = 0.01, 15.0
+
+
+def f1_expected(order):
+    """fillH by position 1..4, derived by hand in tests/golden/README.md (F1)."""
+    if order == "ascending":       # ids ascend left to right: one sweep, every write is a dry-out or a capped write
+        return [20.0, 0.0 + TH, -10.0 + TH, 30.0]
+    if order == "descending":      # ids ascend right to left: sweep 1 leaves 20, 5 + eps, 5, 45; sweep 2 dries position 4
+        return [20.0, 5.0 + EPS, -10.0 + TH, 30.0]
+    raise ValueError(order)
+
+
+# ---------------------------------------------------------------------------------------------------
+# F2  a staircase with two lakes: stack order, basins, drainage chain, discharge, stream power with a two-pit cascade
+#     (the upper lake overflows into the lower one, which overflows to the boundary) and the proportional land-pit fill.
+# positions:   0(g0)  1    2    3     4     5     6     7     8    9(g1)      ids: g0 = 0, g1 = 1, position p -> id p + 1
+F2_Z = [0.0, 10.0, 4.0, 12.0, 20.0, 14.0, 16.0, 25.0, 40.0, 60.0]
+F2_RAIN, F2_EROD, F2_SEA = 1.0, 2.0e-3, -1000.0
+AREA = DX * DX
+
+
+def f2_derive(dt):
+    """Every array of one time step of F2, written out node by node from the reference's formulas
+    (tests/golden/README.md, F2).  ids: g0 = 0, g1 = 1, position p -> p + 1."""
+    import math
+    z = {0: 0.0, 1: 60.0}
+    for p in range(1, 9):
+        z[p + 1] = F2_Z[p]
+    # fillPD, ascending ids, sweep 1 (PDalgo.f90:49-81); sweep 2 changes nothing
+    W = dict(z)
+    W[2] = 10.0                         # z >= W(g0) + eps: dries out
+    W[3] = W[2] + EPS                   # lake 1: spills over position 1
+    W[4] = 12.0; W[5] = 20.0
+    W[6] = W[5] + EPS                   # lake 2: spills over position 4
+    W[7] = W[6] + EPS
+    W[8] = 25.0; W[9] = 40.0
+    rcv1 = {0: 0, 1: 9, 2: 0, 3: 3, 4: 3, 5: 4, 6: 6, 7: 6, 8: 7, 9: 8}     # lowest neighbour on z (sfd.c:113-153)
+    rcv = {0: 0, 1: 9, 2: 0, 3: 2, 4: 3, 5: 4, 6: 5, 7: 6, 8: 7, 9: 8}      # lowest neighbour on W (sfd.c:55-111)
+    stack = [0, 2, 3, 4, 5, 6, 7, 8, 9, 1]       # pre-order DFS from base 0, donors ascending (FLOWstack.f90:24-40)
+    stack1 = [0, 2, 3, 4, 5, 6, 7, 8, 9, 1]      # bases 0, 3, 6 in ascending order
+    pitID = {k: -1 for k in range(10)}
+    pitID[0], pitID[3], pitID[6], pitID[7] = 0, 3, 6, 6                      # FLOWalgo.f90:150-163
+    pitVol = {k: -1.0 for k in range(10)}
+    pitVol[3] = -1.0 + (W[3] - z[3]) * AREA
+    pitVol[6] = (-1.0 + (W[6] - z[6]) * AREA) + (W[7] - z[7]) * AREA         # stack1 order: 6 then 7
+    pitDrain = {k: -1 for k in range(10)}
+    pitDrain[6], pitDrain[3], pitDrain[0] = 3, 0, 0                          # chain 6 -> 3 -> 0 (FLOWalgo.f90:190-234)
+    # discharge, reverse stack (FLOWalgo.f90:70-75): q0 = area * rain on interior nodes
+    Q = {1: 0.0}
+    acc = 0.0
+    for k in (9, 8, 7, 6, 5, 4, 3, 2):
+        Q[k] = AREA * F2_RAIN + (Q[1] if k == 9 else acc)
+        acc = Q[k]
+    Q[0] = 0.0 + Q[2]
+    # stream power (FLOWalgo.f90:635-714, :875-892): eroding nodes 9, 8, 5, 4, 2
+    def erode(d):
+        r = rcv[d]
+        dh = 0.95 * (z[d] - z[r])
+        slp = dh / DX
+        spl = -F2_EROD * 1.0 * 1.0 * math.sqrt(Q[d]) * slp
+        tot = 0.0 + spl
+        if -tot * dt > dh:
+            spl = spl * (dh / (-tot * dt))
+        return spl * dt * AREA
+    ero = {k: 0.0 for k in range(10)}
+    depo = {k: 0.0 for k in range(10)}
+    for k in (9, 8, 5, 4, 2):
+        ero[k] = 0.0 + erode(k)
+    qs9 = -ero[9] + 0.0
+    load6 = -ero[8] + qs9                 # enters lake 2 at node 7 (pit 6)
+    qs5 = -ero[5] + 0.0
+    load3 = -ero[4] + qs5                 # enters lake 1 at node 3 (pit 3)
+    vol = dict(pitVol)
+    # cascade (FLOWalgo.f90:967-1034), events in reverse stack order: lake 2 first
+    def cascade(pit, load):
+        while load > 0.0:
+            have = 0.0 + depo[pit]
+            if have + load <= vol[pit] or pitDrain[pit] == pit:
+                depo[pit] = depo[pit] + load
+                return
+            frac = load / load
+            depo[pit] = depo[pit] + (vol[pit] - have) * frac
+            load = (load - (vol[pit] - have)) * frac
+            vol[pit] = 0.0 + depo[pit]
+            pit = pitDrain[pit]
+    cascade(6, load6)
+    cascade(3, load3)
+    # land-pit fill (flowNetwork.py:750-763): thickness (W - z) scaled so that the pit's members hold depo[pit]
+    th = {k: 0.0 for k in range(10)}
+    t3 = (W[3] - z[3]) * 1.0
+    th[3] = t3 * ((0.0 + depo[3]) / (t3 * AREA))
+    t6, t7 = (W[6] - z[6]) * 1.0, (W[7] - z[7]) * 1.0
+    f6 = (0.0 + depo[6]) / (t6 * AREA + t7 * AREA)
+    th[6], th[7] = t6 * f6, t7 * f6
+    sedflux = {k: 0.0 for k in range(10)}
+    for k in range(2, 10):
+        sedflux[k] = ero[k] / AREA + th[k]
+    tolist = lambda dct: [dct[k] for k in range(10)]
+    return dict(fillH=tolist(W), rcv1=tolist(rcv1), rcv=tolist(rcv), stack=stack, stack1=stack1, pitID=tolist(pitID),
+                pitVol=tolist(pitVol), pitDrain=tolist(pitDrain), allDrain=tolist(pitDrain), Q=tolist(Q), ero=tolist(ero),
+                depo=tolist(depo), sedflux=tolist(sedflux), load6=load6, load3=load3)
+
+
+def f2_cfl_dt():
+    """dt of the first step: floor of min dist / (K sqrt(Q)) over the flowing nodes (FLOWalgo.f90:299-330, buildFlux.py:169-177)."""
+    import math
+    return float(math.floor(DX / (F2_EROD * math.sqrt(8.0 * AREA * F2_RAIN))))
+
+
+# ---------------------------------------------------------------------------------------------------
+# F3  basindrainage with a chainDrain de-duplication hit (FLOWalgo.f90:190-234): two pits whose walks reach each other.
+# Hand-made arrays (not a surface): pit 1 (fillH 9) walks 1 -> 3, node 3 lies in pit 2: drain[1] = 2, jump to 2; 2 -> 4, node 4
+# lies in pit 1, not yet in the chain: drain[2] = 1, jump to 1; 1 -> 3 again, pit 2 IS in the chain now: walk through, 3 -> 5,
+# 5 is a self-receiver: drain[1] = 5 (overwrites 2).  Pit 2 is then found already drained.
+F3 = dict(N=8,
+          rcv=[0, 3, 4, 5, 6, 5, 6, 7],
+          pitID=[-1, 1, 2, 2, 1, -1, -1, -1],
+          pitVol=[-1.0, 5.0, 3.0, -1.0, -1.0, -1.0, -1.0, -1.0],
+          fillH=[0.0, 9.0, 8.0, 7.5, 7.0, 1.0, 2.0, 3.0],
+          pitDrain=[-1, 5, 1, -1, -1, -1, -1, -1])

@@ -188,3 +188,66 @@ def test_sea_level_matches_scipy_interp1d():
     for x in list(rng.uniform(0, 5e5, 200)) + [0.0, 100.0, 5e5, 250.0, 499999.0]:
         assert L.or_sea(C.byref(p), float(x)) == float(f(x))
     assert L.or_sea(C.byref(p), -5.0) == sl[0, 1] and L.or_sea(C.byref(p), 9e9) == sl[-1, 1]
+
+
+# ---------------------------------------------------------------------------------------------------
+# hand-derived micro-fixtures (tests/micro.py, derivations in tests/golden/README.md): they pin the restatement of the
+# Fortran routines (no gfortran here) to values followed by hand from the reference's source
+# ---------------------------------------------------------------------------------------------------
+def test_micro_f1_capped_lake_sweep_order_and_early_stop():
+    """PDalgo.f90:58-79: capped writes do not raise `change`, so the sweep can stop early and its result depends on the
+    node order: the same 4-node profile fills differently when the ids ascend left-to-right or right-to-left."""
+    import micro
+    from oracle import oracle
+    for name, order, sweeps in (("ascending", None, 1), ("descending", [5, 4, 3, 2], 2)):
+        m = micro.chain_mesh(micro.F1_Z, order)
+        om = oracle.OracleModel(m, micro.inputs(fillmax=15.0), seed=1)
+        om.reset(1.0, 1e-5, seed=1)
+        om.streamflow()
+        assert np.array_equal(om.fillH[m.extra["ids"][1:5]], micro.f1_expected(name)), name
+        assert om.fill_sweeps == sweeps
+
+
+def test_micro_f2_two_lakes_full_step():
+    """Stack order, basin ids / volumes, the drainage chain 6 -> 3 -> 0, discharge, stream power with an overflowing lake
+    and the proportional land-pit fill of one full time step, array by array against the hand derivation."""
+    import micro
+    from oracle import oracle
+    m = micro.chain_mesh(micro.F2_Z)
+    om = oracle.OracleModel(m, micro.inputs(fillmax=200.0), seed=1, shuffle_mode=0)
+    om.reset(micro.F2_RAIN, micro.F2_EROD, seed=1)
+    om.streamflow(); om.sediment_flux(5000.0)
+    dt = micro.f2_cfl_dt()
+    assert om.last_dt == dt == 176.0
+    exp = micro.f2_derive(dt)
+    assert exp["load3"] > exp["pitVol"][3] > 0          # lake 1 overflows to the boundary in this step
+    for k in ("fillH", "rcv1", "rcv", "stack", "stack1", "pitID", "pitVol", "pitDrain", "allDrain", "Q", "ero", "depo", "sedflux"):
+        assert np.array_equal(np.asarray(getattr(om, k)), np.asarray(exp[k])), k
+
+
+def test_micro_f2_two_pit_cascade_routine():
+    """FLOWalgo.f90:967-1034 at dt = 300 a: lake 2 receives more than its volume, the excess enters lake 1, whose own load
+    then overflows to the boundary node."""
+    import micro
+    from oracle import oracle
+    m = micro.chain_mesh(micro.F2_Z)
+    om = oracle.OracleModel(m, micro.inputs(fillmax=200.0), seed=1, shuffle_mode=0)
+    om.reset(micro.F2_RAIN, micro.F2_EROD, seed=1)
+    om.streamflow()
+    exp = micro.f2_derive(300.0)
+    assert exp["load6"] > exp["pitVol"][6] and exp["depo"][6] == exp["pitVol"][6] and exp["depo"][3] == exp["pitVol"][3] and exp["depo"][0] > 0
+    depo, ero = om.streampower_routine(om.stack, om.rcv, om.pitID, om.pitVol, om.pitDrain, om.maxh, om.Q, om.fillH, om.z,
+                                       micro.F2_EROD, micro.F2_SEA, 300.0)
+    assert np.array_equal(depo, exp["depo"]) and np.array_equal(ero, exp["ero"])
+
+
+def test_micro_f3_drainage_dedup_hit():
+    """FLOWalgo.f90:190-234: a walk that comes back to a pit already in chainDrain walks through it (and overwrites the
+    first pit's target with the terminal it finally reaches)."""
+    import micro
+    from oracle import oracle
+    m = micro.chain_mesh([0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0])       # any 8-node mesh: the routine reads only the arrays
+    om = oracle.OracleModel(m, micro.inputs(), seed=1)
+    f = micro.F3
+    d1, d2 = om.basindrainage_routine(f["pitID"], f["pitVol"], f["rcv"], f["fillH"], -1000.0)
+    assert d1.tolist() == f["pitDrain"] and d2.tolist() == f["pitDrain"]
