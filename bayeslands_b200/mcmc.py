@@ -250,8 +250,9 @@ class bayeslands_mcmc(object):
         """Single random-walk Metropolis chain with the reference's draw order and output files
         (`bl_mcmc.py:515-835`): numpy's global stream for the start point, the proposals and the three unused eta
         draws, stdlib `random` for the accept test; `description.txt`, `exp_data.txt` (one `rain erod likl` row per
-        sample, `storeParams` :457-480), `prediction_data/mean_pred_{elev,erdp}_<t>.txt` and `mean_pred_erdp_pts.txt`
-        (post burn-in running means, :776-815) and `experiment_stats.txt` (:817-833).  Plots are out of scope.
+        sample, `storeParams` :457-480), `prediction_data/mean_pred_{elev,erdp,erdp_pts}_<t>.txt` (post burn-in running
+        means, :776-815), `experiment_stats.txt` (RMSEelev / RMSEerdp / RMSEerdp_pts, accept ratio, count list, :817-831)
+        and `prediction_data/pred_xslc.txt` / `pred_yslc.txt` (mid-domain slices per sample, :832-833).  Plots are out of scope.
         Returns (pos_rain, pos_erod, pos_likl, accept_ratio).
 
         `speculate=K` (default: the engine's batch size; 1 = strictly sequential evaluation) evaluates the next K proposals
@@ -270,10 +271,19 @@ class bayeslands_mcmc(object):
         rain = np.random.uniform(self.rainlimits[0], self.rainlimits[1])
         erod = np.random.uniform(self.erodlimits[0], self.erodlimits[1])
         m, n = 0.5, 1.0
+        # first evaluation of the start point (:569): the eta step sizes written to description.txt come from it (:571-585)
+        _, ipts, ielev, ierdp = self.blackBox_batch([rain], [erod], grids=True)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            eta_elev = np.log(np.var(ielev[0, -1] - self.real_elev))
+            eta_erdp = np.log(np.var(ierdp[0, -1] - self.real_erdp)) if self.real_erdp is not None else float("nan")
+            eta_erdp_pts = np.log(np.var(ipts[0, -1] - self.real_erdp_pts))
+        step_eta_elev, step_eta_erdp, step_eta_erdp_pts = np.abs(eta_elev * 0.02), np.abs(eta_erdp * 0.02), np.abs(eta_erdp_pts * 0.02)
         if fn:
             with open(os.path.join(fn, "description.txt"), "a") as f:                         # :589-605
                 for k, v in (("samples", samples), ("step_rain", self.step_rain), ("step_erod", self.step_erod),
-                             ("step_m", self.step_m), ("step_n", self.step_n), ("Initial_proposed_rain", rain),
+                             ("step_m", self.step_m), ("step_n", self.step_n), ("step_eta_elev", step_eta_elev),
+                             ("step_eta_erdp", step_eta_erdp), ("step_eta_erdp_pts", step_eta_erdp_pts),
+                             ("Initial_proposed_rain", rain),
                              ("Initial_proposed_erod", erod), ("Initial_proposed_m", m), ("Initial_proposed_n", n),
                              ("erod_limits", self.erodlimits), ("rain_limits", self.rainlimits),
                              ("m_limit", self.mlimit), ("n_limit", self.nlimit)):
@@ -289,8 +299,7 @@ class bayeslands_mcmc(object):
                 with open(os.path.join(fn, "exp_data.txt"), "a") as f:
                     f.write("{0} {1} {2} \n".format(r, e, l))
 
-        self.blackBox_batch([rain], [erod])                  # the reference evaluates the start twice (:569, :610)
-        likelihood, elev, erdp, pts = evaluate(rain, erod)
+        likelihood, elev, erdp, pts = evaluate(rain, erod)     # second evaluation of the start (:610)
         pos_likl = np.full(samples, likelihood)              # np.zeros(samples, likelihood) in the reference (F11)
         prev = (elev, erdp, pts)
         store(pos_rain[0], pos_erod[0], pos_likl[0])
@@ -298,6 +307,10 @@ class bayeslands_mcmc(object):
         burnsamples = int(samples * self.burn_in)
         num_div = 0
         accept_counter = 0
+        count_list = [0]                                     # sample numbers of the accepted proposals (:540, :631, :703)
+        list_yslicepred = np.zeros((samples, self.real_elev.shape[0]))    # mid-domain slices of the accepted topography (:534-537)
+        list_xslicepred = np.zeros((samples, self.real_elev.shape[1]))
+        ymid, xmid = int(self.real_elev.shape[1] / 2), int(self.real_elev.shape[0] / 2)
         K = max(1, min(int(self.batch if speculate is None else speculate), self.batch))
         seed0 = self._evals + self.shuffle_seed * 1000003                       # base-shuffle seed of iteration 0
         nz_r, nz_e, us = [], [], []                                             # noise / uniforms drawn so far, per iteration
@@ -355,8 +368,14 @@ class bayeslands_mcmc(object):
                         _, p1, e1, d1 = self.blackBox_batch([rain], [erod], grids=True, seeds=[seed0 + it])
                         prev = (e1[0], d1[0], p1[0])
                     accept_counter += 1
+                    count_list.append(it)
+                    final_predtopo = prev[0][-1]
+                    list_yslicepred[it + 1, :] = final_predtopo[:, ymid]
+                    list_xslicepred[it + 1, :] = final_predtopo[xmid, :]
                 else:
                     pos_rain[it + 1], pos_erod[it + 1], pos_likl[it + 1] = pos_rain[it], pos_erod[it], pos_likl[it]
+                    list_yslicepred[it + 1, :] = list_yslicepred[it, :]
+                    list_xslicepred[it + 1, :] = list_xslicepred[it, :]
                 store(pos_rain[it + 1], pos_erod[it + 1], pos_likl[it + 1])
                 if it > burnsamples:
                     sum_elev += prev[0]; sum_erdp += prev[1]; sum_pts += prev[2]
@@ -367,16 +386,28 @@ class bayeslands_mcmc(object):
             i += used
         self._evals = seed0 - self.shuffle_seed * 1000003 + samples - 1
         accept_ratio = accept_counter / (samples * 1.0) * 100
+        div = max(num_div, 1)
+        mean_elev, mean_erdp, mean_pts = sum_elev / div, sum_erdp / div, sum_pts / div
+        # RMSE of the mean predictions at the final time (:783, :791, :801) - same numpy broadcasting as the reference
+        self.rmse_elev = float(np.sqrt(np.sum(np.square(mean_elev[-1] - self.real_elev)) / self.real_elev.size))
+        self.rmse_erdp = (float(np.sqrt(np.sum(np.square(mean_erdp[-1] - self.real_erdp)) / np.size(self.real_erdp)))
+                          if self.real_erdp is not None else float("nan"))
+        self.rmse_erdp_pts = float(np.sqrt(np.sum(np.square(mean_pts[-1] - self.real_erdp_pts)) / self.real_erdp_pts.size))
+        self.count_list = count_list
         if fn:
-            div = max(num_div, 1)
             for x, T in enumerate(self.sim_interval):
-                np.savetxt(os.path.join(fn, "prediction_data", "mean_pred_elev_%s.txt" % T), sum_elev[x] / div, fmt="%.5f")
-                np.savetxt(os.path.join(fn, "prediction_data", "mean_pred_erdp_%s.txt" % T), sum_erdp[x] / div, fmt="%.5f")
-            np.savetxt(os.path.join(fn, "prediction_data", "mean_pred_erdp_pts.txt"), sum_pts / div, fmt="%.5f")
-            burn = int(samples * self.burn_in)
-            with open(os.path.join(fn, "experiment_stats.txt"), "w") as f:
-                f.write("Time:(s) {0}\nTime:(mins) {1}\nAccept ratio: {2} %\nSamples accepted: {3} out of {4}\n".format(
-                    time.time() - start, (time.time() - start) / 60.0, accept_ratio, accept_counter, samples))
-                f.write("Mean rain after burn-in: {0}\nMean erod after burn-in: {1}\n".format(
-                    pos_rain[burn:].mean(), pos_erod[burn:].mean()))
+                np.savetxt(os.path.join(fn, "prediction_data", "mean_pred_elev_%s.txt" % T), mean_elev[x], fmt="%.5f")
+                np.savetxt(os.path.join(fn, "prediction_data", "mean_pred_erdp_%s.txt" % T), mean_erdp[x], fmt="%.5f")
+                np.savetxt(os.path.join(fn, "prediction_data", "mean_pred_erdp_pts_%s.txt" % T), mean_pts[x], fmt="%.5f")
+            np.savetxt(os.path.join(fn, "prediction_data", "mean_pred_erdp_pts.txt"), mean_pts, fmt="%.5f")
+            total_time = time.time() - start
+            accepted_count = len(count_list)                 # the reference counts the start point too (:817-819)
+            with open(os.path.join(fn, "experiment_stats.txt"), "w") as f:                    # :826-831
+                f.write("RMSEelev: {0}\nRMSEerdp: {1}\nRMSEerdp_pts: {2}\nTime:(s) {3}\nTime:(mins) {4}\n".format(
+                    self.rmse_elev, self.rmse_erdp, self.rmse_erdp_pts, total_time, total_time / 60.0))
+                f.write("Accept ratio: {0} %\nSamples accepted : {1} out of {2}\n Count List : {3} ".format(
+                    accepted_count / (samples * 1.0) * 100, accepted_count, samples, count_list))
+                f.write("Time Elapsed: (s) {0} , (mins): {1}".format(total_time, total_time / 60.0))
+            np.savetxt(os.path.join(fn, "prediction_data", "pred_xslc.txt"), list_xslicepred)     # :832-833
+            np.savetxt(os.path.join(fn, "prediction_data", "pred_yslc.txt"), list_yslicepred)
         return pos_rain, pos_erod, pos_likl, accept_ratio

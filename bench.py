@@ -110,8 +110,14 @@ def run_reference(args):
     ncores = os.cpu_count() or 1
     _, _, m, simtime, rl, el, _, _ = load_config(cfg)
     per_step = max(ncores, 8)
+    # the oracle library is loaded (and exercised once) in THIS process too, so that the record of native objects the
+    # driver keeps for the reference arm shows oracle/libbl_oracle.so; the pool workers are forks of it
+    _cpu_init(cfg)
+    r0, e0, s0 = proposals(-1000, 0, 1, rl, el)
+    _cpu_eval((r0[0], e0[0], s0[0]))
     ctx = mp.get_context("fork")
-    with ctx.Pool(ncores, initializer=_cpu_init, initargs=(cfg,)) as pool:
+    nsteps_seen = []
+    with ctx.Pool(ncores) as pool:
         def one(step):
             r, e, s = proposals(step, 0, per_step, rl, el)
             return pool.map(_cpu_eval, list(zip(r, e, s)), chunksize=1)
@@ -119,18 +125,24 @@ def run_reference(args):
             one(-1 - w)
         t0 = time.perf_counter()
         for k in range(args.steps):
-            one(k)
+            nsteps_seen += [x[1] for x in one(k)]
         dt = time.perf_counter() - t0
     val = per_step * args.steps / dt
+    mean_steps = float(np.mean(nsteps_seen)) if nsteps_seen else 0.0
     line = dict(impl="reference", metric="mcmc_forward_model_evals_per_sec", value=val, unit="evals/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=dt / args.steps * 1e3,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload="Examples/%s full blackBox+likelihood, T=%d a, N=%d TIN nodes, G=%d grid cells"
                                      % (cfg, simtime, m.N, m.grid_nx * m.grid_ny),
-                            proposals_per_step=per_step, parallelism="%d host processes" % ncores),
+                            proposals_per_gpu_per_step=per_step, mean_time_steps_per_eval=mean_steps,
+                            node_steps_per_s=val * mean_steps * m.N, l2_policy="n/a (host CPU arm)",
+                            parallelism="%d host processes, one evaluation each" % ncores, status_bits=0),
+                reference_is_oracle_port=True,
                 cpu_baseline=dict(value=val, unit="evals/s", cores=ncores, kind="port",
-                                  sample="%d evaluations per step over %d processes, CPU oracle "
-                                         "(reference itself cannot run: py2+gfortran+Triangle)" % (per_step, ncores)),
+                                  sample="%d evaluations per step over %d processes, CPU oracle = C restatement of the "
+                                         "reference path, -O2, sqrt for Q**0.5 (the reference calls libm pow), one mesh build "
+                                         "for all evaluations (the reference rebuilds it per proposal); the reference itself "
+                                         "cannot run here: py2 + gfortran + Triangle" % (per_step, ncores)),
                 e2e=dict(value=val, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -276,11 +288,13 @@ def run_ours(args):
         achieved = alg_bytes / (kernel_ms[-1] * 1e-3) / 1e9
         # DRAM traffic of this launch, scaled from the committed ncu --set full capture (bytes per node-step there
         # times the node-steps of this launch); null when the capture is for another config
-        traffic = None
+        traffic, traffic_source = None, "none: no ncu --set full capture for this config"
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             if cfg == "crater" and tj.get("N") == m.N:
                 traffic = float(tj["dram_bytes_per_node_step"] * np.sum(steps_last) * m.N)
+                traffic_source = ("not measured in this run: dram__bytes_read+write per node-step of the committed ncu --set full "
+                                  "capture (profiles/ncu_traffic.json, %s) x the node-steps of this launch" % tj.get("capture", "?"))
         except Exception:
             pass
         cpu = cpu_baseline(cfg) if world == 1 and not args.no_cpu else None
@@ -297,15 +311,119 @@ def run_ours(args):
                     e2e=dict(value=e2e_val, unit="evals/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=int(launches),
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                                  traffic=traffic, kernel="bl_run_kernel", kernel_ms=kernel_ms[-1],
+                                  traffic=traffic, traffic_source=traffic_source, kernel="bl_run_kernel",
+                                  alg_bytes_per_node_step=B_ALG_NODE_STEP, kernel_ms=kernel_ms[-1],
                                   peak_source="MEASURED_PEAKS.json" if peaks else "fallback",
                                   share_of_step=sum(kernel_ms) / ms),
                     clocks=clocks)
         if cpu:
             line["cpu_baseline"] = cpu
+        if cfg == "crater" and not args.no_other:
+            # the other BASELINE configs, measured after the headline's timed region (short batches; same JSON line)
+            del mc, eng
+            torch.cuda.empty_cache()
+            line["config"]["other_workloads"] = other_workloads(local, peak, not args.no_cpu and world == 1)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _resident_rate(cfg, B, device, steps=2, warmup=1):
+    """evals/s of `cfg` with inputs resident in HBM (same protocol as the headline), mean time steps, roofline fraction inputs."""
+    import torch
+    from bayeslands_b200.mcmc import bayeslands_mcmc
+    d, inp, m, simtime, rl, el, coords, likl_sed = load_config(cfg)
+    mc = bayeslands_mcmc(True, simtime, 0, d["final_elev"], d["final_erdp"], d["final_erdp_pts"], coords, None, inp,
+                         el, rl, (0.4, 0.6), (0.9, 1.1), "bench", likl_sed, batch=B, device=device, mesh=m,
+                         sealevel=d["sealevel"] if "sealevel" in d else None)
+    eng = mc.engine
+    dev = eng.tdev
+    st = []
+    for k in range(-warmup, steps):
+        r, e, s = proposals(7000 + k, 0, B, rl, el)
+        st.append((torch.as_tensor(r, device=dev), torch.as_tensor(e, device=dev), torch.as_tensor(s, device=dev)))
+    torch.cuda.synchronize(dev)
+    for k in range(warmup):
+        eng.reset(*st[k]); eng.run_schedule(mc.sim_interval)
+    torch.cuda.synchronize(dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(warmup, warmup + steps):
+        eng.reset(*st[k]); eng.run_schedule(mc.sim_interval)
+    t1.record()
+    torch.cuda.synchronize(dev)
+    ms = t0.elapsed_time(t1)
+    sc = eng.scalars()
+    return mc, dict(value=B * steps / (ms * 1e-3), unit="evals/s", proposals_per_step=B, steps=steps,
+                    mean_time_steps_per_eval=float(sc["steps"].mean()), N=m.N, G=eng.G,
+                    status_bits=int(np.bitwise_or.reduce(sc["status"])),
+                    alg_bytes_last=float(sc["steps"].sum() * m.N * B_ALG_NODE_STEP + B * B_ALG_CELL * eng.G), ms_last=ms / steps)
+
+
+def other_workloads(device, peak, with_cpu):
+    """Short measurements of the BASELINE configs the headline does not cover: etopo_fast (marine path), a crater_fast
+    single chain with speculative batching, a small synthetic lattice.  Each: value, mean steps, roofline fraction, CPU leg."""
+    import torch
+    out = {}
+    # ---- Examples/etopo_fast: sea-level curve, marine deposition + diffusion (BASELINE configs[2])
+    mc, r = _resident_rate("etopo_fast", 888, device)
+    r["roofline_frac"] = r.pop("alg_bytes_last") / (r.pop("ms_last") * 1e-3) / 1e9 / peak
+    if with_cpu:
+        r["cpu_baseline"] = cpu_baseline("etopo_fast", budget_s=3.0)
+    out["etopo_fast"] = r
+    del mc
+    torch.cuda.empty_cache()
+    # ---- Examples/crater_fast: ONE Metropolis chain, 300 samples, speculative batches of 148 proposals (configs[0])
+    mc, r = _resident_rate("crater_fast", 148, device, steps=1, warmup=1)
+    mc.samples = 300
+    mc.filename = None
+    np.random.seed(0)
+    import random
+    random.seed(0)
+    l0 = mc.engine.launches
+    t0 = time.perf_counter()
+    pos_rain, pos_erod, pos_likl, acc = mc.sampler(speculate=148)
+    dt = time.perf_counter() - t0
+    r["roofline_frac"] = r.pop("alg_bytes_last") / (r.pop("ms_last") * 1e-3) / 1e9 / peak
+    r["single_chain"] = dict(value=(mc.samples - 1) / dt, unit="chain iterations/s", samples=mc.samples, speculate=148,
+                             accept_ratio_percent=float(acc), launches=int(mc.engine.launches - l0))
+    if with_cpu:
+        r["cpu_baseline"] = cpu_baseline("crater_fast", budget_s=3.0)
+    out["crater_fast"] = r
+    del mc
+    torch.cuda.empty_cache()
+    # ---- synthetic regular-grid landscape on the lattice engine, small lattice (configs[4] in miniature; the full
+    #      2048 x 2048 x 256 run is `bench.py --config synthetic`)
+    from bayeslands_b200 import synthetic
+    from bayeslands_b200.grid_engine import GridEngine
+    nx, T, B = 256, 50000.0, 16
+    lat, inp = synthetic.build(nx, nx, T=T)
+    eng = GridEngine(lat, inp, B, device=device, real_elev=lat.z0 + lat.disp * T)
+    times = [T / 4, T / 2, 3 * T / 4, T]
+    rr, ee = synthetic.proposals(B, offset=424242)
+    dr, de = torch.as_tensor(rr, device=eng.tdev), torch.as_tensor(ee, device=eng.tdev)
+    eng.reset(dr, de); eng.run_schedule(times)
+    torch.cuda.synchronize(eng.tdev)
+    l0 = eng.launches
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record()
+    eng.reset(dr, de); eng.run_schedule(times)
+    t1e.record()
+    torch.cuda.synchronize(eng.tdev)
+    ms = t0e.elapsed_time(t1e)
+    sc = eng.scalars()
+    N = (nx + 2) * (nx + 2)
+    syn = dict(value=B / (ms * 1e-3), unit="evals/s", proposals_per_step=B, steps=1, lattice="%dx%d" % (nx, nx), N=N,
+               mean_time_steps_per_eval=float(sc["steps"].mean()),
+               mean_fill_sweeps_per_step=float(sc["fill_sweeps"].sum() / max(1.0, float(sc["steps"].sum()))),
+               launches=int(eng.launches - l0),
+               roofline_frac=float(sc["steps"].sum()) * N * 157.0 / (ms * 1e-3) / 1e9 / peak)
+    if with_cpu:
+        per_step = _synthetic_cpu(nx, nx, T)
+        syn["cpu_baseline"] = dict(value=1.0 / (per_step * syn["mean_time_steps_per_eval"]), unit="evals/s", cores=1, kind="port",
+                                   sample="2 time steps of one proposal on the same lattice, CPU oracle, scaled by the steps of an evaluation")
+    out["synthetic_%d" % nx] = syn
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -445,6 +563,7 @@ def main():
     ap.add_argument("--nx", type=int, default=2048, help="synthetic config: lattice size (nx = ny)")
     ap.add_argument("--simtime", type=float, default=50000.0, help="synthetic config: simulated years")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the short measurements of the other BASELINE configs")
     args = ap.parse_args()
     if args.config == "synthetic":
         if args.impl == "reference":

@@ -170,6 +170,18 @@ def test_sampler_writes_reference_outputs_and_is_seeded(crater_fast, tmp_path):
     g = np.loadtxt(tmp_path / "run0" / "prediction_data" / "mean_pred_elev_15000.txt")
     assert g.shape == (123, 123) and 20.0 < g.mean() < 120.0
     assert 0.0 <= out[0][3] <= 100.0
+    # bl_mcmc.py:595-597, :776-833: eta step sizes, RMSE lines, count list, per-time point means, mid-domain slices
+    desc = open(tmp_path / "run0" / "description.txt").read()
+    assert all(k in desc for k in ("step_eta_elev:", "step_eta_erdp:", "step_eta_erdp_pts:", "Initial_proposed_rain:"))
+    stats = open(tmp_path / "run0" / "experiment_stats.txt").read()
+    assert stats.startswith("RMSEelev: ") and "RMSEerdp: " in stats and "RMSEerdp_pts: " in stats and "Count List : [0" in stats
+    rm = float(stats.split("RMSEelev: ")[1].split()[0])
+    d = crater_fast[0]
+    assert abs(rm - np.sqrt(np.mean((g - d["final_elev"]) ** 2))) < 1e-4 * rm      # the file is written with %.5f
+    xs = np.loadtxt(tmp_path / "run0" / "prediction_data" / "pred_xslc.txt")
+    ys = np.loadtxt(tmp_path / "run0" / "prediction_data" / "pred_yslc.txt")
+    assert xs.shape == (8, 123) and ys.shape == (8, 123) and np.all(xs[0] == 0)
+    assert np.loadtxt(tmp_path / "run0" / "prediction_data" / "mean_pred_erdp_pts_15000.txt").shape == (10,)
 
 
 def test_speculative_sampler_is_the_same_chain(crater_fast, tmp_path):
