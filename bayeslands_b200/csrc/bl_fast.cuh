@@ -144,13 +144,11 @@ __device__ __forceinline__ void fill_eval(const unsigned short *__restrict__ ngb
     // min over the neighbours (exact: any association gives the same bits); four loads in flight at a time keep the
     // evaluation within the register budget (a spill costs an L2 round trip: the L1 is carved out for shared memory)
     double hmin = 2.e6;
+    double wj[KDT];
 #pragma unroll
-    for (int p0 = 0; p0 < KDT; p0 += 4) {
-        double h[4];
+    for (int p = 0; p < KDT; ++p) wj[p] = lds_f64(aW + 8u * ids.get(p));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) h[u] = lds_f64(aW + 8u * ids.get(p0 + u));
-        hmin = fmin(hmin, fmin(fmin(h[0], h[1]), fmin(h[2], h[3])));
-    }
+    for (int p0 = 0; p0 < KDT; p0 += 4) hmin = fmin(hmin, fmin(fmin(wj[p0], wj[p0 + 1]), fmin(wj[p0 + 2], wj[p0 + 3])));
     // PDalgo.f90:51-79 without branches (same arithmetic, same comparisons):
     //   if (W > z) { if (z >= he) W = z; else if (W > he) { W = he; if capped W = floor + TH else change = true } }
     const double he = hmin + eps;
@@ -164,12 +162,13 @@ __device__ __forceinline__ void fill_eval(const unsigned short *__restrict__ ngb
         sts_f64(ak, nw);
         // wake only the neighbours this change can move: re-evaluating j alters W(j) only if
         // min_nb W + eps < W(j), and the neighbour that brings the minimum down below W(j) - eps is the
-        // one that wakes j (W(j) is re-read: other levels do not change during this pass).  Flags of ghost nodes
+        // one that wakes j (other levels do not change during this pass).  Flags of ghost nodes
         // and of the dummy node may get set too: no level ever reads them.
         const double lim = nw + eps;
-        double wj[KDT];
+        if (KDT > 8) {      // wide rows: re-read the neighbour values instead of holding 2 * KDT registers across the min
 #pragma unroll
-        for (int p = 0; p < KDT; ++p) wj[p] = lds_f64(aW + 8u * ids.get(p));
+            for (int p = 0; p < KDT; ++p) wj[p] = lds_f64(aW + 8u * ids.get(p));
+        }
 #pragma unroll
         for (int p = 0; p < KDT; ++p) sts_u8_if(wj[p] > lim, aP + ids.get(p), 1u);
     }
@@ -229,6 +228,8 @@ __device__ __noinline__ void fill_bitmap(const DevConst &c, Smem &S, unsigned ch
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         pb[q] = (((q < 4 ? w2.x : w2.y) >> (8 * (q & 3))) & 0xFFu) != 0u && (unsigned)(k0 + q - n0) < (unsigned)(n1 - n0);
+                    // the id rows of these 8 nodes are one 128-byte line: requested now, needed by the evaluation below
+                    if ((w2.x | w2.y) != 0u) asm volatile("prefetch.global.L1 [%0];" ::"l"(ngb16f + (size_t)k0 * KDT));
                     unsigned mb[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) mb[q] = __ballot_sync(0xffffffffu, pb[q]);

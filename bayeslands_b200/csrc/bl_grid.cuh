@@ -20,6 +20,8 @@
 //     (atomic arrival counter) sums r and walks on downstream; nobody ever spins;
 //   * SFD ties: first lowest neighbour in slot order E,NE,N,NW,W,SW,S,SE (the builder's neighbour order).
 
+#include <cooperative_groups.h>
+
 namespace grid {
 
 constexpr int CHS = 32;   // ints between the `change` flags of two proposals (one line each: they are stored to by every warp)
@@ -159,15 +161,16 @@ __global__ void k_fill_init(GConst g, int p0)
 
 // one colour pass of the Gauss-Seidel sweep (PDalgo.f90:37-91): one warp per pending bitmap word.  Nodes of one
 // colour are never adjacent, so the pass is race free and equals the sequential sweep over that id range.
-__global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
+// (W, the pending words, the rings and their control words are written by other SMs between passes of the persistent
+// loop below: they are read through L2 - __ldcg - so that no stale L1 line can be seen.)
+__device__ __forceinline__ void fill_pass_body(const GConst &g, int c)
 {
-    if (g.counters[1] == 0) return;
     WlCtl *ctl = (WlCtl *)g.wlctl;
-    const unsigned long long h = ctl[c].head, t = ctl[c].tail;      // nobody appends to colour c during its own pass
+    const unsigned long long h = __ldcg(&ctl[c].head), t = __ldcg(&ctl[c].tail);   // nobody appends to colour c during its own pass
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ctl[c].snap = t;
         const int cp = (c + 3) & 3;
-        ctl[cp].head = ctl[cp].snap;                                // retire what the previous pass consumed
+        ctl[cp].head = __ldcg(&ctl[cp].snap);                       // retire what the previous pass consumed
     }
     const int lane = threadIdx.x & 31;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -197,9 +200,9 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
     auto take_word = [&](unsigned ent, int &p, int &w) -> unsigned {
         p = (int)(ent / (unsigned)g.W0); w = (int)(ent % (unsigned)g.W0);
         unsigned word = 0u;
-        if (__ldg(g.fill_active + p)) {
+        if (__ldcg(g.fill_active + p)) {
             unsigned *L0 = g.l0 + ((size_t)p * 4 + c) * g.W0p + w;
-            if (lane == 0) { word = *L0; if (word) *L0 = 0u; }
+            if (lane == 0) { word = __ldcg(L0); if (word) *L0 = 0u; }
             word = __shfl_sync(0xffffffffu, word, 0);
         }
         return word;
@@ -208,13 +211,13 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
     int pN = 0, wN = 0;
     unsigned wordN = 0u;
     bool more = e < t;
-    if (more) wordN = take_word(ring[e & (g.wlcap - 1)], pN, wN);
+    if (more) wordN = take_word(__ldcg(ring + (e & (g.wlcap - 1))), pN, wN);
     while (more) {
         const int p = pN, w = wN;
         const unsigned word = wordN;
         e += nwarps;
         more = e < t;
-        const unsigned ent2 = more ? ring[e & (g.wlcap - 1)] : 0u;
+        const unsigned ent2 = more ? __ldcg(ring + (e & (g.wlcap - 1))) : 0u;
         int loc = 0, changed = 0;
         double av[8], nwv = 0.;                     // neighbour values in slot order E,NE,N,NW,W,SW,S,SE; the new W
 #pragma unroll
@@ -228,8 +231,9 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
             const size_t L = (size_t)(j + 1) * LXP + (i + 1);
             // all ten loads go out together (a pending node almost always still has W > z)
             const double *r0 = W + L - LXP, *r2 = W + L + LXP;
-            const double wk = W[L], zk = z[L];
-            av[0] = W[L + 1]; av[1] = r2[1]; av[2] = r2[0]; av[3] = r2[-1]; av[4] = W[L - 1]; av[5] = r0[-1]; av[6] = r0[0]; av[7] = r0[1];
+            const double wk = __ldcg(W + L), zk = z[L];
+            av[0] = __ldcg(W + L + 1); av[1] = __ldcg(r2 + 1); av[2] = __ldcg(r2); av[3] = __ldcg(r2 - 1);
+            av[4] = __ldcg(W + L - 1); av[5] = __ldcg(r0 - 1); av[6] = __ldcg(r0); av[7] = __ldcg(r0 + 1);
             if (wk > zk) {
                 double hmin = fmin(fmin(fmin(av[0], av[1]), fmin(av[2], av[3])), fmin(fmin(av[4], av[5]), fmin(av[6], av[7])));
                 hmin = fmin(hmin, 2.e6);
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
                 }
             }
         }
-        if (__any_sync(0xffffffffu, loc) && lane == 0 && g.change[p * CHS] == 0) g.change[p * CHS] = 1;
+        if (__any_sync(0xffffffffu, loc) && lane == 0 && __ldcg(g.change + p * CHS) == 0) g.change[p * CHS] = 1;
     }
     __syncthreads();
     if (threadIdx.x < 4) {
@@ -310,24 +314,43 @@ __global__ void __launch_bounds__(256, 8) k_fill_pass(GConst g, int c)
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x)
             g.wl[(size_t)c2 * g.wlcap + ((s_base[c2] + i) & (g.wlcap - 1))] = s_buf[c2][i];
     }
+    __syncthreads();
 }
 
-// end of a sweep: the reference's `do while (change)` per proposal
-__global__ void k_fill_end(GConst g)
+// end of a sweep: the reference's `do while (change)` per proposal (one block)
+__device__ __forceinline__ void fill_end_body(const GConst &g)
 {
     __shared__ int s_act;
     if (threadIdx.x == 0) s_act = 0;
     __syncthreads();
-    if (threadIdx.x == 0 && g.counters[1] > 0) g.counters[2] += 1;      // sweeps this step (max over proposals)
+    if (threadIdx.x == 0 && __ldcg(g.counters + 1) > 0) g.counters[2] += 1;      // sweeps this step (max over proposals)
     for (int p = threadIdx.x; p < g.B; p += blockDim.x) {
-        if (g.fill_active[p]) {
+        if (__ldcg(g.fill_active + p)) {
             g.sweeps[p] += 1;
-            if (g.change[p * CHS] == 0) g.fill_active[p] = 0; else atomicAdd(&s_act, 1);
+            if (__ldcg(g.change + p * CHS) == 0) g.fill_active[p] = 0; else atomicAdd(&s_act, 1);
             g.change[p * CHS] = 0;
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) g.counters[1] = s_act;
+}
+
+// The whole `do while (change)` loop of a group of proposals in ONE cooperative launch: four colour passes and the
+// end-of-sweep bookkeeping per sweep, separated by grid-wide barriers; the loop ends on the device when no proposal of
+// the group raised `change` (no host round trip, no launch per pass).
+__global__ void __launch_bounds__(256, 8) k_fill_loop(GConst g)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    long long guard = 0;
+    while (__ldcg(g.counters + 1) > 0) {
+        for (int c = 0; c < 4; ++c) {
+            fill_pass_body(g, c);
+            grid.sync();
+        }
+        if (blockIdx.x == 0) fill_end_body(g);
+        grid.sync();
+        if (++guard > 50000000) break;
+    }
 }
 __global__ void k_fill_begin(GConst g)
 {
@@ -686,6 +709,7 @@ struct bl_grid {
     grid::GConst g;
     int device, B, debug;
     int group;                 // proposals per fill group (bl_params.opt_grid_group, default 64)
+    int coop_blocks;           // co-resident blocks of the cooperative fill loop (SMs x occupancy)
     long long launches;
     long long last_sweeps;     // sweeps the previous step's fill needed (first chunk size)
     int *h_counters;           // pinned [4]
@@ -844,6 +868,15 @@ extern "C" int bl_grid_create(const bl_lattice *lt, const bl_params *p, int B, i
     g.stops = ctx->d_stops; g.ckpt = ctx->d_ckpt; g.nstops = 0;
     ctx->device = device; ctx->B = B; ctx->debug = debug; ctx->launches = 0; ctx->last_sweeps = 0;
     ctx->group = (p->opt_grid_group > 0) ? p->opt_grid_group : 64;
+    {
+        int nsm = 148, occ = 1, coop = 0;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (!coop) { g_err = "bl_grid_create: the device does not support cooperative launches"; delete ctx; return BL_ERR_UNSUPPORTED; }
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, grid::k_fill_loop, 256, 0));
+        const int want = (p->opt_debug >> 4) & 15;          // experiment knob: blocks per SM of the fill loop
+        ctx->coop_blocks = nsm * std::max(1, std::min(occ, want ? want : 8));
+    }
     CUDA_OK(cudaMallocHost((void **)&ctx->h_counters, 4 * sizeof(int)));
     *out = ctx;
     return BL_OK;
@@ -882,7 +915,6 @@ int grid_one_step(bl_grid *ctx, double *out_pts, double *out_sse, double *out_el
     // Depression filling, a group of proposals at a time: the pending regions of ~64 landscapes (~100 MB of rows) stay in
     // L2 from pass to pass, those of 256 do not (measured: 5.2 ms per proposal-step at B = 256 in one group, 2.75 at 64)
     const int group = ctx->group;
-    long long most = 0;
     for (int p0 = 0; p0 < B; p0 += group) {
         const int nB = std::min(group, B - p0);
         const long long ntask = (long long)nB * g.W0;
@@ -890,23 +922,14 @@ int grid_one_step(bl_grid *ctx, double *out_pts, double *out_sse, double *out_el
         grid::k_fill_init<<<dim3(g1.x, (unsigned)nB), 256, 0, st>>>(g, p0);
         grid::k_fill_begin<<<1, 256, 0, st>>>(g);
         ctx->launches += 2;
-        long long done = 0, chunk = std::max<long long>(2, std::min<long long>(ctx->last_sweeps, 4096));
-        for (;;) {
-            for (long long s = 0; s < chunk; ++s) {
-                for (int c = 0; c < 4; ++c) grid::k_fill_pass<<<pass_blocks, 256, 0, st>>>(g, c);
-                grid::k_fill_end<<<1, 256, 0, st>>>(g);
-            }
-            ctx->launches += 5 * chunk;
-            done += chunk;
-            CUDA_OK(cudaMemcpyAsync(ctx->h_counters, g.counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUDA_OK(cudaStreamSynchronize(st));
-            if (ctx->h_counters[1] == 0) break;
-            if (done > 50000000) { g_err = "bl_grid: depression filling did not terminate"; return BL_ERR_CUDA; }
-            chunk = std::max<long long>(8, std::min<long long>(done / 4, 1024));
+        {
+            grid::GConst garg = g;
+            void *args[] = {(void *)&garg};
+            CUDA_OK(cudaLaunchCooperativeKernel((const void *)grid::k_fill_loop, dim3((unsigned)std::min<long long>(pass_blocks, ctx->coop_blocks)),
+                                                dim3(256), args, 0, st));
+            ctx->launches += 1;
         }
-        most = std::max<long long>(most, ctx->h_counters[2]);
     }
-    ctx->last_sweeps = most + 1;   // the next step's first chunk: landscapes change slowly
     grid::k_sfd<<<dim3((unsigned)((g.LX + 255) / 256), (unsigned)((g.LY + grid::SROWS - 1) / grid::SROWS), (unsigned)B), b2, 0, st>>>(g);
     grid::k_donors<<<dim3((unsigned)((g.LXP + 255) / 256), (unsigned)((g.LY + grid::SROWS - 1) / grid::SROWS), (unsigned)B), b2, 0, st>>>(g);
     grid::k_discharge<<<g2, b2, 0, st>>>(g);

@@ -28,7 +28,8 @@ class GridEngine:
     """One context = one lattice + one parameter set + B proposals resident on `device`."""
 
     def __init__(self, lat: Lattice, inp, B: int, device: int = 0, real_elev: Optional[np.ndarray] = None,
-                 erdp_coords: Optional[Sequence] = None, debug: bool = False):
+                 erdp_coords: Optional[Sequence] = None, debug: bool = False, fill_group: int = 0,
+                 fill_blocks_per_sm: int = 0):
         if not torch.cuda.is_available():
             raise _lib.BlError("bayeslands_b200.GridEngine needs a CUDA device (no CPU fallback)")
         self.L = _lib.load()
@@ -60,6 +61,8 @@ class GridEngine:
         p.minDT, p.maxDT, p.hill_cfl, p.ms_cfl = inp.minDT, inp.maxDT, d.hill_cfl, d.ms_cfl
         p.diffprop, p.diffnb, p.depo, p.btype = inp.diffprop, inp.diffnb, inp.depo, d.btype
         p.shuffle_mode, p.seapos = 0, inp.seapos
+        p.opt_grid_group = int(fill_group)                  # proposals filled together (0: library default)
+        p.opt_debug = int(fill_blocks_per_sm) << 4          # blocks per SM of the cooperative fill loop (0: occupancy limit)
         if inp.seafile is not None:
             raise _lib.BlError("the lattice engine takes a constant sea level only")
         self.npts = 0

@@ -22,11 +22,13 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--T", type=float, default=50000.0)
     ap.add_argument("--steps", type=int, default=0, help="stop after this many single steps (0: full run)")
+    ap.add_argument("--group", type=int, default=0, help="proposals per fill group (0: default 64)")
+    ap.add_argument("--bps", type=int, default=0, help="blocks per SM of the cooperative fill loop (0: occupancy limit)")
     a = ap.parse_args()
     t0 = time.time()
     lat, inp = synthetic.build(a.nx, a.ny, T=a.T)
     rain, erod = synthetic.proposals(a.batch)
-    eng = GridEngine(lat, inp, a.batch)
+    eng = GridEngine(lat, inp, a.batch, fill_group=a.group, fill_blocks_per_sm=a.bps)
     eng.reset(rain, erod)
     torch.cuda.synchronize()
     print("setup %.1f s, workspace %.2f GB" % (time.time() - t0, eng.workspace.numel() / 1e9), flush=True)
