@@ -30,7 +30,7 @@ FIELDS = dict(z=F_Z, cumdiff=F_CUMDIFF, cumhill=F_CUMHILL, fillH=F_FILLH, maxh=F
 
 ST_CASCADE_GUARD, ST_DRAIN_CYCLE, ST_NAN = 1, 4, 8
 ST_FATAL = ST_CASCADE_GUARD | ST_NAN      # evaluations whose result must not enter Metropolis
-OPT_FORCE_GENERIC, OPT_NO_L2_PERSIST, OPT_LEAN = 1, 2, 4
+OPT_FORCE_GENERIC, OPT_NO_L2_PERSIST, OPT_LEAN, OPT_COMPACT, OPT_NO_COMPACT = 1, 2, 4, 8, 16
 
 
 class BlMesh(C.Structure):
@@ -58,7 +58,7 @@ class BlLattice(C.Structure):
 
 
 EXPORTS = ("bl_last_error", "bl_version", "bl_workspace_bytes", "bl_ctx_create", "bl_ctx_destroy", "bl_reset",
-           "bl_run", "bl_step", "bl_get_field", "bl_get_scalars", "bl_get_phase_cycles", "bl_launch_count",
+           "bl_run", "bl_step", "bl_get_field", "bl_get_scalars", "bl_get_phase_cycles", "bl_launch_count", "bl_ctx_info",
            "bl_fill", "bl_sfd", "bl_stack", "bl_discharge", "bl_basins", "bl_drainage", "bl_streampower", "bl_diffuse",
            "bl_interp",
            "bl_grid_workspace_bytes", "bl_grid_create", "bl_grid_destroy", "bl_grid_reset", "bl_grid_run",
@@ -99,6 +99,8 @@ def load():
     L.bl_get_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.bl_launch_count.restype = C.c_int64
     L.bl_launch_count.argtypes = [C.c_void_p]
+    L.bl_ctx_info.restype = C.c_int
+    L.bl_ctx_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
     vp, dbl, i32, u64, i64 = C.c_void_p, C.c_double, C.c_int, C.c_uint64, C.c_int64
     L.bl_fill.argtypes = [vp, vp, dbl, vp, vp]
     L.bl_sfd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]

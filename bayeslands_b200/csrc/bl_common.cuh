@@ -36,6 +36,8 @@ struct DevConst {
     const float *ve32;          // [N][KDT][2] (vor, edge) as float pairs when both are float32-representable, else null
     int lev_contig;             // lev_nodes[i] == bounds + i (colour-major numbering)
     int dbg;                    // BL_DEBUG experiments (timing only)
+    int compact;                // 8-bytes-per-node shared-memory layout (bl_fastc.cuh): two landscapes per SM
+    const unsigned *nbf2;       // [N] bit p = neighbour slot p is an inside node (borders2): the diffusion's neighbour test
     const double *vor, *edge;   // [KD][N]
     const double *area, *xy;    // [N], [N][2]
     const unsigned char *flags; // bit0 borders, bit1 borders2, bit2 indomain
@@ -142,7 +144,8 @@ struct StageArgs {
     cudaError_t bl_launch_run_##NS(int KDT, const DevConst &c, int B, int dyn, cudaStream_t st, const RunArgs &a);       \
     cudaError_t bl_launch_reset_##NS(const DevConst &c, int B, cudaStream_t st, const double *rain, const double *erod,  \
                                      const unsigned long long *seed, double tStart);                                     \
-    cudaError_t bl_func_attr_##NS(int KDT, cudaFuncAttributes *attr);
+    cudaError_t bl_func_attr_##NS(int KDT, cudaFuncAttributes *attr);                                                     \
+    cudaError_t bl_occupancy_##NS(int KDT, int dyn, int *nres);
 BL_DECL_VARIANT(v1024)
 cudaError_t bl_launch_stage_v1024(int KDT, const DevConst &c, int dyn, cudaStream_t st, const StageArgs &a);
 cudaError_t bl_launch_stage_v256(int KDT, const DevConst &c, int dyn, cudaStream_t st, const StageArgs &a);

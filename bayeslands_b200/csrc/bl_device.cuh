@@ -1410,6 +1410,7 @@ __device__ void time_step(const DevConst &c, Smem &S)
 }
 
 #include "bl_fast.cuh"
+#include "bl_fastc.cuh"
 
 // bl_mcmc.interpolateArray (bl_mcmc.py:198-213) on the mesh-constant k=3 table
 __device__ inline double interp_cell(const DevConst &c, const double *v, int g)
@@ -1454,7 +1455,10 @@ bl_run_kernel(const DevConst cpar, int nstops, const double *__restrict__ stops,
         if (tid == 0) S.tStop = stops[s];
         __syncthreads();
         while (S.tNow < S.tStop) {
-            if (KDT > 0) fast::time_step<(KDT > 0 ? KDT : 8)>(c, S, dsm);
+            if (KDT > 0) {
+                if (c.compact) fastc::time_step<(KDT > 0 ? KDT : 8)>(c, S, dsm);
+                else fast::time_step<(KDT > 0 ? KDT : 8)>(c, S, dsm);
+            }
             else time_step(c, S);
             if (single_step) break;
         }

@@ -29,6 +29,8 @@ struct bl_ctx {
     int l2_persist;       // bl_params.opt_flags & BL_OPT_NO_L2_PERSIST == 0
     int dyn_max;          // dynamic shared memory one CTA of the chosen kernel may use (opt-in limit - static)
     int dyn;              // dynamic shared memory of a launch
+    int compact;          // compact shared-memory layout (two landscapes per SM)
+    size_t need_full;     // dynamic shared memory of the 17-bytes-per-node layout (per-stage kernels)
     // stop times / checkpoint ids travel through context-owned pinned slots (no stream synchronisation per launch)
     static constexpr int NSLOT = 4;
     char *h_stage;        // [NSLOT][STOPS_CAP * 12] pinned
@@ -47,7 +49,7 @@ extern "C" int bl_version(void) { return 100; }
 
 namespace {
 struct Layout {
-    size_t off_ve32, off_ngb16, off_ngb16f, off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
+    size_t off_nbf2, off_ve32, off_ngb16, off_ngb16f, off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
         off_levo, off_gidx, off_gw, off_gex, off_real, off_pts, off_seat, off_seav, off_rain, off_erod, off_seed,
         off_tnow, off_lastdt, off_steps, off_status, off_phase, off_stops, off_ckpt, off_prop, total;
     int KD, nlev;
@@ -78,6 +80,9 @@ size_t fast_smem_need(int Nq, int KDT, bool marine)
     return need;
 }
 
+// the compact layout (bl_fastc.cuh): 8 bytes per node, one bit per node, the fill's slot lists (256 bytes per sweeping warp)
+size_t compact_smem_need(int Nq, int tpb) { return (size_t)8 * Nq + Nq / 8 + (size_t)(tpb / 64) * 256 + 64; }
+
 cudaError_t func_attr(int tpb, int KDT, cudaFuncAttributes *fa)
 {
     if (tpb == 256) return bl_func_attr_v256(KDT, fa);
@@ -101,6 +106,7 @@ Layout make_layout(const bl_mesh *m, const bl_params *p, int B, int KD, int nlev
     L.off_area = take(N * 8);
     L.off_xy = take(N * 16);
     L.off_flags = take(N);
+    L.off_nbf2 = take(N * 4);
     L.off_parent = take((size_t)std::max(1, m->bounds) * 4);
     L.off_z0 = take(N * 8);
     L.off_disp = take(N * 8);
@@ -201,21 +207,49 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     // CTA size and device path.  The shared-memory path needs fast_smem_need() bytes of dynamic shared memory; what a CTA
     // may use is the device's opt-in limit minus the kernel's static shared memory (queried, not assumed).
     const int kdt_want = (KD <= 8) ? 8 : (KD <= 12 ? 12 : 20);
-    int tpb = (N <= 4096) ? 256 : 1024;
-    if (p->opt_tpb == 256 || p->opt_tpb == 512 || p->opt_tpb == 768 || p->opt_tpb == 1024) tpb = p->opt_tpb;
-    else if (p->opt_tpb != 0) { g_err = "bl_ctx_create: opt_tpb must be 0, 256, 512, 768 or 1024"; return BL_ERR_ARG; }
-    int dyn_max = 0;
-    {
-        int optin = 0;
-        CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (p->opt_tpb != 0 && p->opt_tpb != 256 && p->opt_tpb != 512 && p->opt_tpb != 768 && p->opt_tpb != 1024) {
+        g_err = "bl_ctx_create: opt_tpb must be 0, 256, 512, 768 or 1024"; return BL_ERR_ARG;
+    }
+    int optin = 0, smem_sm = 0, smem_res = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CUDA_OK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    CUDA_OK(cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, device));
+    int static_smem[1025] = {0};
+    for (int t : {256, 512, 768, 1024}) {
         cudaFuncAttributes fa;
         memset(&fa, 0, sizeof(fa));
-        CUDA_OK(func_attr(tpb, kdt_want, &fa));
-        dyn_max = (optin - (int)fa.sharedSizeBytes) / 1024 * 1024;
+        CUDA_OK(func_attr(t, kdt_want, &fa));
+        static_smem[t] = (int)fa.sharedSizeBytes;
     }
+    // does the mesh numbering put the Gauss-Seidel levels in contiguous id ranges (mesh.py does)?
+    bool lev_contig_h = true;
+    for (int k = m->bounds + 1; k < N; ++k) if (level[k] < level[k - 1]) { lev_contig_h = false; break; }
+    const bool marine_cfg = (p->CDr > 0. || p->nsea > 0);
+    const bool small_ids = (N < 32760 && nlev <= LEVMAX);
+    const size_t need_full = fast_smem_need(Nq, kdt_want, false), need_c512 = compact_smem_need(Nq, 512);
+    auto fits = [&](int t, size_t need, int nres) {        // nres CTAs of t threads resident on one SM with `need` bytes each
+        return (size_t)nres * (static_smem[t] + rup(need, 1024) + smem_res) <= (size_t)smem_sm &&
+               static_smem[t] + rup(need, 1024) <= (size_t)optin;
+    };
+    const bool compact_ok = small_ids && lev_contig_h && !marine_cfg && !(p->opt_flags & BL_OPT_NO_COMPACT);
+    // CTA size and layout: small meshes 256 threads (several CTAs per SM); else two 512-thread CTAs per SM when two
+    // landscapes fit - in the 17-bytes-per-node layout or in the compact one - else one 1024-thread CTA per SM
+    int tpb, compact = 0;
+    if (p->opt_tpb) tpb = p->opt_tpb;
+    else if (N <= 4096) tpb = 256;
+    else if (small_ids && fits(512, need_full, 2)) tpb = 512;
+    else if (compact_ok && fits(512, need_c512, 2)) tpb = 512;
+    else tpb = 1024;
+    if (compact_ok) {
+        if (p->opt_flags & BL_OPT_COMPACT) compact = fits(tpb, compact_smem_need(Nq, tpb), 1) ? 1 : 0;
+        else if (tpb == 512 && !fits(512, need_full, 2) && fits(512, need_c512, 2)) compact = 1;
+    }
+    const size_t need_c = compact_smem_need(Nq, tpb);
+    const int dyn_max = (optin - static_smem[tpb]) / 1024 * 1024;
     int KDT = 0;
-    if (N < 32760 && nlev <= LEVMAX && fast_smem_need(Nq, kdt_want, false) <= (size_t)dyn_max) KDT = kdt_want;
-    if (p->opt_flags & BL_OPT_FORCE_GENERIC) KDT = 0;
+    if (small_ids && (compact ? need_c : need_full) <= (size_t)dyn_max) KDT = kdt_want;
+    if (p->opt_flags & BL_OPT_FORCE_GENERIC) { KDT = 0; compact = 0; }
+    if (!KDT) compact = 0;
     const int KDrow = KDT ? KDT : BL_KP;
     std::vector<unsigned short> ngb16((size_t)BL_KP * Nq, 0xFFFFu);
     for (int i = 0; i < N; ++i)
@@ -245,6 +279,13 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     std::vector<unsigned char> flags(N);
     for (int i = 0; i < N; ++i)
         flags[i] = (unsigned char)((m->borders[i] ? 1 : 0) | (m->borders2[i] ? 2 : 0) | (m->indomain[i] ? 4 : 0));
+    std::vector<unsigned> nbf2(N, 0u);
+    for (int i = 0; i < N; ++i)
+        for (int q = 0; q < KD; ++q) {
+            int j = m->ngb[(size_t)i * BL_KP + q];
+            if (j < 0) break;
+            if (m->borders2[j]) nbf2[i] |= 1u << q;
+        }
     std::vector<int> levn, levo(nlev + 1, 0);
     {
         std::vector<int> cntl(nlev + 1, 0);
@@ -264,6 +305,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     UP(L.off_area, m->area, (size_t)N * 8);
     UP(L.off_xy, m->xy, (size_t)N * 16);
     UP(L.off_flags, flags.data(), (size_t)N);
+    UP(L.off_nbf2, nbf2.data(), (size_t)N * 4);
     if (m->bounds > 0) UP(L.off_parent, m->parent, (size_t)m->bounds * 4);
     UP(L.off_z0, m->z0, (size_t)N * 8);
     if (m->disp) UP(L.off_disp, m->disp, (size_t)N * 8);
@@ -296,6 +338,8 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     c.area = (const double *)(ws + L.off_area);
     c.xy = (const double *)(ws + L.off_xy);
     c.flags = (const unsigned char *)(ws + L.off_flags);
+    c.nbf2 = (const unsigned *)(ws + L.off_nbf2);
+    c.compact = compact;
     c.parent = (const int *)(ws + L.off_parent);
     c.z0 = (const double *)(ws + L.off_z0);
     c.disp = m->disp ? (const double *)(ws + L.off_disp) : nullptr;
@@ -322,12 +366,14 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     c.status = (unsigned *)(ws + L.off_status);
     c.phase_cyc = (long long *)(ws + L.off_phase);
     ctx->tpb = (KDT == 0 && p->opt_tpb == 0) ? 1024 : tpb;
+    ctx->compact = compact;
+    ctx->need_full = rup(need_full, 1024);
     ctx->l2_persist = (p->opt_flags & BL_OPT_NO_L2_PERSIST) ? 0 : 1;
     ctx->dyn_max = dyn_max;
     {   // dynamic shared memory of a launch: what the phases of this configuration need; the marine phases (etopo configs)
         // stage more when it fits and fall back to their global-memory form otherwise (bl_device.cuh: dsm_bytes tests)
         const bool marine = (p->CDr > 0. || p->nsea > 0);
-        size_t need = fast_smem_need(Nq, KDT, false);
+        size_t need = compact ? compact_smem_need(Nq, tpb) : fast_smem_need(Nq, KDT, false);
         if (marine) need = std::max(need, std::min(fast_smem_need(Nq, KDT, true), (size_t)dyn_max));
         ctx->dyn = KDT ? (int)std::min((size_t)dyn_max, rup(need, 1024)) : 0;
         if (KDT && (p->opt_debug & 1)) ctx->dyn = dyn_max;     // experiment: one CTA per SM whatever the mesh size
@@ -528,20 +574,22 @@ Slot0 slot0(const bl_ctx *ctx)
 }
 int stage_launch(bl_ctx *ctx, const StageArgs &a, cudaStream_t st)
 {
-    // the 256-thread unit serves the contexts that run 256-thread CTAs, the 1024-thread unit all others
-    if (ctx->tpb == 256) CUDA_OK(bl_launch_stage_v256(ctx->c.KDT, ctx->c, ctx->dyn, st, a));
-    else {
-        int dyn = ctx->dyn;
-        if (ctx->c.KDT && ctx->tpb != 1024) {      // dyn_max was derived for another unit's static shared memory
-            cudaFuncAttributes fa;
-            memset(&fa, 0, sizeof(fa));
-            int optin = 0;
-            CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-            CUDA_OK(bl_func_attr_v1024(ctx->c.KDT, &fa));
-            dyn = std::min(dyn, (optin - (int)fa.sharedSizeBytes) / 1024 * 1024);
-        }
-        CUDA_OK(bl_launch_stage_v1024(ctx->c.KDT, ctx->c, dyn, st, a));
+    // the 256-thread unit serves the contexts that run 256-thread CTAs, the 1024-thread unit all others; the stage
+    // kernels use the 17-bytes-per-node layout (or the generic path when that does not fit the unit)
+    const bool small = (ctx->tpb == 256);
+    int KDT = ctx->c.KDT, dyn = 0;
+    if (KDT) {
+        cudaFuncAttributes fa;
+        memset(&fa, 0, sizeof(fa));
+        int optin = 0;
+        CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        CUDA_OK(small ? bl_func_attr_v256(KDT, &fa) : bl_func_attr_v1024(KDT, &fa));
+        const int avail = (optin - (int)fa.sharedSizeBytes) / 1024 * 1024;
+        if (ctx->need_full > (size_t)avail) KDT = 0;
+        else dyn = (int)std::min((size_t)avail, std::max(ctx->need_full, (size_t)(ctx->compact ? 0 : ctx->dyn)));
     }
+    if (small) CUDA_OK(bl_launch_stage_v256(KDT, ctx->c, dyn, st, a));
+    else CUDA_OK(bl_launch_stage_v1024(KDT, ctx->c, dyn, st, a));
     ctx->launches++;
     return BL_OK;
 }
@@ -705,4 +753,20 @@ extern "C" int bl_interp(bl_ctx *ctx, const double *v, double *grid, void *strea
 }
 
 extern "C" int64_t bl_launch_count(const bl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int bl_ctx_info(const bl_ctx *ctx, int32_t info[4])
+{
+    if (!ctx || !info) { g_err = "bl_ctx_info: null argument"; return BL_ERR_ARG; }
+    CUDA_OK(cudaSetDevice(ctx->device));
+    info[0] = ctx->tpb;
+    info[1] = ctx->c.KDT ? (ctx->compact ? 2 : 1) : 0;
+    info[2] = ctx->dyn;
+    int nres = 0;
+    if (ctx->tpb == 256) CUDA_OK(bl_occupancy_v256(ctx->c.KDT, ctx->dyn, &nres));
+    else if (ctx->tpb == 512) CUDA_OK(bl_occupancy_v512(ctx->c.KDT, ctx->dyn, &nres));
+    else if (ctx->tpb == 768) CUDA_OK(bl_occupancy_v768(ctx->c.KDT, ctx->dyn, &nres));
+    else CUDA_OK(bl_occupancy_v1024(ctx->c.KDT, ctx->dyn, &nres));
+    info[3] = nres;
+    return BL_OK;
+}
 

@@ -1,0 +1,1011 @@
+// bl_fastc.cuh - "compact" shared-memory time step (included by bl_device.cuh after bl_fast.cuh).
+//
+// bl_fast.cuh keeps 17 bytes of shared memory per node, so a 12.7 k-node landscape owns an SM: one CTA, and nothing to
+// hide its barrier waits (38 % of the warp samples, profiles/r02x_stalls_by_line.txt).  The phases below compute the
+// same values in the same fp64 operation order with at most 8 bytes per node (+ bitmaps) in shared memory, so that TWO
+// 512-thread CTAs - two landscapes - are resident per SM and one runs while the other waits:
+//   fill            W fp64 in shared memory, pending set as one BIT per node (woken with red.shared.or), z read from L2
+//   receivers       two passes over the same 8N bytes (W, then z)
+//   stack order     links built against receivers in shared memory (2N), the Euler tour written to global scratch and
+//                   brought back as (next:16 | rank:16) words for the ranking (8N)
+//   basins          root ids (2N), then the stack-ordered volume terms (8N) in the same bytes
+//   discharge / stream power
+//                   node values fp64 indexed by BREADTH-FIRST POSITION: the depth-first stack is stably sorted by depth,
+//                   which puts the donors of a node next to each other (ascending id), so a node sums the contiguous
+//                   run vals[fc .. fc+cnt) backwards - no donor links, no bucket order, no receiver ids in shared memory.
+//                   (first child, donor count, rule) live in one global word per position, fetched one level ahead.
+//   diffusion       z fp64 (8N); the "neighbour is inside" test comes from a per-node bit mask (mesh constant)
+// Selected by bl_ctx_create (DevConst::compact) for non-marine configurations on colour-major meshes.
+
+namespace fastc {
+
+using namespace fast;
+
+__device__ __forceinline__ unsigned lds_u32(unsigned a)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_or_if(bool p, unsigned a, unsigned v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q red.shared.or.b32 [%1], %2;\n\t}" ::"r"((unsigned)p), "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_and(unsigned a, unsigned v) { asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// dynamic shared memory of the compact layout: 8 bytes per node, one bit per node, the fill's per-warp slot lists
+__device__ __forceinline__ unsigned char *tail_of(unsigned char *dsm, int Nq) { return dsm + (size_t)8 * Nq + Nq / 8; }
+
+// ---- depression filling (PDalgo.f90:19-91), literal Gauss-Seidel sweep by level, see fast::fill_bitmap -------------
+template <int KDT>
+__device__ __forceinline__ void fill_eval_c(const unsigned short *__restrict__ ngb16f, const double *__restrict__ zg, int k,
+                                            unsigned aW, unsigned aB, double sea, double eps, double TH, int &loc)
+{
+    Ids<KDT> ids;        // empty slots hold the dummy node N, whose W is 2e6 (DevConst::ngb16f)
+    {
+        const uint2 *src = reinterpret_cast<const uint2 *>(ngb16f + (size_t)k * KDT);
+#pragma unroll
+        for (int q = 0; q < KDT / 4; ++q) { const uint2 v = __ldg(src + q); ids.w[2 * q] = v.x; ids.w[2 * q + 1] = v.y; }
+    }
+    const double zk = zg[k];                     // constant during the fill; requested together with the id row
+    const unsigned ak = aW + 8u * (unsigned)k;
+    const double wk = lds_f64(ak);
+    double hmin = 2.e6;
+    double wj[KDT];
+#pragma unroll
+    for (int p = 0; p < KDT; ++p) wj[p] = lds_f64(aW + 8u * ids.get(p));
+#pragma unroll
+    for (int p0 = 0; p0 < KDT; p0 += 4) hmin = fmin(hmin, fmin(fmin(wj[p0], wj[p0 + 1]), fmin(wj[p0 + 2], wj[p0 + 3])));
+    const double he = hmin + eps;
+    const bool wet = wk > zk, dry = zk >= he, lower = wk > he;
+    const double floor_ = (zk >= sea) ? zk : sea;
+    const bool capped = (he - floor_) > TH;
+    const double nlow = capped ? floor_ + TH : he;
+    const double nw = wet ? (dry ? zk : (lower ? nlow : wk)) : wk;
+    if (wet && !dry && lower && !capped) loc = 1;
+    if (nw != wk) {
+        sts_f64(ak, nw);
+        const double lim = nw + eps;             // wake only the neighbours this change can move (fast::fill_eval)
+        if (KDT > 8) {
+#pragma unroll
+            for (int p = 0; p < KDT; ++p) wj[p] = lds_f64(aW + 8u * ids.get(p));
+        }
+#pragma unroll
+        for (int p = 0; p < KDT; ++p) {
+            const unsigned j = ids.get(p);
+            red_or_if(wj[p] > lim, aB + 4u * (j >> 5), 1u << (j & 31));
+        }
+    }
+}
+
+template <int KDT>
+__device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *dsm, double sea)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x, nb = c.bounds;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWF = (NWARP >= 2) ? NWARP / 2 : 1;      // sweeping warps (see fast::fill_bitmap)
+    const double *__restrict__ zg = S.P.f[F_Z];
+    {
+        double *W = (double *)dsm;
+        unsigned *bits = (unsigned *)(dsm + (size_t)8 * Nq);
+#pragma unroll 4
+        for (int i = tid; i < N; i += TPB) W[i] = (i < nb) ? zg[i] : 1.e6;
+        if (tid == 0) W[N] = 2.e6;                          // the dummy neighbour of empty slots
+        for (int w = tid; w < Nq / 32; w += TPB) {          // every interior node starts pending
+            const int lo = w * 32;
+            unsigned m = 0u;
+            if (lo + 32 > nb && lo < N) {
+                m = 0xffffffffu;
+                if (lo < nb) m &= 0xffffffffu << (nb - lo);
+                if (lo + 32 > N) m &= 0xffffffffu >> (lo + 32 - N);
+            }
+            bits[w] = m;
+        }
+    }
+    __syncthreads();
+    const unsigned aW = s32(dsm), aB = aW + 8u * (unsigned)Nq;
+    const unsigned aL = aB + (unsigned)(Nq / 8) + (unsigned)warp * 256u;   // [NWF][256] slot list of this warp
+    const unsigned short *ngb16f = c.ngb16f;
+    const double eps = c.eps, TH = c.TH;
+    const int nlev = c.nlev;
+    const unsigned lt = (1u << lane) - 1u;
+    int change = 1;
+    while (change) {
+        int loc = 0;
+        for (int l = 0; l < nlev; ++l) {
+            const int n0 = nb + S.lev_off[l], n1 = nb + S.lev_off[l + 1];     // node id range of the level
+            if (warp < NWF && n1 > n0) {
+                const int whi = (n1 - 1) >> 5;
+                // a batch = 8 bitmap words of this warp (word w0 + NWF * t belongs to lane t): 256 candidate ids
+                for (int w0 = (n0 >> 5) + warp; w0 <= whi; w0 += 8 * NWF) {
+                    unsigned mine = 0u;
+                    const int wi = w0 + NWF * lane;
+                    if (lane < 8 && wi <= whi) {
+                        const int lo = wi * 32;
+                        unsigned m = 0xffffffffu;            // bits of other levels in the boundary words are not ours
+                        if (lo < n0) m &= 0xffffffffu << (n0 - lo);
+                        if (lo + 32 > n1) m &= 0xffffffffu >> (lo + 32 - n1);
+                        const unsigned a = aB + 4u * (unsigned)wi;
+                        mine = lds_u32(a) & m;               // nobody sets a bit of this level during its own pass
+                        if (mine) {
+                            red_and(a, ~mine);
+                            // z and the id rows of these 32 nodes: requested now, needed by the evaluation below
+                            const char *pz = (const char *)(zg + lo);
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(pz));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(pz + 128));
+                            const char *pi = (const char *)(ngb16f + (size_t)lo * KDT);
+#pragma unroll
+                            for (int u = 0; u < KDT / 2; ++u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pi + 128 * u));
+                        }
+                    }
+                    int off = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const unsigned wb = __shfl_sync(0xffffffffu, mine, t);
+                        sts_u8_if((wb >> lane) & 1u, aL + (unsigned)(off + __popc(wb & lt)), (unsigned)(t * 32 + lane));
+                        off += __popc(wb);
+                    }
+                    __syncwarp();
+                    for (int i = lane; i < off; i += 32) {
+                        const int s = (int)lds_u8(aL + (unsigned)i);
+                        fill_eval_c<KDT>(ngb16f, zg, (w0 + NWF * (s >> 5)) * 32 + (s & 31), aW, aB, sea, eps, TH, loc);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (l + 1 < nlev) __syncthreads();
+        }
+        change = __syncthreads_or(loc);
+    }
+}
+
+// sfd.c:55-153: receivers on the filled surface (W is still in shared memory), then on the real one (z staged in the
+// same bytes).  Same slot order and strict comparisons as fast::fill_receivers.
+template <int KDT>
+__device__ __noinline__ void receivers_c(const DevConst &c, Smem &S, unsigned char *dsm, double sea, int &any_marine)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
+    const int N = c.N, tid = threadIdx.x;
+    double *A = (double *)dsm;
+    int *__restrict__ rcv = S.P.i[I_RCV], *__restrict__ rcv1 = S.P.i[I_RCV1];
+    double *__restrict__ maxh = S.P.f[F_MAXH], *__restrict__ fillH = S.P.f[F_FILLH];
+    const double *__restrict__ zg = S.P.f[F_Z];
+    int mar = 0;
+#pragma unroll 2
+    for (int g = tid; g < N; g += TPB) {
+        Ids<KDT> ids;
+        load_ids<KDT>(c, g, ids);
+        const double wg = A[g];
+        int low = g;
+        double wl = wg;
+#pragma unroll
+        for (int p = 0; p < KDT; ++p) {
+            if (ids.get(p) == NONE16) continue;
+            const int j = ids.get(p);
+            const double wj = A[j];
+            if (wj < wl) { low = j; wl = wj; }
+        }
+        rcv[g] = low;
+        fillH[g] = wg;
+        mar |= (wg < sea);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = tid; i < N; i += TPB) A[i] = zg[i];
+    __syncthreads();
+#pragma unroll 2
+    for (int g = tid; g < N; g += TPB) {
+        Ids<KDT> ids;
+        load_ids<KDT>(c, g, ids);
+        const double z0 = A[g];
+        int low1 = g;
+        double zl = z0, dH = 1.e6;
+#pragma unroll
+        for (int p = 0; p < KDT; ++p) {
+            if (ids.get(p) == NONE16) continue;
+            const int j = ids.get(p);
+            const double zj = A[j];
+            if (zj < zl) { low1 = j; zl = zj; }
+            const double dh = zj - z0;
+            if (dh >= 0. && dh < dH) dH = dh;
+        }
+        rcv1[g] = low1;
+        if (dH > 9.99e5) dH = 0.;
+        maxh[g] = dH;
+    }
+    any_marine = __syncthreads_or(mar);
+}
+
+// ---- stack order (FLWnetwork.f90:21-71, FLOWstack.f90:24-40), see fast::links_stack -------------------------------
+// The link construction needs the receivers (2N) in shared memory, the ranking the tour (8N): the tour words are written
+// to global scratch while the receivers are in place and come back with one coalesced copy.
+template <int KDT>
+__device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned char *dsm, const int *rcvg, int *stack, int *pos,
+                                           int *baselist, int &nbase, bool filled, bool shuffle, unsigned long long seedstep)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    unsigned short *r16 = (unsigned short *)dsm;                                  // [Nq]
+    unsigned long long *K = (unsigned long long *)(dsm + (size_t)2 * Nq + 64);    // shuffle keys behind the receivers
+    const int kcap = (int)(((size_t)6 * Nq - 128) / 8);
+    unsigned *eug = (unsigned *)S.P.euA;                                          // [2N] tour words, global scratch
+#pragma unroll 4
+    for (int v = tid; v < N; v += TPB) r16[v] = (unsigned short)rcvg[v];
+    __syncthreads();
+    unsigned char *cnt8 = (unsigned char *)S.P.i[I_CNT];
+#pragma unroll 2
+    for (int v = tid; v < N; v += TPB) {
+        Ids<KDT> ids, jds;
+        const int r = r16[v];
+        load_ids<KDT>(c, v, ids);
+        load_ids<KDT>(c, r, jds);
+        int f = NONE16, n = 0;
+#pragma unroll
+        for (int p = 0; p < KDT; ++p) {
+            if (ids.get(p) == NONE16) continue;
+            const int w = ids.get(p);
+            if (r16[w] == v) { ++n; if (w < f) f = w; }
+        }
+        int nx = NONE16;
+        if (r != v) {
+#pragma unroll
+            for (int p = 0; p < KDT; ++p) {
+                if (jds.get(p) == NONE16) continue;
+                const int w = jds.get(p);
+                if (w > v && w < nx && r16[w] == r) nx = w;
+            }
+        }
+        eug[2 * v] = ((unsigned)((f != NONE16) ? 2 * f : 2 * v + 1) << 16) | 1u;
+        if (r != v) eug[2 * v + 1] = ((unsigned)((nx != NONE16) ? 2 * nx : 2 * r + 1) << 16);
+        if (filled) cnt8[v] = (unsigned char)n;           // donor counts: the breadth-first layout of discharge_c
+    }
+    nbase = blk_compact(N, baselist, [&](int i) { return r16[i] == i; }, S);
+    if (tid == 0) { if (filled) S.nbase = nbase; else S.nbase1 = nbase; }
+    if (shuffle && nbase > 1) {
+        int n2 = 1;
+        while (n2 < nbase) n2 <<= 1;
+        unsigned long long *KK = (n2 <= kcap) ? K : S.P.keys;
+        for (int i = tid; i < n2; i += TPB)
+            KK[i] = (i < nbase) ? (((mix64(seedstep ^ (unsigned long long)(unsigned)baselist[i]) >> 32) << 32) |
+                                   (unsigned)baselist[i])
+                                : ~0ull;
+        __syncthreads();
+        blk_bitonic(KK, n2);
+        for (int i = tid; i < nbase; i += TPB) baselist[i] = (int)(unsigned)(KK[i] & 0xFFFFFFFFull);
+        __syncthreads();
+    }
+    int *nsroot = S.P.i[I_NS];
+    for (int i = tid; i < nbase; i += TPB) {
+        const int root = baselist[i];
+        const int nxt = (i + 1 < nbase) ? baselist[i + 1] : NONE_I;
+        eug[2 * root + 1] = ((nxt != NONE_I) ? (unsigned)(2 * nxt) : END16) << 16;
+        if (!filled) nsroot[root] = nxt;
+    }
+    __syncthreads();
+    unsigned *eu = (unsigned *)dsm;                                  // [2N]
+    const int M = 2 * N;
+    {
+        const uint2 *src = reinterpret_cast<const uint2 *>(eug);
+        uint2 *dst = reinterpret_cast<uint2 *>(eu);
+#pragma unroll 4
+        for (int e = tid; e < N; e += TPB) dst[e] = src[e];
+    }
+    __syncthreads();
+    int active = 1;
+    while (active) {
+        int loc = 0;
+        for (int e0 = tid; e0 < M; e0 += 4 * TPB) {
+            unsigned w[4], nx[4], w2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int e = e0 + u * TPB; w[u] = (e < M) ? eu[e] : 0xFFFF0000u; nx[u] = w[u] >> 16; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) w2[u] = (nx[u] != END16) ? eu[nx[u]] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (nx[u] != END16) { eu[e0 + u * TPB] = (w2[u] & 0xFFFF0000u) | ((w[u] + w2[u]) & 0xFFFFu); loc = 1; }
+        }
+        active = __syncthreads_or(loc);
+    }
+    for (int v = tid; v < N; v += TPB) {
+        const int p = N - (int)(eu[2 * v] & 0xFFFFu);
+        pos[v] = p;
+        stack[p] = v;
+    }
+    __syncthreads();
+}
+
+// ---- pit ids and volumes (FLOWalgo.f90:130-165), see fast::basins ---------------------------------------------------
+// Root ids (2N) and the stack-ordered volume terms (8N) share the same bytes.  A basin's volume is the sequential sum
+// over its stack segment; a dry node contributes +0.0, which never changes the running sum (it starts at -1 and only
+// non-negative terms are added, so it is never -0), hence long segments are read 32 positions at a time by one warp
+// and only the non-zero terms are added, in order.
+__device__ __noinline__ void basins_c(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned short *root16 = (unsigned short *)dsm;          // [Nq]
+    double *val = (double *)dsm;                             // [Nq], after the roots are consumed
+    unsigned short *queue = (unsigned short *)tail_of(dsm, Nq);   // (lo, hi, root) of the long segments
+    constexpr int QCAP = (NWARP / 2) * 256 / 6;
+    const double *__restrict__ z = S.P.f[F_Z], *__restrict__ W = S.P.f[F_FILLH];
+    const int *__restrict__ rcv1 = S.P.i[I_RCV1], *__restrict__ pos1 = S.P.i[I_POS1], *__restrict__ ns1 = S.P.i[I_NS];
+    int *__restrict__ pitID = S.P.i[I_PITID];
+    double *__restrict__ pitVol = S.P.f[F_PITVOL];
+#pragma unroll 4
+    for (int v = tid; v < N; v += TPB) root16[v] = (unsigned short)rcv1[v];
+    if (tid == 0) S.ibuf[4] = 0;
+    __syncthreads();
+    int ch = 1;
+    while (ch) {
+        int loc = 0;
+        for (int v = tid; v < N; v += TPB) {
+            const unsigned short r = root16[v], rr = root16[r];
+            if (rr != r) { root16[v] = rr; loc = 1; }
+        }
+        ch = __syncthreads_or(loc);
+    }
+#pragma unroll 2
+    for (int v = tid; v < N; v += TPB) {
+        const bool wet = W[v] > z[v];
+        const int root = root16[v];
+        pitID[v] = (wet || root == v) ? root : -1;
+        pitVol[v] = -1.0;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int v = tid; v < N; v += TPB) {
+        const double wv = W[v], zv = z[v];
+        val[pos1[v]] = (wv > zv) ? (wv - zv) * c.area[v] : 0.0;
+    }
+    __syncthreads();
+    for (int i = tid; i < nbase1; i += TPB) {
+        const int root = base1[i];
+        const int lo = pos1[root];
+        const int nr = ns1[root];
+        const int hi = (nr != NONE_I) ? pos1[nr] : N;
+        int slot = QCAP;
+        if (hi - lo > 24) slot = atomicAdd(&S.ibuf[4], 1);
+        if (slot < QCAP) { queue[3 * slot] = (unsigned short)lo; queue[3 * slot + 1] = (unsigned short)hi; queue[3 * slot + 2] = (unsigned short)root; }
+        else {
+            double s = -1.0;
+            for (int k = lo; k < hi; ++k) s = s + val[k];
+            pitVol[root] = s;
+        }
+    }
+    __syncthreads();
+    const int nq = min(S.ibuf[4], QCAP);
+    for (int i = warp; i < nq; i += NWARP) {
+        const int lo = queue[3 * i], hi = queue[3 * i + 1], root = queue[3 * i + 2];
+        double s = -1.0;
+        for (int k0 = lo; k0 < hi; k0 += 32) {
+            const int k = k0 + lane;
+            const double v = (k < hi) ? val[k] : 0.0;
+            unsigned m = __ballot_sync(0xffffffffu, v != 0.0);
+            if (__popc(m) > 6) {            // wet stretch: all 32 terms in order (the zeros among them change nothing)
+#pragma unroll
+                for (int b = 0; b < 32; ++b) s = s + __shfl_sync(0xffffffffu, v, b);
+            } else {
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    s = s + __shfl_sync(0xffffffffu, v, b);
+                }
+            }
+        }
+        if (lane == 0) pitVol[root] = s;
+    }
+    __syncthreads();
+}
+
+// ---- discharge (FLOWalgo.f90:53-81) on the breadth-first layout ---------------------------------------------------------
+// rec[q]   = first-child position : 16 | donor count : 8 | deposition rule : 8 (written by the stream-power pre-pass)
+// order[q] = node at position q, posb[v] = position of node v.  Global scratch (I_LC, I_PS), S.boff = bucket offsets.
+struct Bfs {
+    unsigned *rec;
+    unsigned short *order, *posb;
+};
+__device__ __forceinline__ Bfs bfs_arrays(Smem &S, int N)
+{
+    Bfs b;
+    b.rec = (unsigned *)S.P.i[I_LC];
+    b.order = (unsigned short *)S.P.i[I_PS];
+    b.posb = b.order + np_of(N);
+    return b;
+}
+
+// S.ibuf[5] = 1 when the receiver tree is too deep for the shared-memory tables: generic phases take over for this step
+__device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned char *dsm, double rain)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int *__restrict__ rcv = S.P.i[I_RCV], *__restrict__ stack = S.P.i[I_STACK];
+    const unsigned char *__restrict__ cnt8 = (const unsigned char *)S.P.i[I_CNT];
+    const Bfs B = bfs_arrays(S, N);
+    unsigned *jd = (unsigned *)dsm;                                              // [Nq] (jump:16 | dist:16)
+    unsigned short *dpos = (unsigned short *)(dsm + (size_t)4 * Nq), *qpos = dpos + Nq;   // depth / BFS position by stack position
+    unsigned short *cntW = (unsigned short *)dsm;                                // [maxd + 1][NWARP] after jd
+    double *vals = (double *)dsm;                                                // [Nq] by BFS position, after all of them
+    const unsigned lt = (1u << lane) - 1u;
+    SubTick stc = sub_tick_begin(c);
+    for (int v = tid; v < N; v += TPB) { const unsigned r = (unsigned)rcv[v]; jd[v] = (r << 16) | (r == (unsigned)v ? 0u : 1u); }
+    __syncthreads();
+    int act = 1;
+    while (act) {
+        int loc = 0;
+        for (int v = tid; v < N; v += TPB) {
+            const unsigned w = jd[v], j = w >> 16;
+            const unsigned wj = jd[j];
+            if ((wj >> 16) != j) { jd[v] = (wj & 0xFFFF0000u) | ((w + wj) & 0xFFFFu); loc = 1; }
+        }
+        act = __syncthreads_or(loc);
+    }
+    int md = 0;
+    for (int p = tid; p < N; p += TPB) { const int d = (int)(jd[stack[p]] & 0xFFFFu); dpos[p] = (unsigned short)d; md = max(md, d); }
+    md = __reduce_max_sync(0xffffffffu, md);
+    if (lane == 0) atomicMax(&S.ibuf[2], md);
+    __syncthreads();
+    const int maxd = S.ibuf[2];
+    const int dlim = (c.dbg & 8) ? 12 : min(DEPMAX - 2, (4 * Nq) / (2 * NWARP) - 1);
+    const bool deep = maxd > dlim;
+    __syncthreads();
+    if (tid == 0) { S.ibuf[2] = 0; S.ibuf[3] = maxd; S.ibuf[5] = deep ? 1 : 0; }
+    if (deep) {
+        __syncthreads();
+        tree_links(c, S.P.i[I_RCV], S.P.i[I_FC], S.P.i[I_SUCC], S.P.i[I_LC], S.P.i[I_PS], S.P.i[I_CNT]);
+        phase_discharge(c, S, rain);
+        return;
+    }
+    sub_tick(stc, 22);      // depths
+    // stable counting sort of the stack positions by depth: warp w owns the positions [w * L, (w + 1) * L)
+    const int nflat = (maxd + 1) * NWARP;
+    for (int i = tid; i < nflat; i += TPB) cntW[i] = 0;
+    __syncthreads();
+    const int L = (((N + NWARP - 1) / NWARP) + 31) & ~31;
+    const int p0 = warp * L, p1 = min(N, p0 + L);
+    for (int pb = p0; pb < p1; pb += 32) {
+        const int p = pb + lane;
+        const unsigned d = (p < p1) ? dpos[p] : 0xFFFFu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (p < p1 && (peers & lt) == 0u) cntW[d * NWARP + warp] += (unsigned short)__popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const int R = (nflat + TPB - 1) / TPB;
+        const int i0 = min(nflat, tid * R), i1 = min(nflat, i0 + R);
+        int sum = 0;
+        for (int i = i0; i < i1; ++i) sum += cntW[i];
+        int tot;
+        int ex = blk_exscan(sum, tot, S);
+        for (int i = i0; i < i1; ++i) {
+            const int cv = cntW[i];
+            cntW[i] = (unsigned short)ex;
+            if (i % NWARP == 0) S.boff[i / NWARP] = (unsigned short)ex;
+            ex += cv;
+        }
+        if (tid == 0) S.boff[maxd + 1] = (unsigned short)N;
+    }
+    __syncthreads();
+    for (int pb = p0; pb < p1; pb += 32) {
+        const int p = pb + lane;
+        const bool valid = p < p1;
+        const unsigned d = valid ? dpos[p] : 0xFFFFu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int base = valid ? cntW[d * NWARP + warp] : 0;
+        __syncwarp();
+        if (valid && (peers & lt) == 0u) cntW[d * NWARP + warp] = (unsigned short)(base + __popc(peers));
+        __syncwarp();
+        if (valid) qpos[p] = (unsigned short)(base + __popc(peers & lt));
+    }
+    __syncthreads();
+    sub_tick(stc, 23);      // stable sort by depth
+    // in the stack a node's first (lowest-id) donor follows it directly; the donors of one node are contiguous in q
+    for (int p = tid; p < N; p += TPB) {
+        const int v = stack[p];
+        const unsigned q = qpos[p];
+        const unsigned n = cnt8[v];
+        const unsigned f = (p + 1 < N) ? qpos[p + 1] : 0u;
+        B.rec[q] = f | (n << 16);
+        B.order[q] = (unsigned short)v;
+        B.posb[v] = (unsigned short)q;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int q = tid; q < N; q += TPB) { const int v = B.order[q]; vals[q] = c.area[v] * ((v >= c.bounds) ? rain : 0.); }
+    __syncthreads();
+    sub_tick(stc, 24);      // records + initial values
+    {
+        int b0 = S.boff[maxd], b1 = S.boff[maxd + 1];
+        unsigned rcur = (b0 + tid < b1) ? B.rec[b0 + tid] : 0u;
+        for (int d = maxd; d >= 0; --d) {
+            int nb0 = 0, nb1 = 0;
+            unsigned rnext = 0u;
+            if (d > 0) { nb0 = S.boff[d - 1]; nb1 = S.boff[d]; if (nb0 + tid < nb1) rnext = B.rec[nb0 + tid]; }
+            for (int q = b0 + tid; q < b1; q += TPB) {
+                const unsigned r = (q == b0 + tid) ? rcur : B.rec[q];
+                const int n = (int)((r >> 16) & 0xFFu), f = (int)(r & 0xFFFFu);
+                if (n) {
+                    double acc = vals[q];
+                    for (int j = f + n - 1; j >= f; --j) acc = acc + vals[j];       // donors in descending id
+                    vals[q] = acc;
+                }
+            }
+            __syncthreads();
+            b0 = nb0; b1 = nb1; rcur = rnext;
+        }
+    }
+    sub_tick(stc, 25);      // level loop
+    double *__restrict__ Q = S.P.f[F_Q];
+#pragma unroll 4
+    for (int q = tid; q < N; q += TPB) Q[B.order[q]] = vals[q];
+    __syncthreads();
+    sub_tick(stc, 26);      // Q by node id
+}
+
+// FLOWalgo.f90:299-330 on the filled surface, same arithmetic as fast::flow_cfl; everything comes from global memory
+__device__ __noinline__ double flow_cfl_c(const DevConst &c, Smem &S, double erod)
+{
+    __builtin_assume(__isShared(&c)); __builtin_assume(__isShared(&S));
+    const int N = c.N;
+    const int *__restrict__ rcv = S.P.i[I_RCV];
+    const double *__restrict__ W = S.P.f[F_FILLH], *__restrict__ Q = S.P.f[F_Q];
+    const double2 *__restrict__ xy2 = reinterpret_cast<const double2 *>(c.xy);
+    const double em = c.m, en1 = c.n - 1.;
+    double cfl = 1.e6;
+#pragma unroll 2
+    for (int d = threadIdx.x; d < N; d += TPB) {
+        const int r = rcv[d];
+        const double q = Q[d], wd = W[d];
+        const double2 xd = xy2[d];
+        const double wr = W[r];
+        const double2 xr = xy2[r];
+        if (d == r || !(q > 0.)) continue;
+        const double dz = wd - wr;
+        if (dz > 0.) {
+            const double dx = xd.x - xr.x, dy = xd.y - xr.y;
+            const double dist = sqrt(dx * dx + dy * dy);
+            const double tmp = dist / (erod * powx(q, em) * powx(dz / dist, en1));
+            cfl = fmin(tmp, cfl);
+        }
+    }
+    return blk_min(cfl, S);
+}
+
+// ---- stream power (FLOWalgo.f90:583-1044), see fast::streampower ---------------------------------------------------------
+__device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned char *dsm, double erod, double sea, double dt)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    const Bfs B = bfs_arrays(S, N);
+    double *vals = (double *)dsm;
+    unsigned *evbits = (unsigned *)(dsm + (size_t)8 * Nq);
+    unsigned char *kindg = (unsigned char *)B.rec;
+    const int *__restrict__ pitID = S.P.i[I_PITID], *__restrict__ rcv = S.P.i[I_RCV];
+    const double *__restrict__ z = S.P.f[F_Z], *__restrict__ W = S.P.f[F_FILLH], *__restrict__ Qg = S.P.f[F_Q];
+    const double *__restrict__ maxhA = S.P.f[F_MAXH];
+    double *__restrict__ depo = S.P.f[F_DEPO], *__restrict__ ero = S.P.f[F_ERO];
+#pragma unroll 2
+    for (int d = tid; d < N; d += TPB) {
+        const int r = rcv[d];
+        const unsigned qd = B.posb[d];
+        const double zd = z[d], zr = z[r], fh = W[d], area = c.area[d];
+        const double q = Qg[d];
+        double dh = 0.95 * (zd - zr);
+        if (zd > sea && zr < sea) dh = 0.99 * (zd - sea);
+        if (dh < 0.001) dh = 0.;
+        const double waterH = fh - zd;
+        double SPL = 0., totspl = 0.;
+        if (r != d && dh > 0. && waterH == 0. && fh >= sea) {
+            const double dx = c.xy[2 * d] - c.xy[2 * r], dy = c.xy[2 * d + 1] - c.xy[2 * r + 1];
+            const double dist = sqrt(dx * dx + dy * dy);
+            if (dist > 0.) {
+                const double slp = dh / dist;
+                SPL = -erod * 1. * 1. * powx(q, c.m) * powx(slp, c.n);
+                totspl = totspl + SPL;
+                if (-totspl * dt > dh) {
+                    const double frac = dh / (-totspl * dt);
+                    SPL = SPL * frac;
+                    totspl = -dh;
+                }
+            }
+        }
+        double maxh = maxhA[d];
+        if (waterH > 0.) maxh = waterH;
+        else if (zd < sea) maxh = sea - zd;
+        maxh = 0.95 * maxh;
+        int k;
+        double e = 0.;
+        if (totspl < 0.) { k = 0; e = SPL * dt * area; }
+        else if (totspl >= 0. && area > 0.) {
+            if (waterH > 0. && fh > sea) {
+                k = 1;
+                const int pp = pitID[d];          // pit under the sea: static first cascade step (:979-991)
+                if (pp >= 0 && c.area[pp] > 0. && W[pp] < sea) k = (zd < sea) ? 2 : 4;
+            }
+            else if (zd <= sea) k = 2;
+            else if (maxh > 0. && waterH == 0. && d != r && zd > sea) { k = 3; e = maxh; }
+            else if (d == r) k = 2;
+            else k = 4;
+        } else k = 5;
+        kindg[4 * qd + 3] = (unsigned char)k;
+        vals[qd] = e;
+        depo[d] = 0.;
+        ero[d] = 0.;
+    }
+    for (int v = tid; v < Nq / 32; v += TPB) evbits[v] = 0u;
+    __syncthreads();
+}
+
+// ordered sediment routing (FLOWalgo.f90:875-964) over the breadth-first buckets
+__device__ __noinline__ void sp_route_c(const DevConst &c, Smem &S, unsigned char *dsm, double dt)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    const Bfs B = bfs_arrays(S, N);
+    double *vals = (double *)dsm;
+    unsigned *evbits = (unsigned *)(dsm + (size_t)8 * Nq);
+    double *depo = S.P.f[F_DEPO], *ero = S.P.f[F_ERO], *pdep = S.P.f[F_PDEP];
+    const int *posg = S.P.i[I_POS];
+    const int maxd = S.ibuf[3];
+    int b0 = S.boff[maxd], b1 = S.boff[maxd + 1];
+    unsigned rcur = 0u, ccur = 0u;
+    if (b0 + tid < b1) { rcur = B.rec[b0 + tid]; ccur = B.order[b0 + tid]; }
+    for (int d = maxd; d >= 0; --d) {
+        int nb0 = 0, nb1 = 0;
+        unsigned rnext = 0u, cnext = 0u;
+        if (d > 0) { nb0 = S.boff[d - 1]; nb1 = S.boff[d]; if (nb0 + tid < nb1) { rnext = B.rec[nb0 + tid]; cnext = B.order[nb0 + tid]; } }
+        for (int q = b0 + tid; q < b1; q += TPB) {
+            const bool pre = (q == b0 + tid);
+            const unsigned r = pre ? rcur : B.rec[q];
+            const int cur = (int)(pre ? ccur : (unsigned)B.order[q]);
+            const int n = (int)((r >> 16) & 0xFFu), f = (int)(r & 0xFFFFu), k = (int)(r >> 24);
+            double acc = 0. * dt;
+            for (int j = f + n - 1; j >= f; --j) acc = acc + vals[j];
+            const double own = vals[q];
+            double Qs = 0., erodep = 0.;
+            if (k == 0) { erodep = own; Qs = -erodep + acc; }
+            else if (k == 1) {
+                if (acc != 0.) {
+                    pdep[cur] = acc;
+                    if (acc > 0.) { const int ri = N - 1 - posg[cur]; atomicOr(&evbits[ri >> 5], 1u << (ri & 31)); }
+                }
+            }
+            else if (k == 2) { erodep = acc; }
+            else if (k == 3) {
+                const double area = c.area[cur];
+                const double totflx = 0. + acc, maxh = own;
+                if (totflx / area < maxh) erodep = acc;
+                else { const double frac = acc / totflx; erodep = frac * maxh * area; Qs = acc - erodep; }
+            } else if (k == 4) Qs = acc;
+            if (!(k == 1 && acc != 0.)) {
+                if (erodep < 0.) ero[cur] = 0. + erodep;
+                else if (erodep != 0.) depo[cur] = 0. + erodep;
+            }
+            vals[q] = Qs;
+        }
+        __syncthreads();
+        b0 = nb0; b1 = nb1; rcur = rnext; ccur = cnext;
+    }
+    __syncthreads();
+}
+
+__device__ __noinline__ void streampower_c(const DevConst &c, Smem &S, unsigned char *dsm, double erod, double sea, double dt,
+                                           const int *base1, int nbase1)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    const int *pitID = S.P.i[I_PITID], *stack = S.P.i[I_STACK], *pitDrain = S.P.i[I_PITDRAIN], *rcv = S.P.i[I_RCV];
+    const double *z = S.P.f[F_Z], *W = S.P.f[F_FILLH];
+    const double *pitVol1 = S.P.f[F_PITVOL];
+    double *depo = S.P.f[F_DEPO], *pdep = S.P.f[F_PDEP], *pitVol = S.P.f[F_PITVOLW];
+    long long *pcs = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
+    long long ts0 = clock64();
+#define STICK(i) do { if (tid == 0) { long long t1_ = clock64(); pcs[i] += t1_ - ts0; ts0 = t1_; } } while (0)
+    sp_prepass_c(c, S, dsm, erod, sea, dt);
+    STICK(27);
+    sp_route_c(c, S, dsm, dt);
+    STICK(15);
+    // lake-entry events in reverse stack order, staged in the bytes the routing no longer needs:
+    // loads fp64 [cap] | pits u16 [cap] | donors u16 [cap] | "pit receives an event" bytes [Nq]
+    unsigned *evbits = (unsigned *)(dsm + (size_t)8 * Nq);
+    const int cap = (int)(((size_t)7 * Nq) / 12) & ~7;
+    double *ev_dep = (double *)dsm;
+    unsigned short *ev_pit = (unsigned short *)(dsm + (size_t)8 * cap), *ev_donor = ev_pit + cap;
+    unsigned char *has_ev = dsm + (size_t)7 * Nq;
+    int nev;
+    {
+        const int nw = (N + 31) >> 5;
+        int tot_mine = 0;
+        unsigned words[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int wi = tid * 4 + u;
+            words[u] = (wi < nw) ? evbits[wi] : 0u;
+            tot_mine += __popc(words[u]);
+        }
+        const int off0 = blk_exscan(tot_mine, nev, S);      // barriers inside: every thread has its words, vals is free
+        if (nev <= cap) {
+            int off = off0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                unsigned wbits = words[u];
+                while (wbits) {
+                    const int bit = __ffs(wbits) - 1;
+                    wbits &= wbits - 1;
+                    ev_donor[off++] = (unsigned short)((tid * 4 + u) * 32 + bit);     // reverse stack index for now
+                }
+            }
+        }
+    }
+    if (nev > cap) {          // more events than the staging area holds: the literal serial pass (never seen in practice)
+        __syncthreads();
+        phase_streampower_serial(c, S, erod, sea, dt);
+        return;
+    }
+    for (int v = tid; v < Nq / 4; v += TPB) reinterpret_cast<unsigned *>(has_ev)[v] = 0u;
+    __syncthreads();
+    for (int e = tid; e < nev; e += TPB) {
+        const int donor = stack[N - 1 - ev_donor[e]];
+        const int pit = pitID[donor];
+        const bool ok = (pit >= 0 && c.area[pit] > 0.);
+        if (ok) has_ev[pit] = 1;
+        ev_pit[e] = ok ? (unsigned short)pit : NONE16;
+        ev_donor[e] = (unsigned short)donor;
+        ev_dep[e] = pdep[donor];
+    }
+    __syncthreads();
+    STICK(12);
+    if (nev == 0) return;
+    int over = 0;
+    if (S.ibuf[1])
+        for (int e = tid; e < nev; e += TPB) { const int pit = ev_pit[e]; if (pit != NONE16 && W[pit] < sea) over = 1; }
+    for (int i = tid; i < nbase1; i += TPB) {
+        const int pit = base1[i];
+        if (!has_ev[pit]) continue;
+        double dp = depo[pit];
+        bool any = false;
+        double vol = 0.;
+        for (int e = 0; e < nev; ++e) {
+            if (ev_pit[e] != pit) continue;
+            if (!any) { vol = pitVol1[pit]; any = true; }
+            const double pitDep = ev_dep[e];
+            const double totdist = 0. + pitDep, tmpdist = 0. + dp;
+            if (tmpdist + totdist <= vol || pitDrain[pit] == pit) dp = dp + pitDep;
+            else { over = 1; break; }
+        }
+        S.P.f[F_VAL][pit] = dp;
+    }
+    over = __syncthreads_or(over);
+    STICK(13);
+    if (!over) {
+        for (int i = tid; i < nbase1; i += TPB) { const int pit = base1[i]; if (has_ev[pit]) depo[pit] = S.P.f[F_VAL][pit]; }
+        __syncthreads();
+        return;
+    }
+    // serial replay, literal (FLOWalgo.f90:967-1034)
+    for (int k = tid; k < N; k += TPB) pitVol[k] = pitVol1[k];
+    if (tid == 0) S.ibuf[0] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned st = 0;
+        for (int e = 0; e < nev; ++e) {
+            if (ev_pit[e] == NONE16) continue;
+            const int donor = ev_donor[e];
+            const int recvr = rcv[donor];
+            double pitDep = ev_dep[e];
+            double totdist = 0. + pitDep;
+            int tmpID = ev_pit[e], nID = tmpID;
+            long guard = 0;
+            while (totdist > 0.) {
+                if (++guard > 1000000 || tmpID < 0) { st |= BL_ST_CASCADE_GUARD; break; }
+                const double tmpdist = 0. + depo[tmpID];
+                const double pv = pitVol[tmpID];
+                if (W[tmpID] < sea) {
+                    if (z[donor] < sea) depo[donor] = depo[donor] + pitDep;
+                    else { S.ibuf[0] = 1; e = nev; }
+                    totdist = 0.;
+                    nID = recvr;
+                } else if (tmpdist + totdist <= pv) {
+                    depo[tmpID] = depo[tmpID] + pitDep; totdist = 0.; nID = tmpID;
+                } else if (pitDrain[tmpID] == tmpID) {
+                    depo[tmpID] = depo[tmpID] + pitDep; totdist = 0.; nID = tmpID;
+                } else {
+                    if (!(c.flags[tmpID] & 1)) { totdist = 0.; nID = tmpID; }
+                    else if (tmpdist == pv) nID = tmpID;
+                    else {
+                        const double frac = pitDep / totdist;
+                        depo[tmpID] = depo[tmpID] + (pv - tmpdist) * frac;
+                        pitDep = (totdist - (pv - tmpdist)) * frac;
+                        const double newdist = 0. + pitDep;
+                        const double totflx = 0. + depo[tmpID];
+                        totdist = newdist;
+                        pitVol[tmpID] = totflx;
+                        nID = tmpID;
+                    }
+                }
+                tmpID = pitDrain[nID];
+            }
+        }
+        if (st) atomicOr(&c.status[blockIdx.x], st);
+    }
+    __syncthreads();
+    STICK(14);
+    if (S.ibuf[0]) phase_streampower_serial(c, S, erod, sea, dt);
+#undef STICK
+}
+
+// buildFlux.py:193-195, :252-272, :292-315 (see fast::apply): z fp64 in shared memory, the increments in global scratch
+template <int KDT>
+__device__ __noinline__ void apply_c(const DevConst &c, Smem &S, unsigned char *dsm, double sea, double timestep)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
+    const int N = c.N, tid = threadIdx.x;
+    double *__restrict__ zs = (double *)dsm;
+    double *__restrict__ cd = S.P.f[F_VAL];
+    double *__restrict__ z = S.P.f[F_Z];
+    double *__restrict__ cumdiff = S.P.f[F_CUMDIFF];
+    double *__restrict__ cumhill = S.P.f[F_CUMHILL];
+    const double *__restrict__ sedflux = S.P.f[F_SEDFLUX];
+    const unsigned char *__restrict__ gflags = c.flags;
+    const unsigned *__restrict__ nbin = c.nbf2;
+#pragma unroll 4
+    for (int k = tid; k < N; k += TPB) {
+        const double sf = sedflux[k];
+        zs[k] = z[k] + sf;
+        cumdiff[k] += sf;
+    }
+    __syncthreads();
+    for (int g = tid; g < N; g += TPB) {
+        double acc = 0.;
+        const unsigned char fg = gflags[g];
+        const unsigned inm = nbin[g];            // bit p: neighbour slot p is an inside node (borders2)
+        const double zg = zs[g];
+        const double c0 = cumdiff[g], h0 = cumhill[g];
+        if (fg & 2) {
+            Ids<KDT> ids;
+            load_ids<KDT>(c, g, ids);
+            if (c.ve32) {
+                const float4 *ve = reinterpret_cast<const float4 *>(c.ve32 + (size_t)g * KDT * 2);
+#pragma unroll
+                for (int q = 0; q < KDT / 2; ++q) {
+                    const float4 v4 = __ldg(ve + q);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int p = 2 * q + h;
+                        if (ids.get(p) == NONE16) continue;
+                        const int j = ids.get(p);
+                        const double ed = (double)(h ? v4.z : v4.x), di = (double)(h ? v4.w : v4.y), zj = zs[j];
+                        const bool bj = (inm >> p) & 1u;
+                        if (bj && di > 0.) acc += ed * (zj - zg) / di;
+                        if (!bj) { if (zj < zg && di > 0.) acc += ed * (zj - zg) / di; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < KDT; ++p) {
+                    if (ids.get(p) == NONE16) continue;
+                    const int j = ids.get(p);
+                    const double di = c.edge[(size_t)p * N + g], ed = c.vor[(size_t)p * N + g], zj = zs[j];
+                    const bool bj = (inm >> p) & 1u;
+                    if (bj && di > 0.) acc += ed * (zj - zg) / di;
+                    if (!bj) { if (zj < zg && di > 0.) acc += ed * (zj - zg) / di; }
+                }
+            }
+        }
+        const double area = c.area[g];
+        const double ac = (area > 0.) ? 1. / area : 0.;
+        double coeff = ac * ((zg >= sea) ? c.CDa : c.CDm);
+        if (!(fg & 2)) { coeff = 0.; acc = 0.; }
+        if (S.diff_out) S.diff_out[g] = acc;
+        const double d = coeff * acc * timestep;
+        cd[g] = d;
+        if (fg & 1) { cumdiff[g] = c0 + d; cumhill[g] = h0 + d; }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = tid; k < N; k += TPB)
+        if (gflags[k] & 1) zs[k] += cd[k];
+    __syncthreads();
+    if (c.btype != 0) {
+        const double add = (c.btype == 1) ? -0.1 : (c.btype == 2 ? 0. : 100.);
+        for (int k = tid; k < c.bounds; k += TPB) {
+            const double zp = zs[c.parent[k]];
+            cd[k] = (c.btype == 2) ? zp : zp + add;
+        }
+        __syncthreads();
+        for (int k = tid; k < c.bounds; k += TPB) zs[k] = cd[k];
+        __syncthreads();
+    }
+#pragma unroll 4
+    for (int k = tid; k < N; k += TPB) {
+        double zn = zs[k];
+        if (c.disp) zn += c.disp[k] * timestep;
+        z[k] = zn;
+    }
+    __syncthreads();
+}
+
+template <int KDT>
+__device__ void time_step(const DevConst &c, Smem &S, unsigned char *dsm)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) { S.sea = sea_level(c, S.tNow); S.tick0 = clock64(); }
+    __syncthreads();
+    {
+        int any_marine;
+        fill_c<KDT>(c, S, dsm, S.sea);
+        receivers_c<KDT>(c, S, dsm, S.sea, any_marine);
+        if (tid == 0) { S.ibuf[1] = any_marine; S.any_marine = any_marine; }
+    }
+    BL_TICK(0);
+    {
+        int nbase1;
+        links_stack_c<KDT>(c, S, dsm, S.P.i[I_RCV1], S.P.i[I_STACK1], S.P.i[I_POS1], S.P.i[I_LA], nbase1, false, false, 0ull);
+    }
+    BL_TICK(2);
+    basins_c(c, S, dsm, S.P.i[I_LA], S.nbase1);
+    BL_TICK(3);
+    {
+        int nbase;
+        links_stack_c<KDT>(c, S, dsm, S.P.i[I_RCV], S.P.i[I_STACK], S.P.i[I_POS], S.P.i[I_LB], nbase, true, c.shuffle != 0,
+                           mix64(S.seed + (unsigned long long)S.step));
+    }
+    BL_TICK(4);
+    drainage(c, S, dsm, S.P.i[I_LA], S.nbase1, S.sea, S.any_marine);
+    BL_TICK(5);
+    discharge_c(c, S, dsm, S.rain);
+    BL_TICK(6);
+    const bool deep = S.ibuf[5] != 0;          // uniform: written before the barriers that end discharge_c
+    {
+        const double flowcfl = deep ? phase_cfl(c, S, S.erod) : flow_cfl_c(c, S, S.erod);
+        double cfl = fmin(flowcfl, c.hill);
+        cfl = py2_floorish(cfl);
+        cfl = fmin(cfl, S.tStop - S.tNow);
+        cfl = fmax(c.minDT, cfl);
+        cfl = fmin(c.maxDT, cfl);
+        if (tid == 0) { S.dbuf[2] = cfl; S.newdt = cfl; }
+        __syncthreads();
+    }
+    BL_TICK(7);
+    if (deep) phase_streampower(c, S, S.erod, S.sea, S.newdt);
+    else streampower_c(c, S, dsm, S.erod, S.sea, S.newdt, S.P.i[I_LA], S.nbase1);
+    BL_TICK(8);
+    {
+        // getid1 (FLOWalgo.f90:1047-1086), see fast::time_step
+        const double *cdepo = S.P.f[F_DEPO], *cero = S.P.f[F_ERO], *pitVol = S.P.f[F_PITVOL];
+        const int *pitID = S.P.i[I_PITID], *alld = S.P.i[I_ALLDRAIN], *base1 = S.P.i[I_LA];
+        const int nbase1 = S.nbase1;
+        const double cfl = S.dbuf[2];
+        int nb = 0;
+        double minperc = 1.e300;
+        for (int i = tid; i < nbase1; i += TPB) {
+            const int k = base1[i];
+            const double vc = (c.depo == 0) ? cero[k] : cdepo[k] + cero[k];
+            const double sumvol = 0. + vc;
+            const bool in1 = (sumvol > pitVol[k] && pitVol[k] > 0.);
+            const bool in2 = (pitID[k] >= 0 && alld[k] == pitID[k]);
+            if (in1 && in2 && (c.flags[k] & 4)) { nb = 1; minperc = fmin(minperc, pitVol[k] / sumvol); }
+        }
+        nb = __syncthreads_or(nb);
+        double newdt = cfl;
+        if (nb) { minperc = blk_min(minperc, S); newdt = cfl * minperc; }
+        newdt = py2_floorish(newdt);
+        newdt = fmax(c.minDT, newdt);
+        if (tid == 0) S.newdt = newdt;
+        __syncthreads();
+        if (newdt < cfl) {
+            if (deep) phase_streampower(c, S, S.erod, S.sea, S.newdt);
+            else streampower_c(c, S, dsm, S.erod, S.sea, S.newdt, S.P.i[I_LA], S.nbase1);
+        }
+    }
+    BL_TICK(9);
+    phase_erodep(c, S, S.sea);
+    BL_TICK(10);
+    apply_c<KDT>(c, S, dsm, S.sea, S.newdt);
+    BL_TICK(11);
+    if (tid == 0) { S.tNow += S.newdt; S.last_dt = S.newdt; S.step += 1; }
+    __syncthreads();
+}
+
+} // namespace fastc

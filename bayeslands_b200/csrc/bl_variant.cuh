@@ -72,3 +72,23 @@ cudaError_t BL_CAT(bl_func_attr_, BL_NS)(int KDT, cudaFuncAttributes *attr)
         default: return cudaFuncGetAttributes(attr, BL_NS::bl_run_kernel<0>);
     }
 }
+
+// resident CTAs per SM of the run kernel with `dyn` bytes of dynamic shared memory
+cudaError_t BL_CAT(bl_occupancy_, BL_NS)(int KDT, int dyn, int *nres)
+{
+#define OCC(K)                                                                                                          \
+    do {                                                                                                                \
+        if (dyn) {                                                                                                      \
+            cudaError_t e = cudaFuncSetAttribute(BL_NS::bl_run_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn); \
+            if (e != cudaSuccess) return e;                                                                             \
+        }                                                                                                               \
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nres, BL_NS::bl_run_kernel<K>, BL_TPB, (size_t)dyn);       \
+    } while (0)
+    switch (KDT) {
+        case 8: OCC(8);
+        case 12: OCC(12);
+        case 20: OCC(20);
+        default: dyn = 0; OCC(0);
+    }
+#undef OCC
+}

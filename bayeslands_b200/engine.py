@@ -35,10 +35,11 @@ class Engine:
     def __init__(self, mesh, inp, B: int, device: int = 0, real_elev: Optional[np.ndarray] = None,
                  erdp_coords: Optional[Sequence] = None, shuffle_mode: int = 1, sealevel=None, disp=None,
                  tpb: int = 0, force_generic: bool = False, l2_persist: bool = True, lean: bool = False,
-                 debug: int = 0):
+                 debug: int = 0, compact: Optional[bool] = None):
         """Engine options (`bl_params.opt_*`; the library reads no environment variables): `tpb` threads per CTA
         (0 = automatic), `force_generic` the L2-resident device path, `lean` production mode without the per-stage
-        products kept for `field()`."""
+        products kept for `field()`, `compact` the 8-bytes-per-node shared-memory layout (None = automatic: chosen when it
+        lets two landscapes share an SM; True = wherever it fits; False = never)."""
         if not torch.cuda.is_available():
             raise _lib.BlError("bayeslands_b200.Engine needs a CUDA device (no CPU fallback)")
         self.L = _lib.load()
@@ -95,7 +96,8 @@ class Engine:
             p.npts, p.pts_cell = self.npts, _ip(cells)
         p.opt_tpb = int(tpb)
         p.opt_flags = ((_lib.OPT_FORCE_GENERIC if force_generic else 0) | (0 if l2_persist else _lib.OPT_NO_L2_PERSIST)
-                       | (_lib.OPT_LEAN if lean else 0))
+                       | (_lib.OPT_LEAN if lean else 0)
+                       | (0 if compact is None else (_lib.OPT_COMPACT if compact else _lib.OPT_NO_COMPACT)))
         p.opt_debug = int(debug)
         self._m, self._p = m, p
         nbytes = self.L.bl_workspace_bytes(C.byref(m), C.byref(p), self.B)
@@ -300,3 +302,10 @@ class Engine:
     @property
     def launches(self) -> int:
         return int(self.L.bl_launch_count(self.ctx))
+
+    def info(self) -> dict:
+        """Launch configuration the context selected (`bl_ctx_info`)."""
+        a = (C.c_int32 * 4)()
+        _lib.check(self.L.bl_ctx_info(self.ctx, a))
+        return dict(tpb=int(a[0]), path=("generic", "shared", "compact")[int(a[1])], dyn_smem=int(a[2]),
+                    ctas_per_sm=int(a[3]))

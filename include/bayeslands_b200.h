@@ -100,6 +100,8 @@ typedef struct {
 
 #define BL_OPT_FORCE_GENERIC 1   /* use the L2-resident device path even if the mesh fits shared memory */
 #define BL_OPT_NO_L2_PERSIST 2   /* do not pin the mesh constants in L2 */
+#define BL_OPT_COMPACT       8   /* use the 8-bytes-per-node shared-memory layout wherever it fits (it is chosen automatically when it lets two landscapes share an SM) */
+#define BL_OPT_NO_COMPACT   16   /* never use it */
 #define BL_OPT_LEAN          4   /* production mode: skip the stores of per-stage products kept only for bl_get_field */
 
 typedef struct bl_ctx bl_ctx;
@@ -156,6 +158,10 @@ int bl_get_scalars(bl_ctx *ctx, double *tnow, int64_t *steps, uint32_t *status, 
 int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst_host, void *stream);
 /* number of kernel launches issued by this context so far (for bench.py's gpu_launches) */
 int64_t bl_launch_count(const bl_ctx *ctx);
+/* launch configuration the context selected: info[0] threads per CTA, info[1] device path (0 generic / L2-resident,
+ * 1 shared memory 17 B per node, 2 compact shared memory 8 B per node), info[2] dynamic shared memory per CTA in bytes,
+ * info[3] CTAs of this kernel resident per SM (occupancy query). */
+int bl_ctx_info(const bl_ctx *ctx, int32_t info[4]);
 
 /* ---- per-stage entry points on caller-owned DEVICE arrays ------------------------------------------
  * One routine of the time step per call, in the argument order of the f2py signature it replaces, executed by the SAME

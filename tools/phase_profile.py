@@ -11,9 +11,10 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "crater_fast"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 148
 TPB = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 DBG = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+COMPACT = {"auto": None, "on": True, "off": False}[sys.argv[5] if len(sys.argv) > 5 else "auto"]
 d, inp, m, simtime, rl, el, coords, likl_sed = bench.load_config(cfg)
 eng = Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=coords, sealevel=d["sealevel"] if "sealevel" in d else None,
-             tpb=TPB, debug=DBG)
+             tpb=TPB, debug=DBG, compact=COMPACT)
 r, e, s = bench.proposals(0, 0, B, rl, el)
 from bayeslands_b200 import hostparams
 for it in range(2):
@@ -40,6 +41,11 @@ names = {16: "erodep pass1+compact", 17: "erodep small basins", 18: "erodep larg
 for i in sorted(names):
     print("  sub %-32s %10.1f /step" % (names[i], (pc[:, i] / steps).mean()))
 
+info = eng.info()
+print("  launch:", info)
+if info["path"] == "compact":
+    print("  sub discharge_c (cyc/step): depths %.0f, stable sort %.0f, records+init %.0f, level loop %.0f, Q scatter %.0f; stream power pre-pass %.0f (routing = prepass+scan - pre-pass)"
+          % tuple((pc[:, i] / steps).mean() for i in (22, 23, 24, 25, 26, 27)))
 if DBG & 4:
     print("  fill diag (warp 0, cyc/step): scan %.0f, eval %.0f, barrier %.0f; rounds/step %.1f, evals/step (CTA) %.0f, eval passes/step (warp 0) %.1f"
           % tuple((pc[:, i] / steps).mean() for i in (22, 23, 24, 25, 26, 27)))
