@@ -150,5 +150,6 @@ BL_DECL_VARIANT(v1024)
 cudaError_t bl_launch_stage_v1024(int KDT, const DevConst &c, int dyn, cudaStream_t st, const StageArgs &a);
 cudaError_t bl_launch_stage_v256(int KDT, const DevConst &c, int dyn, cudaStream_t st, const StageArgs &a);
 BL_DECL_VARIANT(v768)
+BL_DECL_VARIANT(v384)
 BL_DECL_VARIANT(v512)
 BL_DECL_VARIANT(v256)

@@ -88,6 +88,7 @@ cudaError_t func_attr(int tpb, int KDT, cudaFuncAttributes *fa)
     if (tpb == 256) return bl_func_attr_v256(KDT, fa);
     if (tpb == 512) return bl_func_attr_v512(KDT, fa);
     if (tpb == 768) return bl_func_attr_v768(KDT, fa);
+    if (tpb == 384) return bl_func_attr_v384(KDT, fa);
     return bl_func_attr_v1024(KDT, fa);
 }
 
@@ -207,15 +208,15 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     // CTA size and device path.  The shared-memory path needs fast_smem_need() bytes of dynamic shared memory; what a CTA
     // may use is the device's opt-in limit minus the kernel's static shared memory (queried, not assumed).
     const int kdt_want = (KD <= 8) ? 8 : (KD <= 12 ? 12 : 20);
-    if (p->opt_tpb != 0 && p->opt_tpb != 256 && p->opt_tpb != 512 && p->opt_tpb != 768 && p->opt_tpb != 1024) {
-        g_err = "bl_ctx_create: opt_tpb must be 0, 256, 512, 768 or 1024"; return BL_ERR_ARG;
+    if (p->opt_tpb != 0 && p->opt_tpb != 256 && p->opt_tpb != 384 && p->opt_tpb != 512 && p->opt_tpb != 768 && p->opt_tpb != 1024) {
+        g_err = "bl_ctx_create: opt_tpb must be 0, 256, 384, 512, 768 or 1024"; return BL_ERR_ARG;
     }
     int optin = 0, smem_sm = 0, smem_res = 0;
     CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_OK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
     CUDA_OK(cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, device));
     int static_smem[1025] = {0};
-    for (int t : {256, 512, 768, 1024}) {
+    for (int t : {256, 384, 512, 768, 1024}) {
         cudaFuncAttributes fa;
         memset(&fa, 0, sizeof(fa));
         CUDA_OK(func_attr(t, kdt_want, &fa));
@@ -469,6 +470,7 @@ static int run_common(bl_ctx *ctx, int nstops, const double *stops, const int32_
     if (ctx->tpb == 256) CUDA_OK(bl_launch_run_v256(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
     else if (ctx->tpb == 512) CUDA_OK(bl_launch_run_v512(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
     else if (ctx->tpb == 768) CUDA_OK(bl_launch_run_v768(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
+    else if (ctx->tpb == 384) CUDA_OK(bl_launch_run_v384(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
     else CUDA_OK(bl_launch_run_v1024(ctx->c.KDT, ctx->c, ctx->B, ctx->dyn, st, a));
     ctx->launches++;
     return BL_OK;
@@ -765,6 +767,7 @@ extern "C" int bl_ctx_info(const bl_ctx *ctx, int32_t info[4])
     if (ctx->tpb == 256) CUDA_OK(bl_occupancy_v256(ctx->c.KDT, ctx->dyn, &nres));
     else if (ctx->tpb == 512) CUDA_OK(bl_occupancy_v512(ctx->c.KDT, ctx->dyn, &nres));
     else if (ctx->tpb == 768) CUDA_OK(bl_occupancy_v768(ctx->c.KDT, ctx->dyn, &nres));
+    else if (ctx->tpb == 384) CUDA_OK(bl_occupancy_v384(ctx->c.KDT, ctx->dyn, &nres));
     else CUDA_OK(bl_occupancy_v1024(ctx->c.KDT, ctx->dyn, &nres));
     info[3] = nres;
     return BL_OK;

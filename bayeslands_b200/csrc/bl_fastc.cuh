@@ -37,7 +37,7 @@ __device__ __forceinline__ void red_and(unsigned a, unsigned v) { asm volatile("
 __device__ __forceinline__ unsigned char *tail_of(unsigned char *dsm, int Nq) { return dsm + (size_t)8 * Nq + Nq / 8; }
 
 // ---- depression filling (PDalgo.f90:19-91), literal Gauss-Seidel sweep by level, see fast::fill_bitmap -------------
-template <int KDT>
+template <int KDT, bool PF>
 __device__ __forceinline__ void fill_eval_c(const unsigned short *__restrict__ ngb16f, const double *__restrict__ zg, int k,
                                             unsigned aW, unsigned aB, double sea, double eps, double TH, int &loc)
 {
@@ -73,7 +73,12 @@ __device__ __forceinline__ void fill_eval_c(const unsigned short *__restrict__ n
 #pragma unroll
         for (int p = 0; p < KDT; ++p) {
             const unsigned j = ids.get(p);
-            red_or_if(wj[p] > lim, aB + 4u * (j >> 5), 1u << (j & 31));
+            const bool wake = wj[p] > lim;
+            red_or_if(wake, aB + 4u * (j >> 5), 1u << (j & 31));
+            if (PF && wake) {          // the woken node is evaluated a round or more from now: its z and id row on the way
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(zg + j));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(ngb16f + (size_t)j * KDT));
+            }
         }
     }
 }
@@ -149,7 +154,7 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
                     __syncwarp();
                     for (int i = lane; i < off; i += 32) {
                         const int s = (int)lds_u8(aL + (unsigned)i);
-                        fill_eval_c<KDT>(ngb16f, zg, (w0 + NWF * (s >> 5)) * 32 + (s & 31), aW, aB, sea, eps, TH, loc);
+                        fill_eval_c<KDT, false>(ngb16f, zg, (w0 + NWF * (s >> 5)) * 32 + (s & 31), aW, aB, sea, eps, TH, loc);
                     }
                     __syncwarp();
                 }
@@ -171,11 +176,16 @@ __device__ __noinline__ void receivers_c(const DevConst &c, Smem &S, unsigned ch
     int *__restrict__ rcv = S.P.i[I_RCV], *__restrict__ rcv1 = S.P.i[I_RCV1];
     double *__restrict__ maxh = S.P.f[F_MAXH], *__restrict__ fillH = S.P.f[F_FILLH];
     const double *__restrict__ zg = S.P.f[F_Z];
+    // by-products for the CFL and stream-power passes (same expressions as there, evaluated once per step while the
+    // surfaces are in shared memory): W(d) - W(rcv), the distance to the receiver, z(rcv)
+    double *__restrict__ dzw = S.P.f[F_CAPH], *__restrict__ distr = S.P.f[F_E], *__restrict__ zrA = S.P.f[F_QS];
+    const double2 *__restrict__ xy2 = reinterpret_cast<const double2 *>(c.xy);
     int mar = 0;
 #pragma unroll 2
     for (int g = tid; g < N; g += TPB) {
         Ids<KDT> ids;
         load_ids<KDT>(c, g, ids);
+        const double2 xg = xy2[g];
         const double wg = A[g];
         int low = g;
         double wl = wg;
@@ -186,8 +196,12 @@ __device__ __noinline__ void receivers_c(const DevConst &c, Smem &S, unsigned ch
             const double wj = A[j];
             if (wj < wl) { low = j; wl = wj; }
         }
+        const double2 xr = xy2[low];
         rcv[g] = low;
         fillH[g] = wg;
+        dzw[g] = wg - wl;
+        const double dx = xg.x - xr.x, dy = xg.y - xr.y;
+        distr[g] = sqrt(dx * dx + dy * dy);
         mar |= (wg < sea);
     }
     __syncthreads();
@@ -198,6 +212,7 @@ __device__ __noinline__ void receivers_c(const DevConst &c, Smem &S, unsigned ch
     for (int g = tid; g < N; g += TPB) {
         Ids<KDT> ids;
         load_ids<KDT>(c, g, ids);
+        const int r = rcv[g];
         const double z0 = A[g];
         int low1 = g;
         double zl = z0, dH = 1.e6;
@@ -213,6 +228,7 @@ __device__ __noinline__ void receivers_c(const DevConst &c, Smem &S, unsigned ch
         rcv1[g] = low1;
         if (dH > 9.99e5) dH = 0.;
         maxh[g] = dH;
+        zrA[g] = A[r];
     }
     any_marine = __syncthreads_or(mar);
 }
@@ -537,8 +553,9 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
     }
     sub_tick(stc, 25);      // level loop
     double *__restrict__ Q = S.P.f[F_Q];
+    const unsigned short *__restrict__ ordr = B.order;
 #pragma unroll 4
-    for (int q = tid; q < N; q += TPB) Q[B.order[q]] = vals[q];
+    for (int q = tid; q < N; q += TPB) Q[ordr[q]] = vals[q];
     __syncthreads();
     sub_tick(stc, 26);      // Q by node id
 }
@@ -548,23 +565,13 @@ __device__ __noinline__ double flow_cfl_c(const DevConst &c, Smem &S, double ero
 {
     __builtin_assume(__isShared(&c)); __builtin_assume(__isShared(&S));
     const int N = c.N;
-    const int *__restrict__ rcv = S.P.i[I_RCV];
-    const double *__restrict__ W = S.P.f[F_FILLH], *__restrict__ Q = S.P.f[F_Q];
-    const double2 *__restrict__ xy2 = reinterpret_cast<const double2 *>(c.xy);
+    const double *__restrict__ Q = S.P.f[F_Q], *__restrict__ dzw = S.P.f[F_CAPH], *__restrict__ distr = S.P.f[F_E];
     const double em = c.m, en1 = c.n - 1.;
     double cfl = 1.e6;
-#pragma unroll 2
+#pragma unroll 4
     for (int d = threadIdx.x; d < N; d += TPB) {
-        const int r = rcv[d];
-        const double q = Q[d], wd = W[d];
-        const double2 xd = xy2[d];
-        const double wr = W[r];
-        const double2 xr = xy2[r];
-        if (d == r || !(q > 0.)) continue;
-        const double dz = wd - wr;
-        if (dz > 0.) {
-            const double dx = xd.x - xr.x, dy = xd.y - xr.y;
-            const double dist = sqrt(dx * dx + dy * dy);
+        const double q = Q[d], dz = dzw[d], dist = distr[d];      // a base level has dz = 0: skipped like d == r
+        if (q > 0. && dz > 0.) {
             const double tmp = dist / (erod * powx(q, em) * powx(dz / dist, en1));
             cfl = fmin(tmp, cfl);
         }
@@ -583,22 +590,20 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
     unsigned char *kindg = (unsigned char *)B.rec;
     const int *__restrict__ pitID = S.P.i[I_PITID], *__restrict__ rcv = S.P.i[I_RCV];
     const double *__restrict__ z = S.P.f[F_Z], *__restrict__ W = S.P.f[F_FILLH], *__restrict__ Qg = S.P.f[F_Q];
-    const double *__restrict__ maxhA = S.P.f[F_MAXH];
+    const double *__restrict__ maxhA = S.P.f[F_MAXH], *__restrict__ distr = S.P.f[F_E], *__restrict__ zrA = S.P.f[F_QS];
     double *__restrict__ depo = S.P.f[F_DEPO], *__restrict__ ero = S.P.f[F_ERO];
 #pragma unroll 2
     for (int d = tid; d < N; d += TPB) {
         const int r = rcv[d];
         const unsigned qd = B.posb[d];
-        const double zd = z[d], zr = z[r], fh = W[d], area = c.area[d];
-        const double q = Qg[d];
+        const double zd = z[d], zr = zrA[d], fh = W[d], area = c.area[d];
+        const double q = Qg[d], dist = distr[d];
         double dh = 0.95 * (zd - zr);
         if (zd > sea && zr < sea) dh = 0.99 * (zd - sea);
         if (dh < 0.001) dh = 0.;
         const double waterH = fh - zd;
         double SPL = 0., totspl = 0.;
         if (r != d && dh > 0. && waterH == 0. && fh >= sea) {
-            const double dx = c.xy[2 * d] - c.xy[2 * r], dy = c.xy[2 * d + 1] - c.xy[2 * r + 1];
-            const double dist = sqrt(dx * dx + dy * dy);
             if (dist > 0.) {
                 const double slp = dh / dist;
                 SPL = -erod * 1. * 1. * powx(q, c.m) * powx(slp, c.n);
@@ -850,18 +855,18 @@ __device__ __noinline__ void apply_c(const DevConst &c, Smem &S, unsigned char *
     const unsigned char *__restrict__ gflags = c.flags;
     const unsigned *__restrict__ nbin = c.nbf2;
 #pragma unroll 4
-    for (int k = tid; k < N; k += TPB) {
-        const double sf = sedflux[k];
-        zs[k] = z[k] + sf;
-        cumdiff[k] += sf;
-    }
+    for (int k = tid; k < N; k += TPB) zs[k] = z[k] + sedflux[k];
     __syncthreads();
+    const double *__restrict__ dispA = c.disp;
+    const int nbn = c.bounds;
     for (int g = tid; g < N; g += TPB) {
         double acc = 0.;
         const unsigned char fg = gflags[g];
         const unsigned inm = nbin[g];            // bit p: neighbour slot p is an inside node (borders2)
         const double zg = zs[g];
-        const double c0 = cumdiff[g], h0 = cumhill[g];
+        const double sf = sedflux[g];
+        const double c0 = cumdiff[g] + sf, h0 = cumhill[g];
+        const double dsp = dispA ? dispA[g] * timestep : 0.;
         if (fg & 2) {
             Ids<KDT> ids;
             load_ids<KDT>(c, g, ids);
@@ -899,31 +904,30 @@ __device__ __noinline__ void apply_c(const DevConst &c, Smem &S, unsigned char *
         if (!(fg & 2)) { coeff = 0.; acc = 0.; }
         if (S.diff_out) S.diff_out[g] = acc;
         const double d = coeff * acc * timestep;
+        // the node's new elevation is final here (its neighbours read the old one from shared memory); ghost nodes
+        // take their parent's new elevation below, so the increments of the parents are kept
         cd[g] = d;
         if (fg & 1) { cumdiff[g] = c0 + d; cumhill[g] = h0 + d; }
+        else cumdiff[g] = c0;
+        if (g >= nbn || c.btype == 0) {
+            double zn = (fg & 1) ? zg + d : zg;
+            if (dispA) zn += dsp;
+            z[g] = zn;
+        }
     }
-    __syncthreads();
-#pragma unroll 4
-    for (int k = tid; k < N; k += TPB)
-        if (gflags[k] & 1) zs[k] += cd[k];
     __syncthreads();
     if (c.btype != 0) {
         const double add = (c.btype == 1) ? -0.1 : (c.btype == 2 ? 0. : 100.);
-        for (int k = tid; k < c.bounds; k += TPB) {
-            const double zp = zs[c.parent[k]];
-            cd[k] = (c.btype == 2) ? zp : zp + add;
+        for (int k = tid; k < nbn; k += TPB) {
+            const int pk = c.parent[k];
+            double zp = zs[pk];
+            if (gflags[pk] & 1) zp += cd[pk];
+            double zn = (c.btype == 2) ? zp : zp + add;
+            if (dispA) zn += dispA[k] * timestep;
+            z[k] = zn;
         }
         __syncthreads();
-        for (int k = tid; k < c.bounds; k += TPB) zs[k] = cd[k];
-        __syncthreads();
     }
-#pragma unroll 4
-    for (int k = tid; k < N; k += TPB) {
-        double zn = zs[k];
-        if (c.disp) zn += c.disp[k] * timestep;
-        z[k] = zn;
-    }
-    __syncthreads();
 }
 
 template <int KDT>
