@@ -89,7 +89,14 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
     BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x, nb = c.bounds;
     const int lane = tid & 31, warp = tid >> 5;
-    constexpr int NWF = (NWARP >= 2) ? NWARP / 2 : 1;      // sweeping warps (see fast::fill_bitmap)
+#ifndef BL_FILLC_ALL
+#define BL_FILLC_ALL 1
+#endif
+    // sweeping warps and bitmap words per batch: with BL_FILLC_ALL every warp of a (<= 512-thread) CTA sweeps, 4 words at
+    // a time, so a thin front is spread over twice as many warps; the slot lists take NWF * BW * 32 bytes either way
+    constexpr bool ALLW = BL_FILLC_ALL && (NWARP <= 16);
+    constexpr int NWF = ALLW ? NWARP : ((NWARP >= 2) ? NWARP / 2 : 1);
+    constexpr int BW = ALLW ? 4 : 8;
     const double *__restrict__ zg = S.P.f[F_Z];
     {
         double *W = (double *)dsm;
@@ -110,7 +117,7 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
     }
     __syncthreads();
     const unsigned aW = s32(dsm), aB = aW + 8u * (unsigned)Nq;
-    const unsigned aL = aB + (unsigned)(Nq / 8) + (unsigned)warp * 256u;   // [NWF][256] slot list of this warp
+    const unsigned aL = aB + (unsigned)(Nq / 8) + (unsigned)warp * (unsigned)(BW * 32);   // [NWF][BW * 32] slot list of this warp
     const unsigned short *ngb16f = c.ngb16f;
     const double eps = c.eps, TH = c.TH;
     const int nlev = c.nlev;
@@ -122,11 +129,11 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
             const int n0 = nb + S.lev_off[l], n1 = nb + S.lev_off[l + 1];     // node id range of the level
             if (warp < NWF && n1 > n0) {
                 const int whi = (n1 - 1) >> 5;
-                // a batch = 8 bitmap words of this warp (word w0 + NWF * t belongs to lane t): 256 candidate ids
-                for (int w0 = (n0 >> 5) + warp; w0 <= whi; w0 += 8 * NWF) {
+                // a batch = BW bitmap words of this warp (word w0 + NWF * t belongs to lane t): BW * 32 candidate ids
+                for (int w0 = (n0 >> 5) + warp; w0 <= whi; w0 += BW * NWF) {
                     unsigned mine = 0u;
                     const int wi = w0 + NWF * lane;
-                    if (lane < 8 && wi <= whi) {
+                    if (lane < BW && wi <= whi) {
                         const int lo = wi * 32;
                         unsigned m = 0xffffffffu;            // bits of other levels in the boundary words are not ours
                         if (lo < n0) m &= 0xffffffffu << (n0 - lo);
@@ -146,7 +153,7 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
                     }
                     int off = 0;
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
+                    for (int t = 0; t < BW; ++t) {
                         const unsigned wb = __shfl_sync(0xffffffffu, mine, t);
                         sts_u8_if((wb >> lane) & 1u, aL + (unsigned)(off + __popc(wb & lt)), (unsigned)(t * 32 + lane));
                         off += __popc(wb);
@@ -233,9 +240,19 @@ __device__ __noinline__ void receivers_c(const DevConst &c, Smem &S, unsigned ch
     any_marine = __syncthreads_or(mar);
 }
 
-// ---- stack order (FLWnetwork.f90:21-71, FLOWstack.f90:24-40), see fast::links_stack -------------------------------
-// The link construction needs the receivers (2N) in shared memory, the ranking the tour (8N): the tour words are written
-// to global scratch while the receivers are in place and come back with one coalesced copy.
+// ---- stack order (FLWnetwork.f90:21-71, FLOWstack.f90:24-40) ------------------------------------------------------------
+// Same Euler tour as fast::links_stack (enter -> first child, exit -> next sibling / parent's exit / next root), ranked in
+// O(2N) work instead of ~15 pointer-jumping rounds over all 2N elements (Helman-JaJa list ranking):
+//  * an element's weight is its parity (enter events are the even elements), so the tour is 2N u16 successors (4N bytes);
+//    they are written to global scratch while the receivers (2N bytes) sit in shared memory for the link construction
+//    and come back with one coalesced copy;
+//  * every element whose index is a multiple of 2^sh, plus the head of the tour, is a splitter; a thread walks from its
+//    splitter to the next one counting enter events and elements (a few steps: the splitters are dense because the
+//    other half of the shared memory holds their table), the splitters are ranked by pointer jumping on one 64-bit word
+//    each (successor | enter events to the end | elements to the end), a second walk hands every enter event its rank;
+//  * counting all elements as well gives the tour index, and with it the depth of a node in the receiver tree:
+//        depth(v) = 2 * (#enter events before enter(v)) - (#elements before enter(v))
+//    which discharge_c needs for its breadth-first layout (filled surface only).
 template <int KDT>
 __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned char *dsm, const int *rcvg, int *stack, int *pos,
                                            int *baselist, int &nbase, bool filled, bool shuffle, unsigned long long seedstep)
@@ -245,7 +262,8 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     unsigned short *r16 = (unsigned short *)dsm;                                  // [Nq]
     unsigned long long *K = (unsigned long long *)(dsm + (size_t)2 * Nq + 64);    // shuffle keys behind the receivers
     const int kcap = (int)(((size_t)6 * Nq - 128) / 8);
-    unsigned *eug = (unsigned *)S.P.euA;                                          // [2N] tour words, global scratch
+    unsigned short *nxg = (unsigned short *)S.P.euA;                              // [2N] successors, global scratch
+    SubTick stl = sub_tick_begin(c);
 #pragma unroll 4
     for (int v = tid; v < N; v += TPB) r16[v] = (unsigned short)rcvg[v];
     __syncthreads();
@@ -272,10 +290,13 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
                 if (w > v && w < nx && r16[w] == r) nx = w;
             }
         }
-        eug[2 * v] = ((unsigned)((f != NONE16) ? 2 * f : 2 * v + 1) << 16) | 1u;
-        if (r != v) eug[2 * v + 1] = ((unsigned)((nx != NONE16) ? 2 * nx : 2 * r + 1) << 16);
-        if (filled) cnt8[v] = (unsigned char)n;           // donor counts: the breadth-first layout of discharge_c
+        const unsigned en = (unsigned)((f != NONE16) ? 2 * f : 2 * v + 1);
+        if (r != v) reinterpret_cast<unsigned *>(nxg)[v] = en | ((unsigned)((nx != NONE16) ? 2 * nx : 2 * r + 1) << 16);
+        else nxg[2 * v] = (unsigned short)en;               // a root's exit is linked to the next root below
+        if (filled) cnt8[v] = (unsigned char)n;              // donor counts: the breadth-first layout of discharge_c
     }
+    __syncthreads();
+    sub_tick(stl, 28);      // receivers to shared memory + link construction
     nbase = blk_compact(N, baselist, [&](int i) { return r16[i] == i; }, S);
     if (tid == 0) { if (filled) S.nbase = nbase; else S.nbase1 = nbase; }
     if (shuffle && nbase > 1) {
@@ -295,40 +316,99 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     for (int i = tid; i < nbase; i += TPB) {
         const int root = baselist[i];
         const int nxt = (i + 1 < nbase) ? baselist[i + 1] : NONE_I;
-        eug[2 * root + 1] = ((nxt != NONE_I) ? (unsigned)(2 * nxt) : END16) << 16;
+        nxg[2 * root + 1] = (unsigned short)((nxt != NONE_I) ? (unsigned)(2 * nxt) : END16);
         if (!filled) nsroot[root] = nxt;
     }
     __syncthreads();
-    unsigned *eu = (unsigned *)dsm;                                  // [2N]
+    unsigned short *nx16 = (unsigned short *)dsm;                    // [2N] successor of every tour element
     const int M = 2 * N;
     {
-        const uint2 *src = reinterpret_cast<const uint2 *>(eug);
-        uint2 *dst = reinterpret_cast<uint2 *>(eu);
+        const unsigned *src = reinterpret_cast<const unsigned *>(nxg);
+        unsigned *dst = reinterpret_cast<unsigned *>(nx16);
 #pragma unroll 4
         for (int e = tid; e < N; e += TPB) dst[e] = src[e];
     }
     __syncthreads();
+    sub_tick(stl, 29);      // base levels, shuffle, tour back into shared memory
+    unsigned long long *T = (unsigned long long *)(dsm + (size_t)4 * Nq);   // [<= Nq / 2] splitter table
+    const int sh = 3 + ((c.dbg >> 5) & 3);
+    const int S_reg = ((M - 1) >> sh) + 1;                           // (M >> 3) + 2 <= Nq / 2 always
+    const unsigned smask = (1u << sh) - 1u;
+    const unsigned head = 2u * (unsigned)baselist[0];
+    const bool head_extra = (head & smask) != 0u;
+    const int S_tot = S_reg + (head_extra ? 1 : 0);
+    // Both walks are ONE loop per lane over all its sublists (a lane that finishes a sublist starts its next one in the
+    // same iteration), so the lanes of a warp stay busy until their whole share is done instead of idling at the end of
+    // every sublist behind the longest one of the 32.
+    {
+        int sp = tid;
+        unsigned e = 0u, ce = 0u, ca = 0u;
+        bool run = sp < S_tot;
+        if (run) e = (sp < S_reg) ? ((unsigned)sp << sh) : head;
+        while (run) {
+            const unsigned nx = nx16[e];
+            ce += (~e) & 1u;
+            ++ca;
+            const bool last = (nx == END16), split = !last && ((nx & smask) == 0u || nx == head);
+            if (last || split) {
+                const unsigned t = last ? END16 : ((head_extra && nx == head) ? (unsigned)S_reg : (nx >> sh));
+                T[sp] = (unsigned long long)t | ((unsigned long long)ce << 16) | ((unsigned long long)ca << 32);
+                sp += TPB;
+                run = sp < S_tot;
+                ce = 0u; ca = 0u;
+                e = (sp < S_reg) ? ((unsigned)sp << sh) : head;
+            } else e = nx;
+        }
+    }
+    __syncthreads();
     int active = 1;
-    while (active) {
+    while (active) {            // suffix sums over the splitter chain; a word is read and written as one 64-bit access
         int loc = 0;
-        for (int e0 = tid; e0 < M; e0 += 4 * TPB) {
-            unsigned w[4], nx[4], w2[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { const int e = e0 + u * TPB; w[u] = (e < M) ? eu[e] : 0xFFFF0000u; nx[u] = w[u] >> 16; }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) w2[u] = (nx[u] != END16) ? eu[nx[u]] : 0u;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (nx[u] != END16) { eu[e0 + u * TPB] = (w2[u] & 0xFFFF0000u) | ((w[u] + w2[u]) & 0xFFFFu); loc = 1; }
+        for (int sp = tid; sp < S_tot; sp += TPB) {
+            const unsigned long long a = T[sp];
+            const unsigned na = (unsigned)(a & 0xFFFFull);
+            if (na != END16) {
+                const unsigned long long a2 = T[na];
+                T[sp] = (a2 & 0xFFFFull) | ((((a >> 16) + (a2 >> 16)) & 0xFFFFull) << 16) | (((a >> 32) + (a2 >> 32)) << 32);
+                loc = 1;
+            }
         }
         active = __syncthreads_or(loc);
     }
-    for (int v = tid; v < N; v += TPB) {
-        const int p = N - (int)(eu[2 * v] & 0xFFFFu);
-        pos[v] = p;
-        stack[p] = v;
+    sub_tick(stl, 30);      // first walk + splitter ranking
+    unsigned short *depg = (unsigned short *)S.P.i[I_FC];            // depth by stack position (filled surface: discharge_c)
+    {
+        int sp = tid;
+        unsigned e = 0u, re = 0u, ra = 0u;
+        bool run = sp < S_tot;
+        if (run) {
+            e = (sp < S_reg) ? ((unsigned)sp << sh) : head;
+            const unsigned long long a = T[sp];
+            re = (unsigned)((a >> 16) & 0xFFFFull); ra = (unsigned)(a >> 32);
+        }
+        while (run) {
+            const unsigned nx = nx16[e];
+            if (!(e & 1u)) {
+                const int v = (int)(e >> 1), p = N - (int)re;
+                pos[v] = p;
+                stack[p] = v;
+                if (filled) depg[p] = (unsigned short)(2 * p - (M - (int)ra));
+                --re;
+            }
+            --ra;
+            if (nx == END16 || (nx & smask) == 0u || nx == head) {
+                sp += TPB;
+                run = sp < S_tot;
+                if (run) {
+                    e = (sp < S_reg) ? ((unsigned)sp << sh) : head;
+                    const unsigned long long a = T[sp];
+                    re = (unsigned)((a >> 16) & 0xFFFFull); ra = (unsigned)(a >> 32);
+                }
+            } else e = nx;
+        }
     }
     __syncthreads();
+    sub_tick(stl, 31);      // second walk
 }
 
 // ---- pit ids and volumes (FLOWalgo.f90:130-165), see fast::basins ---------------------------------------------------
@@ -444,20 +524,26 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
     double *vals = (double *)dsm;                                                // [Nq] by BFS position, after all of them
     const unsigned lt = (1u << lane) - 1u;
     SubTick stc = sub_tick_begin(c);
-    for (int v = tid; v < N; v += TPB) { const unsigned r = (unsigned)rcv[v]; jd[v] = (r << 16) | (r == (unsigned)v ? 0u : 1u); }
-    __syncthreads();
-    int act = 1;
-    while (act) {
-        int loc = 0;
-        for (int v = tid; v < N; v += TPB) {
-            const unsigned w = jd[v], j = w >> 16;
-            const unsigned wj = jd[j];
-            if ((wj >> 16) != j) { jd[v] = (wj & 0xFFFF0000u) | ((w + wj) & 0xFFFFu); loc = 1; }
-        }
-        act = __syncthreads_or(loc);
-    }
     int md = 0;
-    for (int p = tid; p < N; p += TPB) { const int d = (int)(jd[stack[p]] & 0xFFFFu); dpos[p] = (unsigned short)d; md = max(md, d); }
+    if (c.dbg & 16) {            // reference form: depths by pointer jumping over the receivers
+        for (int v = tid; v < N; v += TPB) { const unsigned r = (unsigned)rcv[v]; jd[v] = (r << 16) | (r == (unsigned)v ? 0u : 1u); }
+        __syncthreads();
+        int act = 1;
+        while (act) {
+            int loc = 0;
+            for (int v = tid; v < N; v += TPB) {
+                const unsigned w = jd[v], j = w >> 16;
+                const unsigned wj = jd[j];
+                if ((wj >> 16) != j) { jd[v] = (wj & 0xFFFF0000u) | ((w + wj) & 0xFFFFu); loc = 1; }
+            }
+            act = __syncthreads_or(loc);
+        }
+        for (int p = tid; p < N; p += TPB) { const int d = (int)(jd[stack[p]] & 0xFFFFu); dpos[p] = (unsigned short)d; md = max(md, d); }
+    } else {                     // links_stack_c left the depth of every stack position behind
+        const unsigned short *__restrict__ depg = (const unsigned short *)S.P.i[I_FC];
+#pragma unroll 4
+        for (int p = tid; p < N; p += TPB) { const int d = depg[p]; dpos[p] = (unsigned short)d; md = max(md, d); }
+    }
     md = __reduce_max_sync(0xffffffffu, md);
     if (lane == 0) atomicMax(&S.ibuf[2], md);
     __syncthreads();
@@ -561,6 +647,8 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
 }
 
 // FLOWalgo.f90:299-330 on the filled surface, same arithmetic as fast::flow_cfl; everything comes from global memory
+// STD = the exponents every BASELINE config uses (m = 0.5, n = 1): sqrt and the identity, no call to pow in the loop
+template <bool STD>
 __device__ __noinline__ double flow_cfl_c(const DevConst &c, Smem &S, double erod)
 {
     __builtin_assume(__isShared(&c)); __builtin_assume(__isShared(&S));
@@ -572,7 +660,7 @@ __device__ __noinline__ double flow_cfl_c(const DevConst &c, Smem &S, double ero
     for (int d = threadIdx.x; d < N; d += TPB) {
         const double q = Q[d], dz = dzw[d], dist = distr[d];      // a base level has dz = 0: skipped like d == r
         if (q > 0. && dz > 0.) {
-            const double tmp = dist / (erod * powx(q, em) * powx(dz / dist, en1));
+            const double tmp = STD ? dist / (erod * sqrt(q) * 1.0) : dist / (erod * powx(q, em) * powx(dz / dist, en1));
             cfl = fmin(tmp, cfl);
         }
     }
@@ -580,6 +668,7 @@ __device__ __noinline__ double flow_cfl_c(const DevConst &c, Smem &S, double ero
 }
 
 // ---- stream power (FLOWalgo.f90:583-1044), see fast::streampower ---------------------------------------------------------
+template <bool STD>
 __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned char *dsm, double erod, double sea, double dt)
 {
     BL_ASSUME_SHARED(c, S, dsm);
@@ -606,7 +695,7 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
         if (r != d && dh > 0. && waterH == 0. && fh >= sea) {
             if (dist > 0.) {
                 const double slp = dh / dist;
-                SPL = -erod * 1. * 1. * powx(q, c.m) * powx(slp, c.n);
+                SPL = STD ? -erod * 1. * 1. * sqrt(q) * slp : -erod * 1. * 1. * powx(q, c.m) * powx(slp, c.n);
                 totspl = totspl + SPL;
                 if (-totspl * dt > dh) {
                     const double frac = dh / (-totspl * dt);
@@ -707,7 +796,8 @@ __device__ __noinline__ void streampower_c(const DevConst &c, Smem &S, unsigned 
     long long *pcs = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
     long long ts0 = clock64();
 #define STICK(i) do { if (tid == 0) { long long t1_ = clock64(); pcs[i] += t1_ - ts0; ts0 = t1_; } } while (0)
-    sp_prepass_c(c, S, dsm, erod, sea, dt);
+    if (c.m == 0.5 && c.n == 1.0) sp_prepass_c<true>(c, S, dsm, erod, sea, dt);
+    else sp_prepass_c<false>(c, S, dsm, erod, sea, dt);
     STICK(27);
     sp_route_c(c, S, dsm, dt);
     STICK(15);
@@ -962,7 +1052,8 @@ __device__ void time_step(const DevConst &c, Smem &S, unsigned char *dsm)
     BL_TICK(6);
     const bool deep = S.ibuf[5] != 0;          // uniform: written before the barriers that end discharge_c
     {
-        const double flowcfl = deep ? phase_cfl(c, S, S.erod) : flow_cfl_c(c, S, S.erod);
+        const bool stdexp = (c.m == 0.5 && c.n == 1.0);
+        const double flowcfl = deep ? phase_cfl(c, S, S.erod) : (stdexp ? flow_cfl_c<true>(c, S, S.erod) : flow_cfl_c<false>(c, S, S.erod));
         double cfl = fmin(flowcfl, c.hill);
         cfl = py2_floorish(cfl);
         cfl = fmin(cfl, S.tStop - S.tNow);

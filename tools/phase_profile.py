@@ -46,6 +46,8 @@ print("  launch:", info)
 if info["path"] == "compact":
     print("  sub discharge_c (cyc/step): depths %.0f, stable sort %.0f, records+init %.0f, level loop %.0f, Q scatter %.0f; stream power pre-pass %.0f (routing = prepass+scan - pre-pass)"
           % tuple((pc[:, i] / steps).mean() for i in (22, 23, 24, 25, 26, 27)))
+    print("  sub links_stack_c, both surfaces (cyc/step): links %.0f, bases+copy %.0f, walk A + splitter rank %.0f, walk B %.0f"
+          % tuple((pc[:, i] / steps).mean() for i in (28, 29, 30, 31)))
 if DBG & 4:
     print("  fill diag (warp 0, cyc/step): scan %.0f, eval %.0f, barrier %.0f; rounds/step %.1f, evals/step (CTA) %.0f, eval passes/step (warp 0) %.1f"
           % tuple((pc[:, i] / steps).mean() for i in (22, 23, 24, 25, 26, 27)))
