@@ -30,7 +30,7 @@ FIELDS = dict(z=F_Z, cumdiff=F_CUMDIFF, cumhill=F_CUMHILL, fillH=F_FILLH, maxh=F
 
 ST_CASCADE_GUARD, ST_DRAIN_CYCLE, ST_NAN = 1, 4, 8
 ST_FATAL = ST_CASCADE_GUARD | ST_NAN      # evaluations whose result must not enter Metropolis
-OPT_FORCE_GENERIC, OPT_NO_L2_PERSIST, OPT_LEAN, OPT_COMPACT, OPT_NO_COMPACT = 1, 2, 4, 8, 16
+OPT_FORCE_GENERIC, OPT_NO_L2_PERSIST, OPT_COMPACT, OPT_NO_COMPACT = 1, 2, 8, 16
 
 
 class BlMesh(C.Structure):

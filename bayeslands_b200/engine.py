@@ -34,11 +34,10 @@ class Engine:
 
     def __init__(self, mesh, inp, B: int, device: int = 0, real_elev: Optional[np.ndarray] = None,
                  erdp_coords: Optional[Sequence] = None, shuffle_mode: int = 1, sealevel=None, disp=None,
-                 tpb: int = 0, force_generic: bool = False, l2_persist: bool = True, lean: bool = False,
+                 tpb: int = 0, force_generic: bool = False, l2_persist: bool = True,
                  debug: int = 0, compact: Optional[bool] = None):
         """Engine options (`bl_params.opt_*`; the library reads no environment variables): `tpb` threads per CTA
-        (0 = automatic), `force_generic` the L2-resident device path, `lean` production mode without the per-stage
-        products kept for `field()`, `compact` the 8-bytes-per-node shared-memory layout (None = automatic: chosen when it
+        (0 = automatic), `force_generic` the L2-resident device path, `compact` the 8-bytes-per-node shared-memory layout (None = automatic: chosen when it
         lets two landscapes share an SM; True = wherever it fits; False = never)."""
         if not torch.cuda.is_available():
             raise _lib.BlError("bayeslands_b200.Engine needs a CUDA device (no CPU fallback)")
@@ -96,7 +95,6 @@ class Engine:
             p.npts, p.pts_cell = self.npts, _ip(cells)
         p.opt_tpb = int(tpb)
         p.opt_flags = ((_lib.OPT_FORCE_GENERIC if force_generic else 0) | (0 if l2_persist else _lib.OPT_NO_L2_PERSIST)
-                       | (_lib.OPT_LEAN if lean else 0)
                        | (0 if compact is None else (_lib.OPT_COMPACT if compact else _lib.OPT_NO_COMPACT)))
         p.opt_debug = int(debug)
         self._m, self._p = m, p

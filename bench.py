@@ -307,7 +307,8 @@ def run_ours(args):
                                 node_steps_per_s=value * float(np.mean(steps_last)) * m.N,
                                 l2_policy="per-step working set %.0f MB > L2 (fresh proposals every step)"
                                           % (eng.workspace.numel() / 1e6),
-                                parallelism="proposals sharded, %d per GPU" % B, status_bits=status),
+                                parallelism="proposals sharded, %d per GPU" % B, status_bits=status,
+                                launch=eng.info()),
                     e2e=dict(value=e2e_val, unit="evals/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=int(launches),
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,

@@ -102,7 +102,6 @@ typedef struct {
 #define BL_OPT_NO_L2_PERSIST 2   /* do not pin the mesh constants in L2 */
 #define BL_OPT_COMPACT       8   /* use the 8-bytes-per-node shared-memory layout wherever it fits (it is chosen automatically when it lets two landscapes share an SM) */
 #define BL_OPT_NO_COMPACT   16   /* never use it */
-#define BL_OPT_LEAN          4   /* production mode: skip the stores of per-stage products kept only for bl_get_field */
 
 typedef struct bl_ctx bl_ctx;
 
