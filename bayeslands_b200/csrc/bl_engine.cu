@@ -235,11 +235,16 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     const bool compact_ok = small_ids && lev_contig_h && !marine_cfg && !(p->opt_flags & BL_OPT_NO_COMPACT);
     // CTA size and layout: small meshes 256 threads (several CTAs per SM); else two 512-thread CTAs per SM when two
     // landscapes fit - in the 17-bytes-per-node layout or in the compact one - else one 1024-thread CTA per SM
+    // Sharing an SM only pays when there are more landscapes than SMs: a lone CTA finishes a time step sooner with 1024
+    // threads and the 17-byte layout (single chains, speculative look-ahead batches of one wave).
+    int nsm = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    const bool share = (B > nsm) || (p->opt_flags & BL_OPT_COMPACT);
     int tpb, compact = 0;
     if (p->opt_tpb) tpb = p->opt_tpb;
     else if (N <= 4096) tpb = 256;
-    else if (small_ids && fits(512, need_full, 2)) tpb = 512;
-    else if (compact_ok && fits(512, need_c512, 2)) tpb = 512;
+    else if (share && small_ids && fits(512, need_full, 2)) tpb = 512;
+    else if (share && compact_ok && fits(512, need_c512, 2)) tpb = 512;
     else tpb = 1024;
     if (compact_ok) {
         if (p->opt_flags & BL_OPT_COMPACT) compact = fits(tpb, compact_smem_need(Nq, tpb), 1) ? 1 : 0;

@@ -676,17 +676,32 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
     const Bfs B = bfs_arrays(S, N);
     double *vals = (double *)dsm;
     unsigned *evbits = (unsigned *)(dsm + (size_t)8 * Nq);
-    unsigned char *kindg = (unsigned char *)B.rec;
-    const int *__restrict__ pitID = S.P.i[I_PITID], *__restrict__ rcv = S.P.i[I_RCV];
-    const double *__restrict__ z = S.P.f[F_Z], *__restrict__ W = S.P.f[F_FILLH], *__restrict__ Qg = S.P.f[F_Q];
-    const double *__restrict__ maxhA = S.P.f[F_MAXH], *__restrict__ distr = S.P.f[F_E], *__restrict__ zrA = S.P.f[F_QS];
-    double *__restrict__ depo = S.P.f[F_DEPO], *__restrict__ ero = S.P.f[F_ERO];
-#pragma unroll 2
+    unsigned char *kindg;
+    // The per-proposal arrays are addressed as base + field * Np + node: ONE base pointer per element type lives in
+    // registers instead of a dozen array pointers (under the 64-register cap those were spilled and re-read from local
+    // memory in every iteration, a second memory round trip in front of each load).
+    double *__restrict__ const F = S.P.f[0];
+    int *__restrict__ const I = S.P.i[0];
+    const size_t Np = (size_t)np_of(N);
+#define PF_(k) (F + (size_t)(k) * Np)
+#define PI_(k) (I + (size_t)(k) * Np)
+    const int *pitID = PI_(I_PITID), *rcv = PI_(I_RCV);
+    const double *z = PF_(F_Z), *W = PF_(F_FILLH), *Qg = PF_(F_Q), *maxhA = PF_(F_MAXH), *distr = PF_(F_E), *zrA = PF_(F_QS);
+    double *depo = PF_(F_DEPO), *ero = PF_(F_ERO);
+    const unsigned short *posbA = reinterpret_cast<const unsigned short *>(PI_(I_PS)) + np_of(N);
+    kindg = reinterpret_cast<unsigned char *>(PI_(I_LC));
+#undef PF_
+#undef PI_
+    const double *__restrict__ areaA = c.area;
+    // every load of a node is issued before the first branch on it (a load behind a data-dependent branch costs its own
+    // memory round trip: the profile of the first version showed ten separate long-scoreboard waits per node)
+#pragma unroll 1
     for (int d = tid; d < N; d += TPB) {
         const int r = rcv[d];
-        const unsigned qd = B.posb[d];
-        const double zd = z[d], zr = zrA[d], fh = W[d], area = c.area[d];
-        const double q = Qg[d], dist = distr[d];
+        const unsigned qd = posbA[d];
+        const double zd = z[d], zr = zrA[d], fh = W[d], area = areaA[d];
+        const double q = Qg[d], dist = distr[d], mh0 = maxhA[d];
+        const int pp = pitID[d];
         double dh = 0.95 * (zd - zr);
         if (zd > sea && zr < sea) dh = 0.99 * (zd - sea);
         if (dh < 0.001) dh = 0.;
@@ -704,7 +719,7 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
                 }
             }
         }
-        double maxh = maxhA[d];
+        double maxh = mh0;
         if (waterH > 0.) maxh = waterH;
         else if (zd < sea) maxh = sea - zd;
         maxh = 0.95 * maxh;
@@ -713,9 +728,8 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
         if (totspl < 0.) { k = 0; e = SPL * dt * area; }
         else if (totspl >= 0. && area > 0.) {
             if (waterH > 0. && fh > sea) {
-                k = 1;
-                const int pp = pitID[d];          // pit under the sea: static first cascade step (:979-991)
-                if (pp >= 0 && c.area[pp] > 0. && W[pp] < sea) k = (zd < sea) ? 2 : 4;
+                k = 1;                            // pit under the sea: static first cascade step (:979-991)
+                if (pp >= 0 && areaA[pp] > 0. && W[pp] < sea) k = (zd < sea) ? 2 : 4;
             }
             else if (zd <= sea) k = 2;
             else if (maxh > 0. && waterH == 0. && d != r && zd > sea) { k = 3; e = maxh; }

@@ -18,11 +18,16 @@ def _engine(crater_fast, B, **kw):
     return Engine(m, inp, B, real_elev=d["final_elev"], erdp_coords=CRATER_FAST_COORDS, **kw)
 
 
-def test_crater_default_is_two_compact_ctas_per_sm(crater_fast):
-    eng = _engine(crater_fast, 2)
-    info = eng.info()
+def test_crater_layout_follows_the_batch_size(crater_fast):
+    """More landscapes than SMs: two compact 512-thread CTAs per SM.  Up to one wave: one 1024-thread CTA per SM in the
+    17-byte layout (a lone landscape finishes a time step sooner that way)."""
+    import torch
+    nsm = torch.cuda.get_device_properties(0).multi_processor_count
+    info = _engine(crater_fast, 2 * nsm).info()
     assert info["path"] == "compact" and info["tpb"] == 512 and info["ctas_per_sm"] >= 2, info
-    assert _engine(crater_fast, 2, compact=False).info()["path"] == "shared"
+    info = _engine(crater_fast, 2).info()
+    assert info["path"] == "shared" and info["tpb"] == 1024, info
+    assert _engine(crater_fast, 2 * nsm, compact=False).info()["path"] == "shared"
 
 
 @pytest.mark.parametrize("shuffle", [0, 1])
