@@ -618,23 +618,30 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
     __syncthreads();
     sub_tick(stc, 24);      // records + initial values
     {
+        const unsigned *__restrict__ recA = B.rec;
         int b0 = S.boff[maxd], b1 = S.boff[maxd + 1];
-        unsigned rcur = (b0 + tid < b1) ? B.rec[b0 + tid] : 0u;
+        unsigned rcur = (b0 + tid < b1) ? recA[b0 + tid] : 0u;
         for (int d = maxd; d >= 0; --d) {
-            int nb0 = 0, nb1 = 0;
-            unsigned rnext = 0u;
-            if (d > 0) { nb0 = S.boff[d - 1]; nb1 = S.boff[d]; if (nb0 + tid < nb1) rnext = B.rec[nb0 + tid]; }
-            for (int q = b0 + tid; q < b1; q += TPB) {
-                const unsigned r = (q == b0 + tid) ? rcur : B.rec[q];
-                const int n = (int)((r >> 16) & 0xFFu), f = (int)(r & 0xFFFFu);
-                if (n) {
-                    double acc = vals[q];
-                    for (int j = f + n - 1; j >= f; --j) acc = acc + vals[j];       // donors in descending id
-                    vals[q] = acc;
+            const int nb0 = (d > 0) ? S.boff[d - 1] : 0, nb1 = (d > 0) ? S.boff[d] : 0;
+            const int niter = (b1 - b0 + TPB - 1) / TPB;          // uniform
+            for (int it = 0; it < niter; ++it) {
+                const int q = b0 + tid + it * TPB;
+                // the record of this thread's next position (same bucket or the next one) is requested first
+                const int nq = (it + 1 < niter) ? q + TPB : nb0 + tid;
+                const int nlim = (it + 1 < niter) ? b1 : nb1;
+                const unsigned rn = (nq < nlim) ? recA[nq] : 0u;
+                if (q < b1) {
+                    const int n = (int)((rcur >> 16) & 0xFFu), f = (int)(rcur & 0xFFFFu);
+                    if (n) {
+                        double acc = vals[q];
+                        for (int j = f + n - 1; j >= f; --j) acc = acc + vals[j];       // donors in descending id
+                        vals[q] = acc;
+                    }
                 }
+                rcur = rn;
             }
             __syncthreads();
-            b0 = nb0; b1 = nb1; rcur = rnext;
+            b0 = nb0; b1 = nb1;
         }
     }
     sub_tick(stc, 25);      // level loop
@@ -682,26 +689,25 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
     // memory in every iteration, a second memory round trip in front of each load).
     double *__restrict__ const F = S.P.f[0];
     int *__restrict__ const I = S.P.i[0];
-    const size_t Np = (size_t)np_of(N);
-#define PF_(k) (F + (size_t)(k) * Np)
-#define PI_(k) (I + (size_t)(k) * Np)
-    const int *pitID = PI_(I_PITID), *rcv = PI_(I_RCV);
-    const double *z = PF_(F_Z), *W = PF_(F_FILLH), *Qg = PF_(F_Q), *maxhA = PF_(F_MAXH), *distr = PF_(F_E), *zrA = PF_(F_QS);
-    double *depo = PF_(F_DEPO), *ero = PF_(F_ERO);
-    const unsigned short *posbA = reinterpret_cast<const unsigned short *>(PI_(I_PS)) + np_of(N);
-    kindg = reinterpret_cast<unsigned char *>(PI_(I_LC));
-#undef PF_
-#undef PI_
+    const unsigned Np = (unsigned)np_of(N);
+#define FD(k, i) F[(unsigned)(k) * Np + (unsigned)(i)]
+#define ID(k, i) I[(unsigned)(k) * Np + (unsigned)(i)]
+    const unsigned short *posbA = reinterpret_cast<const unsigned short *>(I + (size_t)I_PS * Np) + Np;
+    kindg = reinterpret_cast<unsigned char *>(I + (size_t)I_LC * Np);
     const double *__restrict__ areaA = c.area;
     // every load of a node is issued before the first branch on it (a load behind a data-dependent branch costs its own
     // memory round trip: the profile of the first version showed ten separate long-scoreboard waits per node)
 #pragma unroll 1
-    for (int d = tid; d < N; d += TPB) {
-        const int r = rcv[d];
+    for (int d_ = tid; d_ < N; d_ += TPB) {
+        // (the loop index is laundered through an asm move: otherwise the compiler keeps one running address per array,
+        // a dozen 64-bit induction variables that it then spills and re-reads from local memory in every iteration)
+        int d;
+        asm volatile("mov.s32 %0, %1;" : "=r"(d) : "r"(d_));
+        const int r = ID(I_RCV, d);
         const unsigned qd = posbA[d];
-        const double zd = z[d], zr = zrA[d], fh = W[d], area = areaA[d];
-        const double q = Qg[d], dist = distr[d], mh0 = maxhA[d];
-        const int pp = pitID[d];
+        const double zd = FD(F_Z, d), zr = FD(F_QS, d), fh = FD(F_FILLH, d), area = areaA[d];
+        const double q = FD(F_Q, d), dist = FD(F_E, d), mh0 = FD(F_MAXH, d);
+        const int pp = ID(I_PITID, d);
         double dh = 0.95 * (zd - zr);
         if (zd > sea && zr < sea) dh = 0.99 * (zd - sea);
         if (dh < 0.001) dh = 0.;
@@ -729,7 +735,7 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
         else if (totspl >= 0. && area > 0.) {
             if (waterH > 0. && fh > sea) {
                 k = 1;                            // pit under the sea: static first cascade step (:979-991)
-                if (pp >= 0 && areaA[pp] > 0. && W[pp] < sea) k = (zd < sea) ? 2 : 4;
+                if (pp >= 0 && areaA[pp] > 0. && FD(F_FILLH, pp) < sea) k = (zd < sea) ? 2 : 4;
             }
             else if (zd <= sea) k = 2;
             else if (maxh > 0. && waterH == 0. && d != r && zd > sea) { k = 3; e = maxh; }
@@ -738,9 +744,12 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
         } else k = 5;
         kindg[4 * qd + 3] = (unsigned char)k;
         vals[qd] = e;
-        depo[d] = 0.;
-        ero[d] = 0.;
+        if (k == 3) FD(F_SEDIN, qd) = area;          // the routing divides by it (rule 3 only)
+        FD(F_DEPO, d) = 0.;
+        FD(F_ERO, d) = 0.;
     }
+#undef FD
+#undef ID
     for (int v = tid; v < Nq / 32; v += TPB) evbits[v] = 0u;
     __syncthreads();
 }
@@ -754,46 +763,60 @@ __device__ __noinline__ void sp_route_c(const DevConst &c, Smem &S, unsigned cha
     double *vals = (double *)dsm;
     unsigned *evbits = (unsigned *)(dsm + (size_t)8 * Nq);
     double *depo = S.P.f[F_DEPO], *ero = S.P.f[F_ERO], *pdep = S.P.f[F_PDEP];
+    const double *__restrict__ areaq = S.P.f[F_SEDIN];       // control volume by position (pre-pass; rule 3 only)
+    const unsigned *__restrict__ recA = B.rec;
+    const unsigned short *__restrict__ ordA = B.order;
     const int *posg = S.P.i[I_POS];
     const int maxd = S.ibuf[3];
+    // A thread's items are the positions q = b0 + tid, + TPB, ... of every bucket, deepest bucket first.  The record, the
+    // node id and the control volume of the NEXT item (same bucket or the next one) are requested before the current
+    // item is evaluated, so no global load sits on the dependent chain of a level.
     int b0 = S.boff[maxd], b1 = S.boff[maxd + 1];
     unsigned rcur = 0u, ccur = 0u;
-    if (b0 + tid < b1) { rcur = B.rec[b0 + tid]; ccur = B.order[b0 + tid]; }
+    double acur = 0.;
+    if (b0 + tid < b1) { rcur = recA[b0 + tid]; ccur = ordA[b0 + tid]; acur = areaq[b0 + tid]; }
     for (int d = maxd; d >= 0; --d) {
-        int nb0 = 0, nb1 = 0;
-        unsigned rnext = 0u, cnext = 0u;
-        if (d > 0) { nb0 = S.boff[d - 1]; nb1 = S.boff[d]; if (nb0 + tid < nb1) { rnext = B.rec[nb0 + tid]; cnext = B.order[nb0 + tid]; } }
-        for (int q = b0 + tid; q < b1; q += TPB) {
-            const bool pre = (q == b0 + tid);
-            const unsigned r = pre ? rcur : B.rec[q];
-            const int cur = (int)(pre ? ccur : (unsigned)B.order[q]);
-            const int n = (int)((r >> 16) & 0xFFu), f = (int)(r & 0xFFFFu), k = (int)(r >> 24);
-            double acc = 0. * dt;
-            for (int j = f + n - 1; j >= f; --j) acc = acc + vals[j];
-            const double own = vals[q];
-            double Qs = 0., erodep = 0.;
-            if (k == 0) { erodep = own; Qs = -erodep + acc; }
-            else if (k == 1) {
-                if (acc != 0.) {
-                    pdep[cur] = acc;
-                    if (acc > 0.) { const int ri = N - 1 - posg[cur]; atomicOr(&evbits[ri >> 5], 1u << (ri & 31)); }
+        const int nb0 = (d > 0) ? S.boff[d - 1] : 0, nb1 = (d > 0) ? S.boff[d] : 0;
+        const int niter = (b1 - b0 + TPB - 1) / TPB;          // uniform
+        for (int it = 0; it < niter; ++it) {
+            const int q = b0 + tid + it * TPB;
+            const int nq = (it + 1 < niter) ? q + TPB : nb0 + tid;
+            const int nlim = (it + 1 < niter) ? b1 : nb1;
+            unsigned rn = 0u, cn = 0u;
+            double an = 0.;
+            if (nq < nlim) { rn = recA[nq]; cn = ordA[nq]; an = areaq[nq]; }
+            if (q < b1) {
+                const unsigned r = rcur;
+                const int cur = (int)ccur;
+                const int n = (int)((r >> 16) & 0xFFu), f = (int)(r & 0xFFFFu), k = (int)(r >> 24);
+                double acc = 0. * dt;
+                for (int j = f + n - 1; j >= f; --j) acc = acc + vals[j];
+                const double own = vals[q];
+                double Qs = 0., erodep = 0.;
+                if (k == 0) { erodep = own; Qs = -erodep + acc; }
+                else if (k == 1) {
+                    if (acc != 0.) {
+                        pdep[cur] = acc;
+                        if (acc > 0.) { const int ri = N - 1 - posg[cur]; atomicOr(&evbits[ri >> 5], 1u << (ri & 31)); }
+                    }
                 }
+                else if (k == 2) { erodep = acc; }
+                else if (k == 3) {
+                    const double area = acur;
+                    const double totflx = 0. + acc, maxh = own;
+                    if (totflx / area < maxh) erodep = acc;
+                    else { const double frac = acc / totflx; erodep = frac * maxh * area; Qs = acc - erodep; }
+                } else if (k == 4) Qs = acc;
+                if (!(k == 1 && acc != 0.)) {
+                    if (erodep < 0.) ero[cur] = 0. + erodep;
+                    else if (erodep != 0.) depo[cur] = 0. + erodep;
+                }
+                vals[q] = Qs;
             }
-            else if (k == 2) { erodep = acc; }
-            else if (k == 3) {
-                const double area = c.area[cur];
-                const double totflx = 0. + acc, maxh = own;
-                if (totflx / area < maxh) erodep = acc;
-                else { const double frac = acc / totflx; erodep = frac * maxh * area; Qs = acc - erodep; }
-            } else if (k == 4) Qs = acc;
-            if (!(k == 1 && acc != 0.)) {
-                if (erodep < 0.) ero[cur] = 0. + erodep;
-                else if (erodep != 0.) depo[cur] = 0. + erodep;
-            }
-            vals[q] = Qs;
+            rcur = rn; ccur = cn; acur = an;
         }
         __syncthreads();
-        b0 = nb0; b1 = nb1; rcur = rnext; ccur = cnext;
+        b0 = nb0; b1 = nb1;
     }
     __syncthreads();
 }

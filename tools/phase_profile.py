@@ -32,7 +32,7 @@ print("config", cfg, "B", B, "tpb", TPB, "debug", DBG, "evals/s %.1f" % (B / dt)
 print("mean cycles/step per phase:")
 for i, nm in enumerate(_lib.PHASES):
     print("  %-12s %10.0f cyc  %5.1f%%" % (nm, (pc[:, i] / steps).mean(), 100 * pc[:, i].sum() / tot.sum()))
-print("  diag streampower split (cyc/step): prepass+scan %.0f, event compaction %.0f, parallel replay %.0f, serial replay %.0f" % tuple((pc[:,i]/steps).mean() for i in (15,12,13,14)))
+print("  diag streampower split (cyc/step): prepass+scan (compact layout: routing only) %.0f, event compaction %.0f, parallel replay %.0f, serial replay %.0f" % tuple((pc[:,i]/steps).mean() for i in (15,12,13,14)))
 tot = pc[:, :12].sum(1)
 print("  total        %10.0f cyc/step  (%.1f us at 1.965 GHz)" % ((tot / steps).mean(), (tot / steps).mean() / 1965.0))
 
@@ -44,7 +44,7 @@ for i in sorted(names):
 info = eng.info()
 print("  launch:", info)
 if info["path"] == "compact":
-    print("  sub discharge_c (cyc/step): depths %.0f, stable sort %.0f, records+init %.0f, level loop %.0f, Q scatter %.0f; stream power pre-pass %.0f (routing = prepass+scan - pre-pass)"
+    print("  sub discharge_c (cyc/step): depths %.0f, stable sort %.0f, records+init %.0f, level loop %.0f, Q scatter %.0f; stream power pre-pass %.0f"
           % tuple((pc[:, i] / steps).mean() for i in (22, 23, 24, 25, 26, 27)))
     print("  sub links_stack_c, both surfaces (cyc/step): links %.0f, bases+copy %.0f, walk A + splitter rank %.0f, walk B %.0f"
           % tuple((pc[:, i] / steps).mean() for i in (28, 29, 30, 31)))
