@@ -986,7 +986,14 @@ __device__ __noinline__ void apply_c(const DevConst &c, Smem &S, unsigned char *
     __syncthreads();
     const double *__restrict__ dispA = c.disp;
     const int nbn = c.bounds;
-    for (int g = tid; g < N; g += TPB) {
+    const double *__restrict__ areaA = c.area;
+    const float *__restrict__ ve32 = c.ve32;
+#pragma unroll 1
+    for (int g_ = tid; g_ < N; g_ += TPB) {
+        // every load of the node up front (rows included: a row fetched behind the flag test is a second round trip);
+        // the index is laundered so that the compiler keeps no per-array running address (see sp_prepass_c)
+        int g;
+        asm volatile("mov.s32 %0, %1;" : "=r"(g) : "r"(g_));
         double acc = 0.;
         const unsigned char fg = gflags[g];
         const unsigned inm = nbin[g];            // bit p: neighbour slot p is an inside node (borders2)
@@ -994,38 +1001,40 @@ __device__ __noinline__ void apply_c(const DevConst &c, Smem &S, unsigned char *
         const double sf = sedflux[g];
         const double c0 = cumdiff[g] + sf, h0 = cumhill[g];
         const double dsp = dispA ? dispA[g] * timestep : 0.;
-        if (fg & 2) {
-            Ids<KDT> ids;
-            load_ids<KDT>(c, g, ids);
-            if (c.ve32) {
-                const float4 *ve = reinterpret_cast<const float4 *>(c.ve32 + (size_t)g * KDT * 2);
+        const double area = areaA[g];
+        Ids<KDT> ids;
+        load_ids<KDT>(c, g, ids);
+        if (ve32) {
+            float4 v4[KDT / 2];
+            const float4 *ve = reinterpret_cast<const float4 *>(ve32 + (size_t)g * KDT * 2);
+#pragma unroll
+            for (int q = 0; q < KDT / 2; ++q) v4[q] = __ldg(ve + q);
+            if (fg & 2) {
 #pragma unroll
                 for (int q = 0; q < KDT / 2; ++q) {
-                    const float4 v4 = __ldg(ve + q);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int p = 2 * q + h;
                         if (ids.get(p) == NONE16) continue;
                         const int j = ids.get(p);
-                        const double ed = (double)(h ? v4.z : v4.x), di = (double)(h ? v4.w : v4.y), zj = zs[j];
+                        const double ed = (double)(h ? v4[q].z : v4[q].x), di = (double)(h ? v4[q].w : v4[q].y), zj = zs[j];
                         const bool bj = (inm >> p) & 1u;
                         if (bj && di > 0.) acc += ed * (zj - zg) / di;
                         if (!bj) { if (zj < zg && di > 0.) acc += ed * (zj - zg) / di; }
                     }
                 }
-            } else {
+            }
+        } else if (fg & 2) {
 #pragma unroll
-                for (int p = 0; p < KDT; ++p) {
-                    if (ids.get(p) == NONE16) continue;
-                    const int j = ids.get(p);
-                    const double di = c.edge[(size_t)p * N + g], ed = c.vor[(size_t)p * N + g], zj = zs[j];
-                    const bool bj = (inm >> p) & 1u;
-                    if (bj && di > 0.) acc += ed * (zj - zg) / di;
-                    if (!bj) { if (zj < zg && di > 0.) acc += ed * (zj - zg) / di; }
-                }
+            for (int p = 0; p < KDT; ++p) {
+                if (ids.get(p) == NONE16) continue;
+                const int j = ids.get(p);
+                const double di = c.edge[(size_t)p * N + g], ed = c.vor[(size_t)p * N + g], zj = zs[j];
+                const bool bj = (inm >> p) & 1u;
+                if (bj && di > 0.) acc += ed * (zj - zg) / di;
+                if (!bj) { if (zj < zg && di > 0.) acc += ed * (zj - zg) / di; }
             }
         }
-        const double area = c.area[g];
         const double ac = (area > 0.) ? 1. / area : 0.;
         double coeff = ac * ((zg >= sea) ? c.CDa : c.CDm);
         if (!(fg & 2)) { coeff = 0.; acc = 0.; }
