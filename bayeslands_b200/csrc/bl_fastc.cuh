@@ -428,23 +428,42 @@ __device__ __noinline__ void basins_c(const DevConst &c, Smem &S, unsigned char 
     const int *__restrict__ rcv1 = S.P.i[I_RCV1], *__restrict__ pos1 = S.P.i[I_POS1], *__restrict__ ns1 = S.P.i[I_NS];
     int *__restrict__ pitID = S.P.i[I_PITID];
     double *__restrict__ pitVol = S.P.f[F_PITVOL];
-#pragma unroll 4
-    for (int v = tid; v < N; v += TPB) root16[v] = (unsigned short)rcv1[v];
+    // The root of a node is the base level whose stack segment holds it (the real-surface stack lists tree after tree in
+    // base order): every base marks the position where its segment starts, the marks are propagated to the right
+    // (thread-local pass over a contiguous chunk, block scan of the chunks' last marks, second pass), and a node looks
+    // its root up at its own stack position.  O(N) work instead of ~12 pointer-jumping rounds over the receivers.
+    unsigned short *rootpos = root16;                        // [N] by stack position
+    for (int p = tid; p < N; p += TPB) rootpos[p] = NONE16;
     if (tid == 0) S.ibuf[4] = 0;
     __syncthreads();
-    int ch = 1;
-    while (ch) {
-        int loc = 0;
-        for (int v = tid; v < N; v += TPB) {
-            const unsigned short r = root16[v], rr = root16[r];
-            if (rr != r) { root16[v] = rr; loc = 1; }
+    for (int i = tid; i < nbase1; i += TPB) { const int root = base1[i]; rootpos[pos1[root]] = (unsigned short)root; }
+    __syncthreads();
+    {
+        const int C = (N + TPB - 1) / TPB;
+        const int p0 = min(N, tid * C), p1 = min(N, p0 + C);
+        unsigned last = NONE16;
+        for (int p = p0; p < p1; ++p) { const unsigned m = rootpos[p]; if (m != NONE16) last = m; }
+        // inclusive scan of "latest mark" over the threads (warp shuffles, then the warps' totals through S.scan)
+        unsigned inc = last;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o && inc == NONE16) inc = t;
         }
-        ch = __syncthreads_or(loc);
+        if (lane == 31) S.scan[warp] = (int)inc;
+        __syncthreads();
+        unsigned carry = NONE16;                             // latest mark of all earlier warps
+        for (int w = 0; w < warp; ++w) { const unsigned t = (unsigned)S.scan[w]; if (t != NONE16) carry = t; }
+        unsigned prev = __shfl_up_sync(0xffffffffu, inc, 1); // latest mark up to the previous lane
+        if (lane == 0) prev = NONE16;
+        unsigned cur = (prev != NONE16) ? prev : carry;
+        for (int p = p0; p < p1; ++p) { const unsigned m = rootpos[p]; if (m != NONE16) cur = m; else rootpos[p] = (unsigned short)cur; }
     }
+    __syncthreads();
 #pragma unroll 2
     for (int v = tid; v < N; v += TPB) {
         const bool wet = W[v] > z[v];
-        const int root = root16[v];
+        const int root = rootpos[pos1[v]];
         pitID[v] = (wet || root == v) ? root : -1;
         pitVol[v] = -1.0;
     }
