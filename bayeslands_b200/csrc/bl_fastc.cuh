@@ -622,18 +622,32 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
     __syncthreads();
     sub_tick(stc, 23);      // stable sort by depth
     // in the stack a node's first (lowest-id) donor follows it directly; the donors of one node are contiguous in q
-    for (int p = tid; p < N; p += TPB) {
-        const int v = stack[p];
-        const unsigned q = qpos[p];
-        const unsigned n = cnt8[v];
-        const unsigned f = (p + 1 < N) ? qpos[p + 1] : 0u;
-        B.rec[q] = f | (n << 16);
-        B.order[q] = (unsigned short)v;
-        B.posb[v] = (unsigned short)q;
-    }
-    __syncthreads();
+    // (by node id: the stack position, the donor count and the control volume of a node are coalesced, independent loads;
+    // the positions come from shared memory; the initial value travels through global scratch because the position
+    // tables still occupy the bytes of vals[])
+    {
+        const int *__restrict__ posA = S.P.i[I_POS];
+        const double *__restrict__ areaA = c.area;
+        unsigned *__restrict__ recw = B.rec;
+        unsigned short *__restrict__ ordw = B.order, *__restrict__ posw = B.posb;
+        double *__restrict__ q0g = S.P.f[F_VAL];
+        const int nbn = c.bounds;
 #pragma unroll 4
-    for (int q = tid; q < N; q += TPB) { const int v = B.order[q]; vals[q] = c.area[v] * ((v >= c.bounds) ? rain : 0.); }
+        for (int v = tid; v < N; v += TPB) {
+            const int p = posA[v];
+            const unsigned n = cnt8[v];
+            const double a = areaA[v];
+            const unsigned q = qpos[p];
+            const unsigned f = (p + 1 < N) ? qpos[p + 1] : 0u;
+            recw[q] = f | (n << 16);
+            ordw[q] = (unsigned short)v;
+            posw[v] = (unsigned short)q;
+            q0g[q] = a * ((v >= nbn) ? rain : 0.);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int q = tid; q < N; q += TPB) vals[q] = q0g[q];
+    }
     __syncthreads();
     sub_tick(stc, 24);      // records + initial values
     {
