@@ -17,7 +17,7 @@ c_ip = C.POINTER(C.c_int32)
 BL_KP = 20
 BL_NCKPT_MAX = 8
 BL_NPTS_MAX = 16
-BL_NPHASE = 32
+BL_NPHASE = 48
 PHASES = ["fill", "sfd", "stack1", "basins", "stack", "drainage", "discharge", "cfl", "streampower",
           "newdt", "erodep", "apply"]
 

@@ -18,7 +18,7 @@ namespace blc {
 constexpr int NONE_I = -1;
 constexpr unsigned END_U = 0xFFFFFFFFu;
 constexpr int TERM_BIT = 0x40000000;
-constexpr int NPHASE = 32;
+constexpr int NPHASE = 48;
 constexpr int LEVMAX = 63;
 constexpr int DYN_SMEM = 229376; // dynamic shared memory of the fast kernel (224 KB)
 

@@ -92,6 +92,9 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
 #ifndef BL_FILLC_ALL
 #define BL_FILLC_ALL 1
 #endif
+#ifndef BL_FILLC_PF
+#define BL_FILLC_PF 1
+#endif
     // sweeping warps and bitmap words per batch: with BL_FILLC_ALL every warp of a (<= 512-thread) CTA sweeps, 4 words at
     // a time, so a thin front is spread over twice as many warps; the slot lists take NWF * BW * 32 bytes either way
     constexpr bool ALLW = BL_FILLC_ALL && (NWARP <= 16);
@@ -122,11 +125,16 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
     const double eps = c.eps, TH = c.TH;
     const int nlev = c.nlev;
     const unsigned lt = (1u << lane) - 1u;
+    const bool diag = (c.dbg & 4) && tid == 0;          // diagnostics: cycles of warp 0 per round (scan / evaluation / barrier)
+    long long *pcd = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
+    long long tq = diag ? clock64() : 0;
+#define FDIAG(i) do { if (diag) { const long long t_ = clock64(); pcd[i] += t_ - tq; tq = t_; } } while (0)
     int change = 1;
     while (change) {
         int loc = 0;
         for (int l = 0; l < nlev; ++l) {
             const int n0 = nb + S.lev_off[l], n1 = nb + S.lev_off[l + 1];     // node id range of the level
+            if (diag) pcd[32] += 1;
             if (warp < NWF && n1 > n0) {
                 const int whi = (n1 - 1) >> 5;
                 // a batch = BW bitmap words of this warp (word w0 + NWF * t belongs to lane t): BW * 32 candidate ids
@@ -142,6 +150,7 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
                         mine = lds_u32(a) & m;               // nobody sets a bit of this level during its own pass
                         if (mine) {
                             red_and(a, ~mine);
+#if BL_FILLC_PF
                             // z and the id rows of these 32 nodes: requested now, needed by the evaluation below
                             const char *pz = (const char *)(zg + lo);
                             asm volatile("prefetch.global.L1 [%0];" ::"l"(pz));
@@ -149,6 +158,7 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
                             const char *pi = (const char *)(ngb16f + (size_t)lo * KDT);
 #pragma unroll
                             for (int u = 0; u < KDT / 2; ++u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pi + 128 * u));
+#endif
                         }
                     }
                     int off = 0;
@@ -159,17 +169,23 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
                         off += __popc(wb);
                     }
                     __syncwarp();
+                    FDIAG(34);
+                    if (diag) pcd[33] += off;
                     for (int i = lane; i < off; i += 32) {
                         const int s = (int)lds_u8(aL + (unsigned)i);
                         fill_eval_c<KDT, false>(ngb16f, zg, (w0 + NWF * (s >> 5)) * 32 + (s & 31), aW, aB, sea, eps, TH, loc);
                     }
                     __syncwarp();
+                    FDIAG(35);
                 }
             }
             if (l + 1 < nlev) __syncthreads();
+            FDIAG(36);
         }
         change = __syncthreads_or(loc);
+        FDIAG(36);
     }
+#undef FDIAG
 }
 
 // sfd.c:55-153: receivers on the filled surface (W is still in shared memory), then on the real one (z staged in the

@@ -152,8 +152,10 @@ int bl_get_scalars(bl_ctx *ctx, double *tnow, int64_t *steps, uint32_t *status, 
  * Phase order: fill, sfd, stack1, basins, stack, drainage, discharge, cfl, streampower, newdt(+rerun),
  * erodep, apply; slots 12-15 split streampower on the shared-memory path (event compaction, parallel replay,
  * serial replay, pre-pass + routing); slots 16-19 split erodep (first pass + land-pit compaction, small basins,
- * large basins, tail), 20 / 21 count large basins / land pits; the rest are reserved. */
-#define BL_NPHASE 32
+ * large basins, tail), 20 / 21 count large basins / land pits; 22-31 split discharge, the stream-power pre-pass and the
+ * stack ordering of the compact layout; 32-37 are fill diagnostics of the compact layout (opt_debug bit 2: rounds, evaluations,
+ * cycles of warp 0 in scan / evaluation / barrier); the rest are reserved. */
+#define BL_NPHASE 48
 int bl_get_phase_cycles(bl_ctx *ctx, int64_t *dst_host, void *stream);
 /* number of kernel launches issued by this context so far (for bench.py's gpu_launches) */
 int64_t bl_launch_count(const bl_ctx *ctx);

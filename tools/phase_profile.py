@@ -48,6 +48,9 @@ if info["path"] == "compact":
           % tuple((pc[:, i] / steps).mean() for i in (22, 23, 24, 25, 26, 27)))
     print("  sub links_stack_c, both surfaces (cyc/step): links %.0f, bases+copy %.0f, walk A + splitter rank %.0f, walk B %.0f"
           % tuple((pc[:, i] / steps).mean() for i in (28, 29, 30, 31)))
-if DBG & 4:
+    if DBG & 4:
+        print("  fill diag, warp 0 (per step): rounds %.1f, evaluations of warp 0 %.0f, cycles scan %.0f, evaluation %.0f, barrier wait %.0f"
+              % tuple((pc[:, i] / steps).mean() for i in (32, 33, 34, 35, 36)))
+if DBG & 4 and info["path"] != "compact":
     print("  fill diag (warp 0, cyc/step): scan %.0f, eval %.0f, barrier %.0f; rounds/step %.1f, evals/step (CTA) %.0f, eval passes/step (warp 0) %.1f"
           % tuple((pc[:, i] / steps).mean() for i in (22, 23, 24, 25, 26, 27)))
