@@ -941,21 +941,34 @@ __device__ __noinline__ void streampower_c(const DevConst &c, Smem &S, unsigned 
     int over = 0;
     if (S.ibuf[1])
         for (int e = tid; e < nev; e += TPB) { const int pit = ev_pit[e]; if (pit != NONE16 && W[pit] < sea) over = 1; }
-    for (int i = tid; i < nbase1; i += TPB) {
-        const int pit = base1[i];
-        if (!has_ev[pit]) continue;
-        double dp = depo[pit];
-        bool any = false;
-        double vol = 0.;
-        for (int e = 0; e < nev; ++e) {
-            if (ev_pit[e] != pit) continue;
-            if (!any) { vol = pitVol1[pit]; any = true; }
-            const double pitDep = ev_dep[e];
-            const double totdist = 0. + pitDep, tmpdist = 0. + dp;
-            if (tmpdist + totdist <= vol || pitDrain[pit] == pit) dp = dp + pitDep;
-            else { over = 1; break; }
+    // one WARP per pit that receives events: the lanes scan the event list 32 entries at a time and the matching events
+    // are applied in order (same sums as the serial loop: events of other pits do not touch this pit's deposit)
+    int *plist = S.P.i[I_EVENTS];
+    const int npl = blk_compact(nbase1, plist, [&](int i) { return has_ev[base1[i]] != 0; }, S);
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        const double *pitVolA = pitVol1;
+        for (int ip = warp; ip < npl; ip += NWARP) {
+            const int pit = base1[plist[ip]];
+            const double vol = pitVolA[pit];
+            const bool self = (pitDrain[pit] == pit);
+            double dp = depo[pit];
+            bool ovf = false;
+            for (int e0 = 0; e0 < nev && !ovf; e0 += 32) {
+                const int e = e0 + lane;
+                unsigned m = __ballot_sync(0xffffffffu, e < nev && ev_pit[e] == pit);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const double pitDep = ev_dep[e0 + b];
+                    const double totdist = 0. + pitDep, tmpdist = 0. + dp;
+                    if (tmpdist + totdist <= vol || self) dp = dp + pitDep;
+                    else { ovf = true; break; }
+                }
+            }
+            if (ovf) over = 1;
+            if (lane == 0) S.P.f[F_VAL][pit] = dp;
         }
-        S.P.f[F_VAL][pit] = dp;
     }
     over = __syncthreads_or(over);
     STICK(13);
