@@ -33,8 +33,10 @@ struct SubTick { long long *p, t; };
 __device__ inline long long sub_clock() { return clock64(); }
 __device__ inline SubTick sub_tick_begin(const DevConst &c) { SubTick s; s.p = c.phase_cyc + (size_t)blockIdx.x * NPHASE; s.t = sub_clock(); return s; }
 // (__syncwarp: lane 0 must be back with its warp before the caller's next warp-synchronous instruction)
-__device__ inline void sub_tick(SubTick &s, int i) { if (threadIdx.x == 0) { const long long t1 = sub_clock(); s.p[i] += t1 - s.t; s.t = t1; } __syncwarp(); }
-__device__ inline void sub_count(SubTick &s, int i, int n) { if (threadIdx.x == 0) s.p[i] += n; __syncwarp(); }
+// (counters are bumped with a result-less atomic: a plain += would put a global load on thread 0's path at every tick)
+__device__ inline void tick_add(long long *p, long long v) { atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v); }
+__device__ inline void sub_tick(SubTick &s, int i) { if (threadIdx.x == 0) { const long long t1 = sub_clock(); tick_add(s.p + i, t1 - s.t); s.t = t1; } __syncwarp(); }
+__device__ inline void sub_count(SubTick &s, int i, int n) { if (threadIdx.x == 0) tick_add(s.p + i, n); __syncwarp(); }
 
 __device__ inline int blk_exscan(int v, int &total, Smem &S)
 {
@@ -1340,7 +1342,7 @@ __device__ void phase_apply(const DevConst &c, Smem &S, double sea, double times
 // one time step = buildFlux.streamflow (buildFlux.py:21-100) + sediment_flux (:102-320).  Proposal scalars (tNow, step,
 // rain, erodibility, seed, tStop) are read from / written to S (see Smem).
 #define BL_TICK(i) do { if (threadIdx.x == 0) { long long *pc_ = S.c.phase_cyc + (size_t)blockIdx.x * NPHASE; \
-                                               const long long t1_ = clock64(); pc_[i] += t1_ - S.tick0; S.tick0 = t1_; } } while (0)
+                                               const long long t1_ = clock64(); tick_add(pc_ + (i), t1_ - S.tick0); S.tick0 = t1_; } } while (0)
 __device__ void time_step(const DevConst &c, Smem &S)
 {
     const int tid = threadIdx.x;

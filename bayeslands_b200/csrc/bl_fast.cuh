@@ -564,11 +564,16 @@ __device__ __noinline__ void drainage(const DevConst &c, Smem &S, unsigned char 
     const double *W = S.P.f[F_FILLH], *pitVol = S.P.f[F_PITVOL];
     int *succ = S.P.i[I_SUCC], *succ2 = S.P.i[I_SUCC2], *drain = S.P.i[I_PITDRAIN], *alld = S.P.i[I_ALLDRAIN];
     int *mark = S.P.i[I_MARK];
-    for (int v = tid; v < N; v += TPB) {
-        r16[v] = (unsigned short)rcv[v];
-        const int p = pitID[v];
-        pid16[v] = (p < 0) ? NONE16 : (unsigned short)p;
-        drain[v] = -1; alld[v] = -1; mark[v] = 0;
+    {
+        const int *__restrict__ rcvA = rcv, *__restrict__ pitA = pitID;
+        int *__restrict__ drainA = drain, *__restrict__ alldA = alld, *__restrict__ markA = mark;
+#pragma unroll 4
+        for (int v = tid; v < N; v += TPB) {
+            r16[v] = (unsigned short)rcvA[v];
+            const int p = pitA[v];
+            pid16[v] = (p < 0) ? NONE16 : (unsigned short)p;
+            drainA[v] = -1; alldA[v] = -1; markA[v] = 0;
+        }
     }
     __syncthreads();
     for (int i = tid; i < nbase1; i += TPB) {
@@ -754,7 +759,7 @@ __device__ __noinline__ void streampower(const DevConst &c, Smem &S, unsigned ch
     double *depo = S.P.f[F_DEPO], *ero = S.P.f[F_ERO], *pdep = S.P.f[F_PDEP], *pitVol = S.P.f[F_PITVOLW];
     long long *pcs = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
     long long ts0 = clock64();
-#define STICK(i) do { if (tid == 0) { long long t1_ = clock64(); pcs[i] += t1_ - ts0; ts0 = t1_; } } while (0)
+#define STICK(i) do { if (tid == 0) { long long t1_ = clock64(); tick_add(pcs + (i), t1_ - ts0); ts0 = t1_; } } while (0)
     // (1) per-node pre-pass
 #pragma unroll 2
     for (int d = tid; d < N; d += TPB) {

@@ -128,13 +128,13 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
     const bool diag = (c.dbg & 4) && tid == 0;          // diagnostics: cycles of warp 0 per round (scan / evaluation / barrier)
     long long *pcd = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
     long long tq = diag ? clock64() : 0;
-#define FDIAG(i) do { if (diag) { const long long t_ = clock64(); pcd[i] += t_ - tq; tq = t_; } } while (0)
+#define FDIAG(i) do { if (diag) { const long long t_ = clock64(); tick_add(pcd + (i), t_ - tq); tq = t_; } } while (0)
     int change = 1;
     while (change) {
         int loc = 0;
         for (int l = 0; l < nlev; ++l) {
             const int n0 = nb + S.lev_off[l], n1 = nb + S.lev_off[l + 1];     // node id range of the level
-            if (diag) pcd[32] += 1;
+            if (diag) tick_add(pcd + 32, 1);
             if (warp < NWF && n1 > n0) {
                 const int whi = (n1 - 1) >> 5;
                 // a batch = BW bitmap words of this warp (word w0 + NWF * t belongs to lane t): BW * 32 candidate ids
@@ -170,7 +170,7 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
                     }
                     __syncwarp();
                     FDIAG(34);
-                    if (diag) pcd[33] += off;
+                    if (diag) tick_add(pcd + 33, off);
                     for (int i = lane; i < off; i += 32) {
                         const int s = (int)lds_u8(aL + (unsigned)i);
                         fill_eval_c<KDT, false>(ngb16f, zg, (w0 + NWF * (s >> 5)) * 32 + (s & 31), aW, aB, sea, eps, TH, loc);
@@ -881,7 +881,7 @@ __device__ __noinline__ void streampower_c(const DevConst &c, Smem &S, unsigned 
     double *depo = S.P.f[F_DEPO], *pdep = S.P.f[F_PDEP], *pitVol = S.P.f[F_PITVOLW];
     long long *pcs = c.phase_cyc + (size_t)blockIdx.x * NPHASE;
     long long ts0 = clock64();
-#define STICK(i) do { if (tid == 0) { long long t1_ = clock64(); pcs[i] += t1_ - ts0; ts0 = t1_; } } while (0)
+#define STICK(i) do { if (tid == 0) { long long t1_ = clock64(); tick_add(pcs + (i), t1_ - ts0); ts0 = t1_; } } while (0)
     if (c.m == 0.5 && c.n == 1.0) sp_prepass_c<true>(c, S, dsm, erod, sea, dt);
     else sp_prepass_c<false>(c, S, dsm, erod, sea, dt);
     STICK(27);
