@@ -1133,6 +1133,8 @@ __device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea
     int *land = S.P.i[I_LB], *memb = S.P.i[I_MEMB];
     int marine = 0, left = 0;
     SubTick st = sub_tick_begin(c);
+    if (tid == 0) S.ibuf[6] = 0;             // number of land pits found by the first pass
+    __syncthreads();
     // every load of a node is issued before the first branch on it, so the unrolled iterations keep one batch of
     // independent loads in flight (a load under a data-dependent branch costs a memory round trip per branch)
     if (c.depo != 0) {
@@ -1158,6 +1160,8 @@ __device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea
             dep[k] = d;
             dth[k] = th;
             kindA[k] = island;
+            if (island == 1) land[atomicAdd(&S.ibuf[6], 1)] = k;     // a handful per step; their order does not matter:
+                                                                     // every land pit scales its own members only
             left |= (d != 0. && island != 1);          // land pits hand their load on below: what else is left over?
         }
     } else {
@@ -1177,8 +1181,7 @@ __device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea
     }
     int any = 0;
     if (c.depo != 0) {
-        const int *isl = S.P.i[I_KIND];
-        const int nland = blk_compact(N, land, [&](int i) { return isl[i] == 1; }, S);
+        const int nland = S.ibuf[6];         // (the barrier of the reduction above orders the appends)
         // land pits (flowNetwork.py:750-763): members = where(pitID == p) in ascending id; the basin's nodes
         // are a contiguous segment of the real-surface stack.  Small basins: one thread gathers + sorts its
         // members; large basins: the block compacts them in id order.
@@ -1222,7 +1225,10 @@ __device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea
             if (hi - lo <= SMALL) continue;
             sub_count(st, 20, 1);
             // members in ascending id: mark them (they all lie in the basin's stack segment), compact the bitmap
-            unsigned *bm = (unsigned *)S.P.i[I_MARK];
+            // (shared memory is idle in this phase: the bitmap sits behind the first 8 bytes per node, the terms of the
+            // pairwise sum in front; without dynamic shared memory both stay in global scratch)
+            unsigned *bm = S.dsm ? (unsigned *)(S.dsm + (size_t)8 * c.Nq) : (unsigned *)S.P.i[I_MARK];
+            double *tv = S.dsm ? (double *)S.dsm : tmpv;
             for (int w = tid; w < (N + 31) / 32; w += TPB) bm[w] = 0u;
             __syncthreads();
             for (int i = lo + tid; i < hi; i += TPB) {
@@ -1235,10 +1241,10 @@ __device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea
                 const int v = memb[i];
                 const double dd = (W[v] - z[v]) * 1.0;
                 dth[v] = dd;
-                tmpv[i] = dd * c.area[v];
+                tv[i] = dd * c.area[v];
             }
             __syncthreads();
-            const double tmpd = blk_pairwise_sum(tmpv, nm, S, S.P.i[I_EVENTS], S.P.i[I_SUCC], S.P.f[F_CAPH]);
+            const double tmpd = blk_pairwise_sum(tv, nm, S, S.P.i[I_EVENTS], S.P.i[I_SUCC], S.P.f[F_CAPH]);
             if (tid == 0) S.dbuf[0] = (0. + dep[pit]) / tmpd;
             __syncthreads();
             const double dfrac = S.dbuf[0];
