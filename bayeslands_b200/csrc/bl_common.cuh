@@ -38,6 +38,7 @@ struct DevConst {
     int dbg;                    // BL_DEBUG experiments (timing only)
     int compact;                // 8-bytes-per-node shared-memory layout (bl_fastc.cuh): two landscapes per SM
     const unsigned *nbf2;       // [N] bit p = neighbour slot p is an inside node (borders2): the diffusion's neighbour test
+    const unsigned *pend0;      // [Nq / 32] bit k = interior node k has a ghost neighbour: the fill's initial pending set
     const double *vor, *edge;   // [KD][N]
     const double *area, *xy;    // [N], [N][2]
     const unsigned char *flags; // bit0 borders, bit1 borders2, bit2 indomain

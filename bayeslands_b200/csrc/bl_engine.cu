@@ -49,7 +49,7 @@ extern "C" int bl_version(void) { return 100; }
 
 namespace {
 struct Layout {
-    size_t off_nbf2, off_ve32, off_ngb16, off_ngb16f, off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
+    size_t off_pend0, off_nbf2, off_ve32, off_ngb16, off_ngb16f, off_ngb, off_vor, off_edge, off_area, off_xy, off_flags, off_parent, off_z0, off_disp, off_levn,
         off_levo, off_gidx, off_gw, off_gex, off_real, off_pts, off_seat, off_seav, off_rain, off_erod, off_seed,
         off_tnow, off_lastdt, off_steps, off_status, off_phase, off_stops, off_ckpt, off_prop, total;
     int KD, nlev;
@@ -108,6 +108,7 @@ Layout make_layout(const bl_mesh *m, const bl_params *p, int B, int KD, int nlev
     L.off_xy = take(N * 16);
     L.off_flags = take(N);
     L.off_nbf2 = take(N * 4);
+    L.off_pend0 = take(rup(N + 1, 64) / 8 + 64);
     L.off_parent = take((size_t)std::max(1, m->bounds) * 4);
     L.off_z0 = take(N * 8);
     L.off_disp = take(N * 8);
@@ -292,6 +293,15 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
             if (j < 0) break;
             if (m->borders2[j]) nbf2[i] |= 1u << q;
         }
+    // the fill starts from W = 1e6 on every interior node: evaluating a node is a no-op until one of its neighbours has
+    // dropped, so only the interior nodes next to a ghost node (W = z from the start) are pending initially
+    std::vector<unsigned> pend0((size_t)rup((size_t)N + 1, 64) / 32 + 16, 0u);
+    for (int i = m->bounds; i < N; ++i)
+        for (int q = 0; q < KD; ++q) {
+            int j = m->ngb[(size_t)i * BL_KP + q];
+            if (j < 0) break;
+            if (j < m->bounds) { pend0[i >> 5] |= 1u << (i & 31); break; }
+        }
     std::vector<int> levn, levo(nlev + 1, 0);
     {
         std::vector<int> cntl(nlev + 1, 0);
@@ -312,6 +322,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     UP(L.off_xy, m->xy, (size_t)N * 16);
     UP(L.off_flags, flags.data(), (size_t)N);
     UP(L.off_nbf2, nbf2.data(), (size_t)N * 4);
+    UP(L.off_pend0, pend0.data(), (size_t)rup((size_t)N + 1, 64) / 8);
     if (m->bounds > 0) UP(L.off_parent, m->parent, (size_t)m->bounds * 4);
     UP(L.off_z0, m->z0, (size_t)N * 8);
     if (m->disp) UP(L.off_disp, m->disp, (size_t)N * 8);
@@ -345,6 +356,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     c.xy = (const double *)(ws + L.off_xy);
     c.flags = (const unsigned char *)(ws + L.off_flags);
     c.nbf2 = (const unsigned *)(ws + L.off_nbf2);
+    c.pend0 = (const unsigned *)(ws + L.off_pend0);
     c.compact = compact;
     c.parent = (const int *)(ws + L.off_parent);
     c.z0 = (const double *)(ws + L.off_z0);

@@ -188,7 +188,9 @@ __device__ __noinline__ void fill_bitmap(const DevConst &c, Smem &S, unsigned ch
         unsigned char *pend = (unsigned char *)(zs + Nq);                      // [Nq] pending flags (8-byte aligned)
         const double *z = S.P.f[F_Z];
         for (int i = tid; i < N; i += TPB) { const double zi = z[i]; zs[i] = zi; W[i] = (i < nb) ? zi : 1.e6; }
-        for (int i = tid; i < Nq; i += TPB) pend[i] = (i >= nb && i < N) ? 1 : 0;   // every interior node starts pending
+        // initially pending: the interior nodes next to a ghost node (see fastc::fill_c; opt_debug bit 128: all of them)
+        for (int i = tid; i < Nq; i += TPB)
+            pend[i] = (i >= nb && i < N && ((c.dbg & 128) || ((c.pend0[i >> 5] >> (i & 31)) & 1u))) ? 1 : 0;
         if (tid == 0) W[N] = 2.e6;                                              // the dummy neighbour of empty slots
     }
     __syncthreads();

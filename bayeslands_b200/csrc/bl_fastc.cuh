@@ -83,6 +83,18 @@ __device__ __forceinline__ void fill_eval_c(const unsigned short *__restrict__ n
     }
 }
 
+// bits of the interior nodes [nb, N) within the bitmap word that starts at node lo
+__device__ __forceinline__ unsigned interior_mask(int lo, int nb, int N)
+{
+    unsigned m = 0u;
+    if (lo + 32 > nb && lo < N) {
+        m = 0xffffffffu;
+        if (lo < nb) m &= 0xffffffffu << (nb - lo);
+        if (lo + 32 > N) m &= 0xffffffffu >> (lo + 32 - N);
+    }
+    return m;
+}
+
 template <int KDT>
 __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *dsm, double sea)
 {
@@ -107,16 +119,10 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
 #pragma unroll 4
         for (int i = tid; i < N; i += TPB) W[i] = (i < nb) ? zg[i] : 1.e6;
         if (tid == 0) W[N] = 2.e6;                          // the dummy neighbour of empty slots
-        for (int w = tid; w < Nq / 32; w += TPB) {          // every interior node starts pending
-            const int lo = w * 32;
-            unsigned m = 0u;
-            if (lo + 32 > nb && lo < N) {
-                m = 0xffffffffu;
-                if (lo < nb) m &= 0xffffffffu << (nb - lo);
-                if (lo + 32 > N) m &= 0xffffffffu >> (lo + 32 - N);
-            }
-            bits[w] = m;
-        }
+        // initially pending: the interior nodes next to a ghost node (DevConst::pend0).  Everything else still has all
+        // its neighbours at 1e6, where an evaluation changes nothing and raises no flag; it is woken like any other
+        // node when a neighbour drops, so the sweeps see the same effective evaluations as the literal loop.
+        for (int w = tid; w < Nq / 32; w += TPB) bits[w] = ((c.dbg & 128) ? 0xffffffffu : c.pend0[w]) & interior_mask(w * 32, nb, N);
     }
     __syncthreads();
     const unsigned aW = s32(dsm), aB = aW + 8u * (unsigned)Nq;
