@@ -26,6 +26,8 @@ struct Smem {
     unsigned long long seed;
     int nbase1, nbase, any_marine;
     double *diff_out;          // per-stage entry point bl_diffuse: raw diffusion flux of sfd.diffusion (null in a run)
+    unsigned long long mbar;   // mbarrier of the TMA bulk copies global -> shared memory (bl_fastc.cuh: tma_to_smem)
+    unsigned tma_phase;        // its phase parity
 };
 
 // diagnostics: thread 0 adds the cycles since the previous tick to slot i of this CTA's phase_cyc row (slots >= 16)
@@ -1446,6 +1448,9 @@ bl_run_kernel(const DevConst cpar, int nstops, const double *__restrict__ stops,
         S.dsm = (KDT > 0) ? dsm : nullptr;
         S.dsm_bytes = (KDT > 0) ? dyn_bytes : 0;
         S.diff_out = nullptr;
+        S.tma_phase = 0u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&S.mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const DevConst &c = S.c;

@@ -33,6 +33,34 @@ __device__ __forceinline__ void red_or_if(bool p, unsigned a, unsigned v)
 }
 __device__ __forceinline__ void red_and(unsigned a, unsigned v) { asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+// ---- TMA bulk copy global -> shared memory (cp.async.bulk, completion on an mbarrier) -------------------------------
+// Whole arrays that a phase needs in shared memory unchanged (the elevations for the receiver search, the tour successors
+// for the list ranking) are fetched by the copy engine: one thread posts the transfers, nobody spends registers or issue
+// slots on a load / store loop, and the block waits on the mbarrier's transaction count.  Called by every thread of the
+// CTA from uniform code, AFTER a __syncthreads() that retired the previous users of the destination bytes; `bytes` is a
+// multiple of 16, both addresses are 16-byte aligned.
+__device__ __forceinline__ void tma_to_smem(Smem &S, void *dst_smem, const void *src_gmem, unsigned bytes)
+{
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&S.mbar);
+    const unsigned parity = S.tma_phase;
+    if (threadIdx.x == 0) {
+        // generic-proxy accesses of the destination (ordered by the caller's barrier) before the async-proxy writes
+        asm volatile("fence.proxy.async;" ::: "memory");    // (all state spaces: the source was written by this CTA too)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(dst_smem);
+        const char *src = (const char *)src_gmem;
+        for (unsigned off = 0; off < bytes; off += 32768u) {
+            const unsigned n = min(32768u, bytes - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + off), "l"(src + off), "r"(n), "r"(mbar) : "memory");
+        }
+    }
+    asm volatile("{\n\t.reg .pred p;\n\tTMA_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra TMA_DONE;\n\tbra TMA_WAIT;\n\tTMA_DONE:\n\t}"
+                 ::"r"(mbar), "r"(parity) : "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) S.tma_phase = parity ^ 1u;     // read again only after further barriers
+}
+
 // dynamic shared memory of the compact layout: 8 bytes per node, one bit per node, the fill's per-warp slot lists
 __device__ __forceinline__ unsigned char *tail_of(unsigned char *dsm, int Nq) { return dsm + (size_t)8 * Nq + Nq / 8; }
 
@@ -234,9 +262,11 @@ __device__ __noinline__ void receivers_c(const DevConst &c, Smem &S, unsigned ch
         mar |= (wg < sea);
     }
     __syncthreads();
-#pragma unroll 4
-    for (int i = tid; i < N; i += TPB) A[i] = zg[i];
-    __syncthreads();
+    {   // z replaces W in the same bytes: one bulk copy (the odd last element, if any, by hand)
+        const unsigned bytes = ((unsigned)N * 8u) & ~15u;
+        if (tid == 0 && (N & 1)) A[N - 1] = zg[N - 1];
+        tma_to_smem(S, A, zg, bytes);
+    }
 #pragma unroll 2
     for (int g = tid; g < N; g += TPB) {
         Ids<KDT> ids;
@@ -344,13 +374,13 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     __syncthreads();
     unsigned short *nx16 = (unsigned short *)dsm;                    // [2N] successor of every tour element
     const int M = 2 * N;
-    {
+    {   // 2N u16 successors = 4N bytes, bulk copy (the tail of less than 16 bytes by hand)
+        const unsigned bytes = ((unsigned)N * 4u) & ~15u;
         const unsigned *src = reinterpret_cast<const unsigned *>(nxg);
         unsigned *dst = reinterpret_cast<unsigned *>(nx16);
-#pragma unroll 4
-        for (int e = tid; e < N; e += TPB) dst[e] = src[e];
+        if (tid < 4) { const int e = (int)(bytes / 4u) + tid; if (e < N) dst[e] = src[e]; }
+        tma_to_smem(S, nx16, nxg, bytes);
     }
-    __syncthreads();
     sub_tick(stl, 29);      // base levels, shuffle, tour back into shared memory
     unsigned long long *T = (unsigned long long *)(dsm + (size_t)4 * Nq);   // [<= Nq / 2] splitter table
     const int sh = 3 + ((c.dbg >> 5) & 3);
@@ -667,10 +697,12 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
             q0g[q] = a * ((v >= nbn) ? rain : 0.);
         }
         __syncthreads();
-#pragma unroll 4
-        for (int q = tid; q < N; q += TPB) vals[q] = q0g[q];
+        {   // initial values by position into shared memory: bulk copy (the odd last element, if any, by hand)
+            const unsigned bytes = ((unsigned)N * 8u) & ~15u;
+            if (tid == 0 && (N & 1)) vals[N - 1] = q0g[N - 1];
+            tma_to_smem(S, vals, q0g, bytes);
+        }
     }
-    __syncthreads();
     sub_tick(stc, 24);      // records + initial values
     {
         const unsigned *__restrict__ recA = B.rec;
