@@ -236,6 +236,8 @@ __device__ __noinline__ void receivers_c(const DevConst &c, Smem &S, unsigned ch
     // by-products for the CFL and stream-power passes (same expressions as there, evaluated once per step while the
     // surfaces are in shared memory): W(d) - W(rcv), the distance to the receiver, z(rcv)
     double *__restrict__ dzw = S.P.f[F_CAPH], *__restrict__ distr = S.P.f[F_E], *__restrict__ zrA = S.P.f[F_QS];
+    // 16-bit copies of both receiver arrays: links_stack_c brings them into shared memory with one bulk copy each
+    unsigned short *__restrict__ rcv16w = (unsigned short *)S.P.i[I_ROOT1], *__restrict__ rcv116w = rcv16w + np_of(N);
     const double2 *__restrict__ xy2 = reinterpret_cast<const double2 *>(c.xy);
     int mar = 0;
 #pragma unroll 2
@@ -255,6 +257,7 @@ __device__ __noinline__ void receivers_c(const DevConst &c, Smem &S, unsigned ch
         }
         const double2 xr = xy2[low];
         rcv[g] = low;
+        rcv16w[g] = (unsigned short)low;
         fillH[g] = wg;
         dzw[g] = wg - wl;
         const double dx = xg.x - xr.x, dy = xg.y - xr.y;
@@ -285,6 +288,7 @@ __device__ __noinline__ void receivers_c(const DevConst &c, Smem &S, unsigned ch
             if (dh >= 0. && dh < dH) dH = dh;
         }
         rcv1[g] = low1;
+        rcv116w[g] = (unsigned short)low1;
         if (dH > 9.99e5) dH = 0.;
         maxh[g] = dH;
         zrA[g] = A[r];
@@ -316,9 +320,13 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     const int kcap = (int)(((size_t)6 * Nq - 128) / 8);
     unsigned short *nxg = (unsigned short *)S.P.euA;                              // [2N] successors, global scratch
     SubTick stl = sub_tick_begin(c);
-#pragma unroll 4
-    for (int v = tid; v < N; v += TPB) r16[v] = (unsigned short)rcvg[v];
-    __syncthreads();
+    {   // receivers as u16 (written by receivers_c next to the int arrays): one bulk copy, the last < 8 entries by hand
+        const unsigned short *r16g = (const unsigned short *)S.P.i[I_ROOT1] + (filled ? 0 : np_of(N));
+        const unsigned bytes = ((unsigned)N * 2u) & ~15u;
+        if (tid < 8) { const int v = (int)(bytes / 2u) + tid; if (v < N) r16[v] = r16g[v]; }
+        tma_to_smem(S, r16, r16g, bytes);
+    }
+    (void)rcvg;
     unsigned char *cnt8 = (unsigned char *)S.P.i[I_CNT];
 #pragma unroll 2
     for (int v = tid; v < N; v += TPB) {
@@ -429,6 +437,7 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     }
     sub_tick(stl, 30);      // first walk + splitter ranking
     unsigned short *depg = (unsigned short *)S.P.i[I_FC];            // depth by stack position (filled surface: discharge_c)
+    int mdep = 0;
     {
         int sp = tid;
         unsigned e = 0u, re = 0u, ra = 0u;
@@ -444,7 +453,7 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
                 const int v = (int)(e >> 1), p = N - (int)re;
                 pos[v] = p;
                 stack[p] = v;
-                if (filled) depg[p] = (unsigned short)(2 * p - (M - (int)ra));
+                if (filled) { const int dep = 2 * p - (M - (int)ra); depg[p] = (unsigned short)dep; mdep = max(mdep, dep); }
                 --re;
             }
             --ra;
@@ -458,6 +467,10 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
                 }
             } else e = nx;
         }
+    }
+    if (filled) {           // depth of the receiver forest, left in S.ibuf[2] for discharge_c
+        mdep = __reduce_max_sync(0xffffffffu, mdep);
+        if ((tid & 31) == 0) atomicMax(&S.ibuf[2], mdep);
     }
     __syncthreads();
     sub_tick(stl, 31);      // second walk
@@ -610,10 +623,11 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
             act = __syncthreads_or(loc);
         }
         for (int p = tid; p < N; p += TPB) { const int d = (int)(jd[stack[p]] & 0xFFFFu); dpos[p] = (unsigned short)d; md = max(md, d); }
-    } else {                     // links_stack_c left the depth of every stack position behind
-        const unsigned short *__restrict__ depg = (const unsigned short *)S.P.i[I_FC];
-#pragma unroll 4
-        for (int p = tid; p < N; p += TPB) { const int d = depg[p]; dpos[p] = (unsigned short)d; md = max(md, d); }
+    } else {                     // links_stack_c left the depth of every stack position behind, and their maximum in S.ibuf[2]
+        const unsigned short *depg = (const unsigned short *)S.P.i[I_FC];
+        const unsigned bytes = ((unsigned)N * 2u) & ~15u;
+        if (tid < 8) { const int p = (int)(bytes / 2u) + tid; if (p < N) dpos[p] = depg[p]; }
+        tma_to_smem(S, dpos, depg, bytes);
     }
     md = __reduce_max_sync(0xffffffffu, md);
     if (lane == 0) atomicMax(&S.ibuf[2], md);
