@@ -556,8 +556,9 @@ __device__ inline int pit_walk16(const unsigned short *r16, const unsigned short
     }
 }
 
-__device__ __noinline__ void drainage(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1, double sea,
-                                      int any_marine)
+// `staged`: r16 / pid16 are in shared memory already (compact layout: bulk copies), only the outputs are reset here
+__device__ __forceinline__ void drainage_body(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1, double sea,
+                                              int any_marine, bool staged)
 {
     BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
@@ -569,12 +570,17 @@ __device__ __noinline__ void drainage(const DevConst &c, Smem &S, unsigned char 
     {
         const int *__restrict__ rcvA = rcv, *__restrict__ pitA = pitID;
         int *__restrict__ drainA = drain, *__restrict__ alldA = alld, *__restrict__ markA = mark;
+        if (staged) {
 #pragma unroll 4
-        for (int v = tid; v < N; v += TPB) {
-            r16[v] = (unsigned short)rcvA[v];
-            const int p = pitA[v];
-            pid16[v] = (p < 0) ? NONE16 : (unsigned short)p;
-            drainA[v] = -1; alldA[v] = -1; markA[v] = 0;
+            for (int v = tid; v < N; v += TPB) { drainA[v] = -1; alldA[v] = -1; markA[v] = 0; }
+        } else {
+#pragma unroll 4
+            for (int v = tid; v < N; v += TPB) {
+                r16[v] = (unsigned short)rcvA[v];
+                const int p = pitA[v];
+                pid16[v] = (p < 0) ? NONE16 : (unsigned short)p;
+                drainA[v] = -1; alldA[v] = -1; markA[v] = 0;
+            }
         }
     }
     __syncthreads();
@@ -623,6 +629,12 @@ __device__ __noinline__ void drainage(const DevConst &c, Smem &S, unsigned char 
     }
     __syncthreads();
     phase_drainage(c, S, base1, nbase1, sea);   // generic path handles the cyclic case literally
+}
+
+__device__ __noinline__ void drainage(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1, double sea,
+                                      int any_marine)
+{
+    drainage_body(c, S, dsm, base1, nbase1, sea, any_marine, false);
 }
 
 // ---- shared-memory layout of the discharge / stream-power scans -------------------------------------------

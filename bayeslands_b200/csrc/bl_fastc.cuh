@@ -58,7 +58,8 @@ __device__ __forceinline__ void tma_to_smem(Smem &S, void *dst_smem, const void 
     asm volatile("{\n\t.reg .pred p;\n\tTMA_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra TMA_DONE;\n\tbra TMA_WAIT;\n\tTMA_DONE:\n\t}"
                  ::"r"(mbar), "r"(parity) : "memory");
     __syncthreads();
-    if (threadIdx.x == 0) S.tma_phase = parity ^ 1u;     // read again only after further barriers
+    if (threadIdx.x == 0) S.tma_phase = parity ^ 1u;
+    __syncthreads();                                     // the next call (possibly the very next statement) reads the new parity
 }
 
 // dynamic shared memory of the compact layout: 8 bytes per node, one bit per node, the fill's per-warp slot lists
@@ -493,6 +494,7 @@ __device__ __noinline__ void basins_c(const DevConst &c, Smem &S, unsigned char 
     const int *__restrict__ rcv1 = S.P.i[I_RCV1], *__restrict__ pos1 = S.P.i[I_POS1], *__restrict__ ns1 = S.P.i[I_NS];
     int *__restrict__ pitID = S.P.i[I_PITID];
     double *__restrict__ pitVol = S.P.f[F_PITVOL];
+    unsigned short *__restrict__ pid16w = (unsigned short *)S.P.i[I_FC] + np_of(N);
     // The root of a node is the base level whose stack segment holds it (the real-surface stack lists tree after tree in
     // base order): every base marks the position where its segment starts, the marks are propagated to the right
     // (thread-local pass over a contiguous chunk, block scan of the chunks' last marks, second pass), and a node looks
@@ -529,7 +531,9 @@ __device__ __noinline__ void basins_c(const DevConst &c, Smem &S, unsigned char 
     for (int v = tid; v < N; v += TPB) {
         const bool wet = W[v] > z[v];
         const int root = rootpos[pos1[v]];
-        pitID[v] = (wet || root == v) ? root : -1;
+        const bool in = wet || root == v;
+        pitID[v] = in ? root : -1;
+        pid16w[v] = in ? (unsigned short)root : NONE16;      // 16-bit copy: drainage_c stages it with a bulk copy
         pitVol[v] = -1.0;
     }
     __syncthreads();
@@ -576,6 +580,22 @@ __device__ __noinline__ void basins_c(const DevConst &c, Smem &S, unsigned char 
         if (lane == 0) pitVol[root] = s;
     }
     __syncthreads();
+}
+
+// ---- pit drainage (FLOWalgo.f90:167-297): fast::drainage with its two shared-memory tables staged by bulk copies ----------
+__device__ __noinline__ void drainage_c(const DevConst &c, Smem &S, unsigned char *dsm, const int *base1, int nbase1, double sea,
+                                        int any_marine)
+{
+    BL_ASSUME_SHARED(c, S, dsm);
+    const int N = c.N, Nq = c.Nq, tid = threadIdx.x;
+    unsigned short *r16 = (unsigned short *)dsm, *pid16 = r16 + Nq;
+    const unsigned short *r16g = (const unsigned short *)S.P.i[I_ROOT1];                 // filled-surface receivers (receivers_c)
+    const unsigned short *pid16g = (const unsigned short *)S.P.i[I_FC] + np_of(N);       // pit ids (basins_c)
+    const unsigned bytes = ((unsigned)N * 2u) & ~15u;
+    if (tid < 8) { const int v = (int)(bytes / 2u) + tid; if (v < N) { r16[v] = r16g[v]; pid16[v] = pid16g[v]; } }
+    tma_to_smem(S, r16, r16g, bytes);
+    tma_to_smem(S, pid16, pid16g, bytes);
+    drainage_body(c, S, dsm, base1, nbase1, sea, any_marine, true);
 }
 
 // ---- discharge (FLOWalgo.f90:53-81) on the breadth-first layout ---------------------------------------------------------
@@ -1206,7 +1226,7 @@ __device__ void time_step(const DevConst &c, Smem &S, unsigned char *dsm)
                            mix64(S.seed + (unsigned long long)S.step));
     }
     BL_TICK(4);
-    drainage(c, S, dsm, S.P.i[I_LA], S.nbase1, S.sea, S.any_marine);
+    drainage_c(c, S, dsm, S.P.i[I_LA], S.nbase1, S.sea, S.any_marine);
     BL_TICK(5);
     discharge_c(c, S, dsm, S.rain);
     BL_TICK(6);
