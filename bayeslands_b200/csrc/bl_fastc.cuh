@@ -401,13 +401,23 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     // Both walks are ONE loop per lane over all its sublists (a lane that finishes a sublist starts its next one in the
     // same iteration), so the lanes of a warp stay busy until their whole share is done instead of idling at the end of
     // every sublist behind the longest one of the 32.
+    // The first walk also leaves, for every enter event, (its sublist : 12 | enter events before it in the sublist : 10 |
+    // elements before it : 10) in global scratch, so that the ranks can be finished by a dense pass over the nodes
+    // instead of a second divergent walk; a sublist of 1024 elements or more (never seen: the splitters are 8 apart in
+    // index space) raises S.ibuf[7] and the second walk below takes over.
+    unsigned *infog = (unsigned *)S.P.euB;                           // [N]
+    if (tid == 0) S.ibuf[7] = 0;
+    __syncthreads();
     {
         int sp = tid;
         unsigned e = 0u, ce = 0u, ca = 0u;
         bool run = sp < S_tot;
+        bool ovf = false;
         if (run) e = (sp < S_reg) ? ((unsigned)sp << sh) : head;
         while (run) {
             const unsigned nx = nx16[e];
+            if (!(e & 1u)) infog[e >> 1] = ((unsigned)sp << 20) | (ce << 10) | ca;
+            ovf |= (ca >= 1023u);
             ce += (~e) & 1u;
             ++ca;
             const bool last = (nx == END16), split = !last && ((nx & smask) == 0u || nx == head);
@@ -420,6 +430,7 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
                 e = (sp < S_reg) ? ((unsigned)sp << sh) : head;
             } else e = nx;
         }
+        if (ovf) S.ibuf[7] = 1;
     }
     __syncthreads();
     int active = 1;
@@ -439,7 +450,20 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     sub_tick(stl, 30);      // first walk + splitter ranking
     unsigned short *depg = (unsigned short *)S.P.i[I_FC];            // depth by stack position (filled surface: discharge_c)
     int mdep = 0;
-    {
+    if (!S.ibuf[7] && S_tot <= 4096 && !(c.dbg & 256)) {
+        // dense finish: rank of enter(v) = (enter events from its sublist's splitter to the end) - (those before it)
+#pragma unroll 4
+        for (int v = tid; v < N; v += TPB) {
+            const unsigned info = infog[v];
+            const unsigned long long a = T[info >> 20];
+            const int re = (int)((a >> 16) & 0xFFFFull) - (int)((info >> 10) & 0x3FFu);
+            const int ra = (int)(a >> 32) - (int)(info & 0x3FFu);
+            const int p = N - re;
+            pos[v] = p;
+            stack[p] = v;
+            if (filled) { const int dep = 2 * p - (M - ra); depg[p] = (unsigned short)dep; mdep = max(mdep, dep); }
+        }
+    } else {
         int sp = tid;
         unsigned e = 0u, re = 0u, ra = 0u;
         bool run = sp < S_tot;

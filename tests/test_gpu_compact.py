@@ -60,7 +60,7 @@ def test_compact_stepwise_all_stages_bit_exact(crater_fast, shuffle):
             assert sc["status"][b] == 0
 
 
-@pytest.mark.parametrize("tpb,debug", [(256, 0), (384, 0), (768, 0), (1024, 0), (512, 8), (512, 16), (512, 32)])
+@pytest.mark.parametrize("tpb,debug", [(256, 0), (384, 0), (768, 0), (1024, 0), (512, 8), (512, 16), (512, 32), (512, 256)])
 def test_compact_every_cta_size_and_deep_tree_fallback(crater_fast, tpb, debug):
     """`compact=True` forces the layout at any CTA size; debug bit 8 lowers the depth limit of its breadth-first tables to
     12 levels, so that every step takes the generic discharge / stream-power fallback."""
