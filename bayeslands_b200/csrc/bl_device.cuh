@@ -888,8 +888,10 @@ __device__ __noinline__ void phase_marine_distribution(const DevConst &c, Smem &
     __syncthreads();
     const double diff_res = 1.e-2;
     const int max_it_cyc = 500000;
-    // The walk is sequential, but each step scans one node's neighbours twice: warp 0 runs it with one lane
-    // per neighbour slot (max / first-lowest by shuffles); all lanes carry the same scalars, lane 0 writes.
+    // The walk is sequential, but each step scans one node's neighbours twice: warp 0 runs it with one lane per neighbour
+    // slot.  The two scans - highest neighbour, first lowest neighbour - are warp reductions (redux.sync) on order-preserving
+    // 64-bit keys of the elevations, high word first; all lanes carry the same scalars, so every branch is uniform; lane 0
+    // writes, once per iteration, between two warp barriers (readers of the old values before, readers of the new after).
     const int lane = tid & 31;
     const int KDv = nb16 ? KDT : c.KD;
     auto nbr = [&](int id, int q) -> int {
@@ -897,7 +899,15 @@ __device__ __noinline__ void phase_marine_distribution(const DevConst &c, Smem &
         if (nb16) { const int j = nb16[id * KDT + q]; return (j == 0xFFFF) ? -1 : j; }
         return c.ngb[(size_t)q * N + id];
     };
-    auto wr = [&](double *p, double v) { __syncwarp(); if (lane == 0) *p = v; __syncwarp(); };
+    auto key_of = [](double x) -> unsigned long long {      // x < y  <=>  key(x) < key(y)   (-0 counts as +0)
+        unsigned long long u = (unsigned long long)__double_as_longlong(x);
+        if (u == 0x8000000000000000ull) u = 0ull;
+        return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    };
+    auto val_of = [](unsigned long long k) -> double {
+        const unsigned long long u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+        return __longlong_as_double((long long)u);
+    };
     for (int mm = 0; mm < c.diffnb; ++mm) {
         for (int k = tid; k < N; k += TPB) seadep[k] = ((isl[k] == 2) ? dep[k] : 0.) / (double)(float)c.diffnb;
         __syncthreads();
@@ -906,54 +916,73 @@ __device__ __noinline__ void phase_marine_distribution(const DevConst &c, Smem &
                 int id = seaid[k];
                 int it = 0;
                 for (;;) {
-                    if (!(flagA[id] & 1)) { wr(&seadep[id], 0.); break; }
+                    // ---- reads of this iteration (every lane) ----
+                    const bool inside = (flagA[id] & 1);
                     const double area = areaA[id];
                     const double eid = elev[id], sd = seadep[id];
-                    int j = nbr(id, lane);
-                    double ej = (j >= 0) ? elev[j] : -1.e8;
-                    double maxz = ej;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) maxz = fmax(maxz, __shfl_xor_sync(0xffffffffu, maxz, o));
-                    maxz = fmax(maxz, -1.e8);
-                    const double maxnb = maxz;
+                    const int j = nbr(id, lane);
+                    const double ej = (j >= 0) ? elev[j] : -1.e8;
+                    // highest neighbour (floor -1e8, as the reference's initial value)
+                    const unsigned long long kj = key_of(ej);
+                    const unsigned khi = (unsigned)(kj >> 32), klo = (unsigned)kj;
+                    const unsigned mh = __reduce_max_sync(0xffffffffu, khi);
+                    const unsigned ml = __reduce_max_sync(0xffffffffu, (khi == mh) ? klo : 0u);
+                    const double maxnb = val_of(((unsigned long long)mh << 32) | ml);
+                    // first lowest neighbour (PDalgo.f90:197-209: strictly lower than the running minimum, first slot wins ties)
+                    const unsigned nh = __reduce_min_sync(0xffffffffu, (j >= 0) ? khi : 0xffffffffu);
+                    const unsigned nl = __reduce_min_sync(0xffffffffu, (j >= 0 && khi == nh) ? klo : 0xffffffffu);
+                    const unsigned best = __ballot_sync(0xffffffffu, j >= 0 && khi == nh && klo == nl);
+                    const int bq = best ? (__ffs(best) - 1) : 0;
+                    const int bj = __shfl_sync(0xffffffffu, j, bq);
+                    const double bv = best ? val_of(((unsigned long long)nh << 32) | nl) : 1.e300;
+                    double maxz = maxnb;
                     if (maxz > sea) maxz = sea;
                     if (maxz < eid) maxz = eid;
                     const double vol = fmax(0., c.diffprop * (maxz - eid) * area);
-                    if (it > max_it_cyc) { wr(&elev[id], eid + sd / area); wr(&seadep[id], 0.); break; }
-                    if (sd / area < diff_res) { wr(&elev[id], eid + sd / area); wr(&seadep[id], 0.); break; }
-                    it = it + 1;
-                    if (sd < vol) { wr(&elev[id], eid + sd / area); wr(&seadep[id], 0.); break; }
-                    const double sd2 = sd - vol, e2 = eid + vol / area;
-                    wr(&seadep[id], sd2); wr(&elev[id], e2);
-                    if (sd2 > 0.) {
-                        // lowest neighbour strictly below the node, first slot wins ties (PDalgo.f90:197-209)
-                        double bv = (j >= 0) ? ej : 1.e300;
-                        int bq = (j >= 0) ? lane : 64, bj = j;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                            const int oq = __shfl_xor_sync(0xffffffffu, bq, o), oj = __shfl_xor_sync(0xffffffffu, bj, o);
-                            if (ov < bv || (ov == bv && oq < bq)) { bv = ov; bq = oq; bj = oj; }
+                    // ---- decide (uniform) and collect the writes: up to three (address, value) pairs ----
+                    double *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+                    double v0 = 0., v1 = 0., v2 = 0.;
+                    bool done = false;
+                    int nextid = id;
+                    if (!inside) { p0 = &seadep[id]; v0 = 0.; done = true; }
+                    else if (it > max_it_cyc || sd / area < diff_res) { p0 = &elev[id]; v0 = eid + sd / area; p1 = &seadep[id]; v1 = 0.; done = true; }
+                    else {
+                        it = it + 1;
+                        if (sd < vol) { p0 = &elev[id]; v0 = eid + sd / area; p1 = &seadep[id]; v1 = 0.; done = true; }
+                        else {
+                            const double sd2 = sd - vol, e2 = eid + vol / area;
+                            if (sd2 > 0.) {
+                                int nid = (best && bv < e2) ? bj : -1;
+                                if (nid == -1) {
+                                    const double dh = maxnb - e2 + 0.1;
+                                    if (sd2 > dh * area) {
+                                        const double e3 = e2 + dh, sd3 = sd2 - dh * area;
+                                        p0 = &elev[id]; v0 = e3;
+                                        nid = seaid[k];
+                                        it = 0;
+                                        if (nid == id) { p1 = &seadep[nid]; v1 = sd3; }
+                                        else { const double t = seadep[nid]; p1 = &seadep[nid]; v1 = t + sd3; p2 = &seadep[id]; v2 = 0.; }
+                                        nextid = nid;
+                                    } else { p0 = &elev[id]; v0 = e2 + sd2 / area; p1 = &seadep[id]; v1 = 0.; done = true; }
+                                } else {
+                                    const double t = seadep[nid];
+                                    p0 = &elev[id]; v0 = e2;
+                                    p1 = &seadep[nid]; v1 = t + sd2;
+                                    p2 = &seadep[id]; v2 = 0.;
+                                    nextid = nid;
+                                }
+                            } else { p0 = &elev[id]; v0 = e2; p1 = &seadep[id]; v1 = 0.; done = true; }
                         }
-                        int nid = (bq < 64 && bv < e2) ? bj : -1;
-                        if (nid == -1) {
-                            const double dh = maxnb - e2 + 0.1;
-                            if (sd2 > dh * area) {
-                                const double e3 = e2 + dh, sd3 = sd2 - dh * area;
-                                wr(&elev[id], e3);
-                                nid = seaid[k];
-                                it = 0;
-                                if (nid == id) wr(&seadep[nid], sd3);
-                                else { const double t = seadep[nid]; wr(&seadep[nid], t + sd3); wr(&seadep[id], 0.); }
-                                id = seaid[k];
-                            } else { wr(&elev[id], e2 + sd2 / area); wr(&seadep[id], 0.); break; }
-                        } else {
-                            const double t = seadep[nid];
-                            wr(&seadep[nid], t + sd2);
-                            wr(&seadep[id], 0.);
-                            id = nid;
-                        }
-                    } else { wr(&seadep[id], 0.); break; }
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p0) *p0 = v0;
+                        if (p1) *p1 = v1;
+                        if (p2) *p2 = v2;
+                    }
+                    __syncwarp();
+                    if (done) break;
+                    id = nextid;
                 }
             }
         }
