@@ -81,7 +81,11 @@ size_t fast_smem_need(int Nq, int KDT, bool marine)
 }
 
 // the compact layout (bl_fastc.cuh): 8 bytes per node, one bit per node, the fill's slot lists (256 bytes per sweeping warp)
-size_t compact_smem_need(int Nq, int tpb) { return (size_t)8 * Nq + Nq / 8 + (size_t)(tpb / 64) * 256 + 64; }
+size_t compact_smem_need(int Nq, int tpb)
+{
+    const int nwf = (tpb <= 512) ? tpb / 32 : tpb / 64;      // sweeping warps of the fill (bl_fastc.cuh: fill_c), 256-byte slot lists
+    return (size_t)8 * Nq + Nq / 8 + (size_t)nwf * 256 + 64;
+}
 
 cudaError_t func_attr(int tpb, int KDT, cudaFuncAttributes *fa)
 {
@@ -230,8 +234,8 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
     const bool small_ids = (N < 32760 && nlev <= LEVMAX);
     const size_t need_full = fast_smem_need(Nq, kdt_want, false), need_c512 = compact_smem_need(Nq, 512);
     auto fits = [&](int t, size_t need, int nres) {        // nres CTAs of t threads resident on one SM with `need` bytes each
-        return (size_t)nres * (static_smem[t] + rup(need, 1024) + smem_res) <= (size_t)smem_sm &&
-               static_smem[t] + rup(need, 1024) <= (size_t)optin;
+        return (size_t)nres * (static_smem[t] + rup(need, 128) + smem_res) <= (size_t)smem_sm &&
+               static_smem[t] + rup(need, 128) <= (size_t)optin;
     };
     const bool compact_ok = small_ids && lev_contig_h && !marine_cfg && !(p->opt_flags & BL_OPT_NO_COMPACT);
     // CTA size and layout: small meshes 256 threads (several CTAs per SM); else two 512-thread CTAs per SM when two
@@ -393,7 +397,7 @@ extern "C" int bl_ctx_create(const bl_mesh *m, const bl_params *p, int B, int de
         const bool marine = (p->CDr > 0. || p->nsea > 0);
         size_t need = compact ? compact_smem_need(Nq, tpb) : fast_smem_need(Nq, KDT, false);
         if (marine) need = std::max(need, std::min(fast_smem_need(Nq, KDT, true), (size_t)dyn_max));
-        ctx->dyn = KDT ? (int)std::min((size_t)dyn_max, rup(need, 1024)) : 0;
+        ctx->dyn = KDT ? (int)std::min((size_t)dyn_max, rup(need, compact ? 128 : 1024)) : 0;
         if (KDT && (p->opt_debug & 1)) ctx->dyn = dyn_max;     // experiment: one CTA per SM whatever the mesh size
     }
     CUDA_OK(cudaMallocHost((void **)&ctx->h_stage, (size_t)bl_ctx::NSLOT * STOPS_CAP * 12));

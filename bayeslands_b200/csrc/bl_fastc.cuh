@@ -136,11 +136,12 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
 #ifndef BL_FILLC_PF
 #define BL_FILLC_PF 1
 #endif
-    // sweeping warps and bitmap words per batch: with BL_FILLC_ALL every warp of a (<= 512-thread) CTA sweeps, 4 words at
-    // a time, so a thin front is spread over twice as many warps; the slot lists take NWF * BW * 32 bytes either way
+    // sweeping warps: with BL_FILLC_ALL every warp of a (<= 512-thread) CTA sweeps, so a thin front is spread over twice as
+    // many warps; a batch is 8 bitmap words per warp (one batch covers a level of up to NWF * 256 nodes); the slot lists take
+    // NWF * 256 bytes (compact_smem_need in bl_engine.cu)
     constexpr bool ALLW = BL_FILLC_ALL && (NWARP <= 16);
     constexpr int NWF = ALLW ? NWARP : ((NWARP >= 2) ? NWARP / 2 : 1);
-    constexpr int BW = ALLW ? 4 : 8;
+    constexpr int BW = 8;
     const double *__restrict__ zg = S.P.f[F_Z];
     {
         double *W = (double *)dsm;
