@@ -197,12 +197,15 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
 #endif
                         }
                     }
+                    if (__ballot_sync(0xffffffffu, mine != 0u) == 0u) continue;     // nothing pending in this warp's words
                     int off = 0;
 #pragma unroll
                     for (int t = 0; t < BW; ++t) {
                         const unsigned wb = __shfl_sync(0xffffffffu, mine, t);
-                        sts_u8_if((wb >> lane) & 1u, aL + (unsigned)(off + __popc(wb & lt)), (unsigned)(t * 32 + lane));
-                        off += __popc(wb);
+                        if (wb) {
+                            sts_u8_if((wb >> lane) & 1u, aL + (unsigned)(off + __popc(wb & lt)), (unsigned)(t * 32 + lane));
+                            off += __popc(wb);
+                        }
                     }
                     __syncwarp();
                     FDIAG(34);
