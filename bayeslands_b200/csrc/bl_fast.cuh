@@ -10,6 +10,13 @@
 // Neighbour ids come from a u16 slot-major table (coalesced).  Requires N < 32768 and 17*Nq <= 225 KB.
 
 
+// the diffusion pass of the compact layout (bl_fastc.cuh) needs 8 bytes of shared memory per node only and is the faster
+// one wherever there is no river-borne marine diffusion: fast::time_step uses it too
+namespace fastc {
+template <int KDT>
+__device__ __noinline__ void apply_c(const DevConst &c, Smem &S, unsigned char *dsm, double sea, double timestep);
+}
+
 namespace fast {
 
 // The phases are separate (__noinline__) functions so that each gets its own register allocation under the kernel's
@@ -917,21 +924,33 @@ __device__ __noinline__ void streampower(const DevConst &c, Smem &S, unsigned ch
     int over = 0;
     if (S.ibuf[1])      // some node lies under the sea: an event whose pit is submerged needs the serial path
         for (int e = tid; e < nev; e += TPB) { const int pit = ev_pit[e]; if (pit != NONE16 && W[pit] < sea) over = 1; }
-    for (int i = tid; i < nbase1; i += TPB) {
-        const int pit = base1[i];
-        if (!has_ev[pit]) continue;              // no event: depo[pit] stays as it is
-        double dp = depo[pit];
-        bool any = false;
-        double vol = 0.;
-        for (int e = 0; e < nev; ++e) {
-            if (ev_pit[e] != pit) continue;
-            if (!any) { vol = pitVol1[pit]; any = true; }
-            const double pitDep = ev_dep[e];
-            const double totdist = 0. + pitDep, tmpdist = 0. + dp;
-            if (tmpdist + totdist <= vol || pitDrain[pit] == pit) dp = dp + pitDep;
-            else { over = 1; break; }
+    // one WARP per pit that receives events: the lanes scan the event list 32 entries at a time and the matching events
+    // are applied in order (same sums as the serial loop: events of other pits do not touch this pit's deposit)
+    int *plist = S.P.i[I_MEMB];
+    const int npl = blk_compact(nbase1, plist, [&](int i) { return has_ev[base1[i]] != 0; }, S);
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int ip = warp; ip < npl; ip += NWARP) {
+            const int pit = base1[plist[ip]];
+            const double vol = pitVol1[pit];
+            const bool self = (pitDrain[pit] == pit);
+            double dp = depo[pit];
+            bool ovf = false;
+            for (int e0 = 0; e0 < nev && !ovf; e0 += 32) {
+                const int e = e0 + lane;
+                unsigned m = __ballot_sync(0xffffffffu, e < nev && ev_pit[e] == pit);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const double pitDep = ev_dep[e0 + b];
+                    const double totdist = 0. + pitDep, tmpdist = 0. + dp;
+                    if (tmpdist + totdist <= vol || self) dp = dp + pitDep;
+                    else { ovf = true; break; }
+                }
+            }
+            if (ovf) over = 1;
+            if (lane == 0) S.P.f[F_VAL][pit] = dp;   // staged, committed below when no event overflowed
         }
-        S.P.f[F_VAL][pit] = dp;   // staged, committed below when no event overflowed
     }
     over = __syncthreads_or(over);
     STICK(13);  // parallel replay
@@ -1232,7 +1251,8 @@ __device__ void time_step(const DevConst &c, Smem &S, unsigned char *dsm)
     BL_TICK(9);
     phase_erodep(c, S, S.sea);
     BL_TICK(10);
-    apply<KDT>(c, S, dsm, S.sea, S.newdt);
+    if (c.CDr > 0.) apply<KDT>(c, S, dsm, S.sea, S.newdt);
+    else fastc::apply_c<KDT>(c, S, dsm, S.sea, S.newdt);
     BL_TICK(11);
     if (tid == 0) { S.tNow += S.newdt; S.last_dt = S.newdt; S.step += 1; }
     __syncthreads();
