@@ -795,9 +795,9 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
     }
     sub_tick(stc, 25);      // level loop
     double *__restrict__ Q = S.P.f[F_Q];
-    const unsigned short *__restrict__ ordr = B.order;
+    const unsigned short *__restrict__ posr = B.posb;       // by node id: coalesced loads and stores, the gather is in shared memory
 #pragma unroll 4
-    for (int q = tid; q < N; q += TPB) Q[ordr[q]] = vals[q];
+    for (int v = tid; v < N; v += TPB) Q[v] = vals[posr[v]];
     __syncthreads();
     sub_tick(stc, 26);      // Q by node id
 }
