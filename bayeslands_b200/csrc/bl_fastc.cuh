@@ -333,6 +333,9 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     }
     (void)rcvg;
     unsigned char *cnt8 = (unsigned char *)S.P.i[I_CNT];
+    unsigned *rootbits = (unsigned *)(dsm + (size_t)8 * Nq);     // one bit per node: base levels (self-receivers)
+    for (int w = tid; w < Nq / 32; w += TPB) rootbits[w] = 0u;
+    __syncthreads();
 #pragma unroll 2
     for (int v = tid; v < N; v += TPB) {
         Ids<KDT> ids, jds;
@@ -357,12 +360,15 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
         }
         const unsigned en = (unsigned)((f != NONE16) ? 2 * f : 2 * v + 1);
         if (r != v) reinterpret_cast<unsigned *>(nxg)[v] = en | ((unsigned)((nx != NONE16) ? 2 * nx : 2 * r + 1) << 16);
-        else nxg[2 * v] = (unsigned short)en;               // a root's exit is linked to the next root below
+        else {                                              // a root's exit is linked to the next root below
+            nxg[2 * v] = (unsigned short)en;
+            atomicOr(&rootbits[v >> 5], 1u << (v & 31));
+        }
         if (filled) cnt8[v] = (unsigned char)n;              // donor counts: the breadth-first layout of discharge_c
     }
     __syncthreads();
     sub_tick(stl, 28);      // receivers to shared memory + link construction
-    nbase = blk_compact(N, baselist, [&](int i) { return r16[i] == i; }, S);
+    nbase = blk_compact_bits(rootbits, N, baselist, S);       // base levels in ascending id
     if (tid == 0) { if (filled) S.nbase = nbase; else S.nbase1 = nbase; }
     if (shuffle && nbase > 1) {
         int n2 = 1;
@@ -643,7 +649,7 @@ __device__ __forceinline__ Bfs bfs_arrays(Smem &S, int N)
 }
 
 // S.ibuf[5] = 1 when the receiver tree is too deep for the shared-memory tables: generic phases take over for this step
-__device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned char *dsm, double rain)
+__device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned char *dsm, double rain, double erod)
 {
     BL_ASSUME_SHARED(c, S, dsm);
     const int N = c.N, Nq = c.Nq, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -794,33 +800,28 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
         }
     }
     sub_tick(stc, 25);      // level loop
+    // Q by node id (coalesced loads and stores, the gather is in shared memory) and, in the same pass, the flow CFL
+    // condition (FLOWalgo.f90:299-330, same arithmetic as fast::flow_cfl; a base level has dz = 0 and is skipped like
+    // d == r; STD exponents m = 0.5, n = 1 take sqrt and the identity): its minimum is left in S.dbuf[3]
     double *__restrict__ Q = S.P.f[F_Q];
-    const unsigned short *__restrict__ posr = B.posb;       // by node id: coalesced loads and stores, the gather is in shared memory
-#pragma unroll 4
-    for (int v = tid; v < N; v += TPB) Q[v] = vals[posr[v]];
-    __syncthreads();
-    sub_tick(stc, 26);      // Q by node id
-}
-
-// FLOWalgo.f90:299-330 on the filled surface, same arithmetic as fast::flow_cfl; everything comes from global memory
-// STD = the exponents every BASELINE config uses (m = 0.5, n = 1): sqrt and the identity, no call to pow in the loop
-template <bool STD>
-__device__ __noinline__ double flow_cfl_c(const DevConst &c, Smem &S, double erod)
-{
-    __builtin_assume(__isShared(&c)); __builtin_assume(__isShared(&S));
-    const int N = c.N;
-    const double *__restrict__ Q = S.P.f[F_Q], *__restrict__ dzw = S.P.f[F_CAPH], *__restrict__ distr = S.P.f[F_E];
+    const unsigned short *__restrict__ posr = B.posb;
+    const double *__restrict__ dzw = S.P.f[F_CAPH], *__restrict__ distr = S.P.f[F_E];
+    const bool stdexp = (c.m == 0.5 && c.n == 1.0);
     const double em = c.m, en1 = c.n - 1.;
     double cfl = 1.e6;
 #pragma unroll 4
-    for (int d = threadIdx.x; d < N; d += TPB) {
-        const double q = Q[d], dz = dzw[d], dist = distr[d];      // a base level has dz = 0: skipped like d == r
+    for (int v = tid; v < N; v += TPB) {
+        const double q = vals[posr[v]], dz = dzw[v], dist = distr[v];
+        Q[v] = q;
         if (q > 0. && dz > 0.) {
-            const double tmp = STD ? dist / (erod * sqrt(q) * 1.0) : dist / (erod * powx(q, em) * powx(dz / dist, en1));
+            const double tmp = stdexp ? dist / (erod * sqrt(q) * 1.0) : dist / (erod * powx(q, em) * powx(dz / dist, en1));
             cfl = fmin(tmp, cfl);
         }
     }
-    return blk_min(cfl, S);
+    cfl = blk_min(cfl, S);
+    if (tid == 0) S.dbuf[3] = cfl;
+    __syncthreads();
+    sub_tick(stc, 26);      // Q by node id + CFL
 }
 
 // ---- stream power (FLOWalgo.f90:583-1044), see fast::streampower ---------------------------------------------------------
@@ -1256,12 +1257,11 @@ __device__ void time_step(const DevConst &c, Smem &S, unsigned char *dsm)
     BL_TICK(4);
     drainage_c(c, S, dsm, S.P.i[I_LA], S.nbase1, S.sea, S.any_marine);
     BL_TICK(5);
-    discharge_c(c, S, dsm, S.rain);
+    discharge_c(c, S, dsm, S.rain, S.erod);
     BL_TICK(6);
     const bool deep = S.ibuf[5] != 0;          // uniform: written before the barriers that end discharge_c
     {
-        const bool stdexp = (c.m == 0.5 && c.n == 1.0);
-        const double flowcfl = deep ? phase_cfl(c, S, S.erod) : (stdexp ? flow_cfl_c<true>(c, S, S.erod) : flow_cfl_c<false>(c, S, S.erod));
+        const double flowcfl = deep ? phase_cfl(c, S, S.erod) : S.dbuf[3];       // discharge_c computed it with its last pass
         double cfl = fmin(flowcfl, c.hill);
         cfl = py2_floorish(cfl);
         cfl = fmin(cfl, S.tStop - S.tNow);
