@@ -633,18 +633,21 @@ __device__ __noinline__ void drainage_c(const DevConst &c, Smem &S, unsigned cha
 }
 
 // ---- discharge (FLOWalgo.f90:53-81) on the breadth-first layout ---------------------------------------------------------
-// rec[q]   = first-child position : 16 | donor count : 8 | deposition rule : 8 (written by the stream-power pre-pass)
-// order[q] = node at position q, posb[v] = position of node v.  Global scratch (I_LC, I_PS), S.boff = bucket offsets.
+// One 16-byte record per breadth-first position q (global scratch, read as one 128-bit load, one level ahead):
+//   x = first-child position : 16 | donor count : 8 | deposition rule : 8 (the rule is written by the stream-power pre-pass)
+//   y = node at position q
+//   z, w = fp64 payload: the node's own discharge (area * rain) for discharge_c; the pre-pass overwrites it with the
+//          control volume where the routing needs it (rule 3)
+// posb[v] = position of node v (u16, I_PS).  S.boff = bucket offsets.
 struct Bfs {
-    unsigned *rec;
-    unsigned short *order, *posb;
+    uint4 *rec;
+    unsigned short *posb;
 };
 __device__ __forceinline__ Bfs bfs_arrays(Smem &S, int N)
 {
     Bfs b;
-    b.rec = (unsigned *)S.P.i[I_LC];
-    b.order = (unsigned short *)S.P.i[I_PS];
-    b.posb = b.order + np_of(N);
+    b.rec = reinterpret_cast<uint4 *>(S.P.euA);          // [Np] 16 bytes each; the tour successors lived here during links_stack_c
+    b.posb = reinterpret_cast<unsigned short *>(S.P.i[I_PS]) + np_of(N);
     return b;
 }
 
@@ -748,9 +751,8 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
     {
         const int *__restrict__ posA = S.P.i[I_POS];
         const double *__restrict__ areaA = c.area;
-        unsigned *__restrict__ recw = B.rec;
-        unsigned short *__restrict__ ordw = B.order, *__restrict__ posw = B.posb;
-        double *__restrict__ q0g = S.P.f[F_VAL];
+        uint4 *__restrict__ recw = B.rec;
+        unsigned short *__restrict__ posw = B.posb;
         const int nbn = c.bounds;
 #pragma unroll 4
         for (int v = tid; v < N; v += TPB) {
@@ -759,23 +761,18 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
             const double a = areaA[v];
             const unsigned q = qpos[p];
             const unsigned f = (p + 1 < N) ? qpos[p + 1] : 0u;
-            recw[q] = f | (n << 16);
-            ordw[q] = (unsigned short)v;
+            const double q0 = a * ((v >= nbn) ? rain : 0.);
+            recw[q] = make_uint4(f | (n << 16), (unsigned)v, (unsigned)__double2loint(q0), (unsigned)__double2hiint(q0));
             posw[v] = (unsigned short)q;
-            q0g[q] = a * ((v >= nbn) ? rain : 0.);
-        }
-        __syncthreads();
-        {   // initial values by position into shared memory: bulk copy (the odd last element, if any, by hand)
-            const unsigned bytes = ((unsigned)N * 8u) & ~15u;
-            if (tid == 0 && (N & 1)) vals[N - 1] = q0g[N - 1];
-            tma_to_smem(S, vals, q0g, bytes);
         }
     }
+    __syncthreads();
     sub_tick(stc, 24);      // records + initial values
     {
-        const unsigned *__restrict__ recA = B.rec;
+        const uint4 *__restrict__ recA = B.rec;
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
         int b0 = S.boff[maxd], b1 = S.boff[maxd + 1];
-        unsigned rcur = (b0 + tid < b1) ? recA[b0 + tid] : 0u;
+        uint4 rcur = (b0 + tid < b1) ? recA[b0 + tid] : zero4;
         for (int d = maxd; d >= 0; --d) {
             const int nb0 = (d > 0) ? S.boff[d - 1] : 0, nb1 = (d > 0) ? S.boff[d] : 0;
             const int niter = (b1 - b0 + TPB - 1) / TPB;          // uniform
@@ -784,14 +781,12 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
                 // the record of this thread's next position (same bucket or the next one) is requested first
                 const int nq = (it + 1 < niter) ? q + TPB : nb0 + tid;
                 const int nlim = (it + 1 < niter) ? b1 : nb1;
-                const unsigned rn = (nq < nlim) ? recA[nq] : 0u;
+                const uint4 rn = (nq < nlim) ? recA[nq] : zero4;
                 if (q < b1) {
-                    const int n = (int)((rcur >> 16) & 0xFFu), f = (int)(rcur & 0xFFFFu);
-                    if (n) {
-                        double acc = vals[q];
-                        for (int j = f + n - 1; j >= f; --j) acc = acc + vals[j];       // donors in descending id
-                        vals[q] = acc;
-                    }
+                    const int n = (int)((rcur.x >> 16) & 0xFFu), f = (int)(rcur.x & 0xFFFFu);
+                    double acc = __hiloint2double((int)rcur.w, (int)rcur.z);           // area * rain of the node itself
+                    for (int j = f + n - 1; j >= f; --j) acc = acc + vals[j];       // donors in descending id
+                    vals[q] = acc;
                 }
                 rcur = rn;
             }
@@ -843,7 +838,8 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
 #define FD(k, i) F[(unsigned)(k) * Np + (unsigned)(i)]
 #define ID(k, i) I[(unsigned)(k) * Np + (unsigned)(i)]
     const unsigned short *posbA = reinterpret_cast<const unsigned short *>(I + (size_t)I_PS * Np) + Np;
-    kindg = reinterpret_cast<unsigned char *>(I + (size_t)I_LC * Np);
+    kindg = reinterpret_cast<unsigned char *>(S.P.euA);            // byte 3 of the 16-byte record of a position
+    double *areaq = reinterpret_cast<double *>(S.P.euA);           // its second half
     const double *__restrict__ areaA = c.area;
     // every load of a node is issued before the first branch on it (a load behind a data-dependent branch costs its own
     // memory round trip: the profile of the first version showed ten separate long-scoreboard waits per node)
@@ -892,9 +888,9 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
             else if (d == r) k = 2;
             else k = 4;
         } else k = 5;
-        kindg[4 * qd + 3] = (unsigned char)k;
+        kindg[16 * qd + 3] = (unsigned char)k;
         vals[qd] = e;
-        if (k == 3) FD(F_SEDIN, qd) = area;          // the routing divides by it (rule 3 only)
+        if (k == 3) areaq[2 * qd + 1] = area;         // the routing divides by it (rule 3 only)
         FD(F_DEPO, d) = 0.;
         FD(F_ERO, d) = 0.;
     }
@@ -913,18 +909,15 @@ __device__ __noinline__ void sp_route_c(const DevConst &c, Smem &S, unsigned cha
     double *vals = (double *)dsm;
     unsigned *evbits = (unsigned *)(dsm + (size_t)8 * Nq);
     double *depo = S.P.f[F_DEPO], *ero = S.P.f[F_ERO], *pdep = S.P.f[F_PDEP];
-    const double *__restrict__ areaq = S.P.f[F_SEDIN];       // control volume by position (pre-pass; rule 3 only)
-    const unsigned *__restrict__ recA = B.rec;
-    const unsigned short *__restrict__ ordA = B.order;
+    const uint4 *__restrict__ recA = B.rec;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     const int *posg = S.P.i[I_POS];
     const int maxd = S.ibuf[3];
     // A thread's items are the positions q = b0 + tid, + TPB, ... of every bucket, deepest bucket first.  The record, the
     // node id and the control volume of the NEXT item (same bucket or the next one) are requested before the current
     // item is evaluated, so no global load sits on the dependent chain of a level.
     int b0 = S.boff[maxd], b1 = S.boff[maxd + 1];
-    unsigned rcur = 0u, ccur = 0u;
-    double acur = 0.;
-    if (b0 + tid < b1) { rcur = recA[b0 + tid]; ccur = ordA[b0 + tid]; acur = areaq[b0 + tid]; }
+    uint4 rcur = (b0 + tid < b1) ? recA[b0 + tid] : zero4;
     for (int d = maxd; d >= 0; --d) {
         const int nb0 = (d > 0) ? S.boff[d - 1] : 0, nb1 = (d > 0) ? S.boff[d] : 0;
         const int niter = (b1 - b0 + TPB - 1) / TPB;          // uniform
@@ -932,12 +925,10 @@ __device__ __noinline__ void sp_route_c(const DevConst &c, Smem &S, unsigned cha
             const int q = b0 + tid + it * TPB;
             const int nq = (it + 1 < niter) ? q + TPB : nb0 + tid;
             const int nlim = (it + 1 < niter) ? b1 : nb1;
-            unsigned rn = 0u, cn = 0u;
-            double an = 0.;
-            if (nq < nlim) { rn = recA[nq]; cn = ordA[nq]; an = areaq[nq]; }
+            const uint4 rn = (nq < nlim) ? recA[nq] : zero4;
             if (q < b1) {
-                const unsigned r = rcur;
-                const int cur = (int)ccur;
+                const unsigned r = rcur.x;
+                const int cur = (int)rcur.y;
                 const int n = (int)((r >> 16) & 0xFFu), f = (int)(r & 0xFFFFu), k = (int)(r >> 24);
                 double acc = 0. * dt;
                 for (int j = f + n - 1; j >= f; --j) acc = acc + vals[j];
@@ -952,7 +943,7 @@ __device__ __noinline__ void sp_route_c(const DevConst &c, Smem &S, unsigned cha
                 }
                 else if (k == 2) { erodep = acc; }
                 else if (k == 3) {
-                    const double area = acur;
+                    const double area = __hiloint2double((int)rcur.w, (int)rcur.z);
                     const double totflx = 0. + acc, maxh = own;
                     if (totflx / area < maxh) erodep = acc;
                     else { const double frac = acc / totflx; erodep = frac * maxh * area; Qs = acc - erodep; }
@@ -963,7 +954,7 @@ __device__ __noinline__ void sp_route_c(const DevConst &c, Smem &S, unsigned cha
                 }
                 vals[q] = Qs;
             }
-            rcur = rn; ccur = cn; acur = an;
+            rcur = rn;
         }
         __syncthreads();
         b0 = nb0; b1 = nb1;
