@@ -1219,6 +1219,55 @@ __device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea
         constexpr int SMALL = 96;
         sub_tick(st, 16);
         sub_count(st, 21, nland);
+        if (S.dsm) {
+            // one WARP per small land pit, on scratch in the (idle) shared memory: the stack segment is read 32 positions at
+            // a time (two dependent global loads per position, now in parallel), the members are ordered by rank counting,
+            // lane 0 evaluates numpy's pairwise sum on the shared-memory terms.  Same members, same order, same arithmetic.
+            const int lane = tid & 31, warp = tid >> 5;
+            int *ids = reinterpret_cast<int *>(S.dsm + (size_t)warp * 1536), *srt = ids + SMALL;
+            double *tvs = reinterpret_cast<double *>(S.dsm + (size_t)warp * 1536 + 768);
+            const unsigned ltm = (1u << lane) - 1u;
+            for (int q = warp; q < nland; q += NWARP) {
+                const int pit = land[q];
+                const int lo = pos1[pit];
+                const int nr = ns1[pit];
+                const int hi = (nr != NONE_I) ? pos1[nr] : N;
+                if (hi - lo > SMALL) continue;
+                int nm = 0;
+                for (int i0 = lo; i0 < hi; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int v = (i < hi) ? stack1[i] : -1;
+                    const bool isM = (v >= 0) && (pitID[v] == pit);
+                    const unsigned mk = __ballot_sync(0xffffffffu, isM);
+                    if (isM) ids[nm + __popc(mk & ltm)] = v;
+                    nm += __popc(mk);
+                }
+                __syncwarp();
+                for (int e = lane; e < nm; e += 32) {
+                    const int v = ids[e];
+                    int r = 0;
+                    for (int j = 0; j < nm; ++j) r += (ids[j] < v);
+                    srt[r] = v;
+                }
+                __syncwarp();
+                for (int e = lane; e < nm; e += 32) {
+                    const int v = srt[e];
+                    const double dd = (W[v] - z[v]) * 1.0;
+                    tvs[e] = dd * c.area[v];
+                }
+                __syncwarp();
+                double tmpd = 0.;
+                if (lane == 0) tmpd = pairwise_sum(tvs, nm);
+                tmpd = __shfl_sync(0xffffffffu, tmpd, 0);
+                const double dfrac = (0. + dep[pit]) / tmpd;
+                for (int e = lane; e < nm; e += 32) {
+                    const int v = srt[e];
+                    const double dd = (W[v] - z[v]) * 1.0;
+                    dth[v] = dd * dfrac;
+                }
+                __syncwarp();
+            }
+        } else
         for (int q = tid; q < nland; q += TPB) {
             const int pit = land[q];
             const int lo = pos1[pit];
