@@ -816,8 +816,49 @@ __device__ inline double pw_leaf(const double *a, int m)
     }
     return res;
 }
-__device__ double blk_pairwise_sum(const double *a, int n, Smem &S, int *loff, int *llen, double *lsum)
+// `stk`: 160 ints + 40 doubles of scratch for thread 0's recursion stacks (shared memory when the caller has some: as
+// local arrays they are dynamically indexed, i.e. live in local memory, and the two serial walks of thread 0 dominate
+// the routine); nullptr = local arrays.
+__device__ double blk_pairwise_sum(const double *a, int n, Smem &S, int *loff, int *llen, double *lsum, int *stk = nullptr)
 {
+    if (stk) {
+        int *ostk = stk, *nstk = stk + 40, *sstk = stk + 80;
+        double *vstk = reinterpret_cast<double *>(stk + 120);
+        if (threadIdx.x == 0) {
+            int sp = 0, nl = 0;
+            ostk[0] = 0; nstk[0] = n; sp = 1;
+            while (sp > 0) {                       // leaves left to right
+                const int o = ostk[sp - 1], m = nstk[sp - 1];
+                --sp;
+                if (m <= 128) { loff[nl] = o; llen[nl] = m; ++nl; }
+                else {
+                    int n2 = m / 2;
+                    n2 -= n2 % 8;
+                    ostk[sp] = o + n2; nstk[sp] = m - n2; ++sp;
+                    ostk[sp] = o; nstk[sp] = n2; ++sp;
+                }
+            }
+            S.ibuf[4] = nl;
+        }
+        __syncthreads();
+        const int nl = S.ibuf[4];
+        for (int t = threadIdx.x; t < nl; t += TPB) lsum[t] = pw_leaf(a + loff[t], llen[t]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int sp = 0, vp = 0, li = 0;
+            nstk[0] = n; sstk[0] = 0; sp = 1;
+            while (sp > 0) {
+                const int m = nstk[sp - 1], st = sstk[sp - 1];
+                if (m <= 128) { vstk[vp++] = lsum[li++]; --sp; }
+                else if (st == 0) { int n2 = m / 2; n2 -= n2 % 8; sstk[sp - 1] = 1; nstk[sp] = n2; sstk[sp] = 0; ++sp; }
+                else if (st == 1) { int n2 = m / 2; n2 -= n2 % 8; sstk[sp - 1] = 2; nstk[sp] = m - n2; sstk[sp] = 0; ++sp; }
+                else { const double b = vstk[--vp], a0 = vstk[--vp]; vstk[vp++] = a0 + b; --sp; }
+            }
+            S.dbuf[1] = vstk[0];
+        }
+        __syncthreads();
+        return S.dbuf[1];
+    }
     if (threadIdx.x == 0) {
         int ostk[40], nstk[40], sp = 0, nl = 0;
         ostk[0] = 0; nstk[0] = n; sp = 1;
@@ -1324,7 +1365,11 @@ __device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea
                 tv[i] = dd * c.area[v];
             }
             __syncthreads();
-            const double tmpd = blk_pairwise_sum(tv, nm, S, S.P.i[I_EVENTS], S.P.i[I_SUCC], S.P.f[F_CAPH]);
+            double tmpd;
+            if (S.dsm && nm <= 11000 && (size_t)8 * c.Nq + c.Nq / 8 + 4160 <= (size_t)S.dsm_bytes) {   // <= 200 leaves: offsets, lengths, sums, thread 0's stacks behind the bitmap
+                int *sc = reinterpret_cast<int *>(S.dsm + (size_t)8 * c.Nq + c.Nq / 8);
+                tmpd = blk_pairwise_sum(tv, nm, S, sc, sc + 200, reinterpret_cast<double *>(sc + 400), sc + 800);
+            } else tmpd = blk_pairwise_sum(tv, nm, S, S.P.i[I_EVENTS], S.P.i[I_SUCC], S.P.f[F_CAPH]);
             if (tid == 0) S.dbuf[0] = (0. + dep[pit]) / tmpd;
             __syncthreads();
             const double dfrac = S.dbuf[0];
