@@ -854,6 +854,20 @@ __device__ __noinline__ void sp_prepass_c(const DevConst &c, Smem &S, unsigned c
         const double zd = FD(F_Z, d), zr = FD(F_QS, d), fh = FD(F_FILLH, d), area = areaA[d];
         const double q = FD(F_Q, d), dist = FD(F_E, d), mh0 = FD(F_MAXH, d);
         const int pp = ID(I_PITID, d);
+        {   // the per-proposal arrays come from DRAM (296 landscapes do not fit the L2): the next iteration's lines are
+            // requested into L2 now
+            const int dn = d + TPB;
+            if (dn < N) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&FD(F_Z, dn)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&FD(F_QS, dn)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&FD(F_FILLH, dn)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&FD(F_Q, dn)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&FD(F_E, dn)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&FD(F_MAXH, dn)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&ID(I_RCV, dn)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&ID(I_PITID, dn)));
+            }
+        }
         double dh = 0.95 * (zd - zr);
         if (zd > sea && zr < sea) dh = 0.99 * (zd - sea);
         if (dh < 0.001) dh = 0.;
