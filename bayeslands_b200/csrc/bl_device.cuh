@@ -132,6 +132,8 @@ __device__ inline int blk_compact(int n, int *out, Pred pred, Smem &S)
     return total;
 }
 
+// request a line into L2 (streaming passes over per-proposal arrays: 296 landscapes do not fit the L2, the data is in DRAM)
+__device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ inline double ldv(const double *p) { return __ldcg(p); }
 __device__ inline void stv(double *p, double v) { __stcg(p, v); }
 
@@ -1214,6 +1216,7 @@ __device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea
         for (int k = tid; k < N; k += TPB) {
             const unsigned char fl = flagsA[k];
             const double cdk = cdepo[k], zk = z[k], fh = W[k], vol = pitVol[k], ar = areaA[k];
+            if (k + 4 * TPB < N) { pf_l2(cdepo + k + 4 * TPB); pf_l2(z + k + 4 * TPB); pf_l2(W + k + 4 * TPB); pf_l2(pitVol + k + 4 * TPB); }
             double d = (fl & 1) ? cdk : 0.;
             double th = 0.;
             int island = 0;
@@ -1396,6 +1399,7 @@ __device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea
             const unsigned char fl = flagsA[k];
             const double ce = cero[k], ar = areaA[k], dp = dep[k];
             double th = dth[k];
+            if (k + 4 * TPB < N) { pf_l2(cero + k + 4 * TPB); pf_l2(dep + k + 4 * TPB); pf_l2(dth + k + 4 * TPB); }
             double sf = 0.;
             if (fl & 1) {
                 th += dp / ar;
@@ -1410,6 +1414,7 @@ __device__ __noinline__ void phase_erodep(const DevConst &c, Smem &S, double sea
         for (int k = tid; k < N; k += TPB) {
             const unsigned char fl = flagsA[k];
             const double ce = cero[k], ar = areaA[k], th = dth[k];
+            if (k + 4 * TPB < N) { pf_l2(cero + k + 4 * TPB); pf_l2(dth + k + 4 * TPB); }
             const double erosion = ce / ar;
             sedflux[k] = (fl & 1) ? erosion + th : 0.;
         }

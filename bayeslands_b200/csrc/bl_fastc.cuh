@@ -564,6 +564,7 @@ __device__ __noinline__ void basins_c(const DevConst &c, Smem &S, unsigned char 
 #pragma unroll 2
     for (int v = tid; v < N; v += TPB) {
         const bool wet = W[v] > z[v];
+        if (v + 2 * TPB < N) { pf_l2(W + v + 2 * TPB); pf_l2(z + v + 2 * TPB); pf_l2(pos1 + v + 2 * TPB); }
         const int root = rootpos[pos1[v]];
         const bool in = wet || root == v;
         pitID[v] = in ? root : -1;
@@ -574,6 +575,7 @@ __device__ __noinline__ void basins_c(const DevConst &c, Smem &S, unsigned char 
 #pragma unroll 2
     for (int v = tid; v < N; v += TPB) {
         const double wv = W[v], zv = z[v];
+        if (v + 2 * TPB < N) { pf_l2(W + v + 2 * TPB); pf_l2(z + v + 2 * TPB); pf_l2(pos1 + v + 2 * TPB); }
         val[pos1[v]] = (wv > zv) ? (wv - zv) * c.area[v] : 0.0;
     }
     __syncthreads();
@@ -759,6 +761,7 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
             const int p = posA[v];
             const unsigned n = cnt8[v];
             const double a = areaA[v];
+            if (v + 4 * TPB < N) { pf_l2(posA + v + 4 * TPB); pf_l2(cnt8 + v + 4 * TPB); }
             const unsigned q = qpos[p];
             const unsigned f = (p + 1 < N) ? qpos[p + 1] : 0u;
             const double q0 = a * ((v >= nbn) ? rain : 0.);
@@ -807,6 +810,7 @@ __device__ __noinline__ void discharge_c(const DevConst &c, Smem &S, unsigned ch
 #pragma unroll 4
     for (int v = tid; v < N; v += TPB) {
         const double q = vals[posr[v]], dz = dzw[v], dist = distr[v];
+        if (v + 4 * TPB < N) { pf_l2(posr + v + 4 * TPB); pf_l2(dzw + v + 4 * TPB); pf_l2(distr + v + 4 * TPB); }
         Q[v] = q;
         if (q > 0. && dz > 0.) {
             const double tmp = stdexp ? dist / (erod * sqrt(q) * 1.0) : dist / (erod * powx(q, em) * powx(dz / dist, en1));
@@ -1150,7 +1154,10 @@ __device__ __noinline__ void apply_c(const DevConst &c, Smem &S, unsigned char *
     const unsigned char *__restrict__ gflags = c.flags;
     const unsigned *__restrict__ nbin = c.nbf2;
 #pragma unroll 4
-    for (int k = tid; k < N; k += TPB) zs[k] = z[k] + sedflux[k];
+    for (int k = tid; k < N; k += TPB) {
+        if (k + 4 * TPB < N) { pf_l2(z + k + 4 * TPB); pf_l2(sedflux + k + 4 * TPB); }
+        zs[k] = z[k] + sedflux[k];
+    }
     __syncthreads();
     const double *__restrict__ dispA = c.disp;
     const int nbn = c.bounds;
