@@ -527,6 +527,7 @@ __device__ __noinline__ void basins(const DevConst &c, Smem &S, unsigned char *d
 #pragma unroll 2
     for (int v = tid; v < N; v += TPB) {
         const double wv = W[v], zv = z[v];
+        if (v + 2 * TPB < N) { pf_l2(W + v + 2 * TPB); pf_l2(z + v + 2 * TPB); pf_l2(pos1 + v + 2 * TPB); }
         const bool wet = wv > zv;
         const int root = root16[v];
         pitID[v] = (wet || root == v) ? root : -1;
@@ -786,6 +787,7 @@ __device__ __noinline__ void streampower(const DevConst &c, Smem &S, unsigned ch
     for (int d = tid; d < N; d += TPB) {
         const int r = sm.r16[d];
         const double zd = z[d], zr = z[r], fh = W[d], area = c.area[d];
+        if (d + 2 * TPB < N) { pf_l2(z + d + 2 * TPB); pf_l2(W + d + 2 * TPB); pf_l2(maxhA + d + 2 * TPB); pf_l2(pitID + d + 2 * TPB); }
         const double q = first ? sm.vals[d] : Qg[d];
         double dh = 0.95 * (zd - zr);
         if (zd > sea && zr < sea) dh = 0.99 * (zd - sea);
