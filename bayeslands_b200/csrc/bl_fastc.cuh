@@ -336,21 +336,44 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     unsigned *rootbits = (unsigned *)(dsm + (size_t)8 * Nq);     // one bit per node: base levels (self-receivers)
     for (int w = tid; w < Nq / 32; w += TPB) rootbits[w] = 0u;
     __syncthreads();
+    // pass 1: the donors of v are the neighbours whose receiver is v: their slots as a bit mask (kept in shared memory for
+    // pass 2), their number, the first (lowest-id) one = the successor of enter(v)
+    unsigned char *dmask = dsm + (size_t)2 * Nq;                 // [Nq] donor slots of every node (KDT <= 8 bits used; wider rows: see below)
 #pragma unroll 2
     for (int v = tid; v < N; v += TPB) {
-        Ids<KDT> ids, jds;
-        const int r = r16[v];
+        Ids<KDT> ids;
         load_ids<KDT>(c, v, ids);
-        load_ids<KDT>(c, r, jds);
         int f = NONE16, n = 0;
+        unsigned dm = 0u;
 #pragma unroll
         for (int p = 0; p < KDT; ++p) {
             if (ids.get(p) == NONE16) continue;
             const int w = ids.get(p);
-            if (r16[w] == v) { ++n; if (w < f) f = w; }
+            if (r16[w] == v) { ++n; if (w < f) f = w; dm |= 1u << p; }
         }
+        if (KDT <= 8) dmask[v] = (unsigned char)dm;
+        nxg[2 * v] = (unsigned short)((f != NONE16) ? 2 * f : 2 * v + 1);
+        if (r16[v] == v) atomicOr(&rootbits[v >> 5], 1u << (v & 31));        // a root's exit is linked to the next root below
+        if (filled) cnt8[v] = (unsigned char)n;              // donor counts: the breadth-first layout of discharge_c
+    }
+    __syncthreads();
+    // pass 2: the successor of exit(v) is the next donor of v's receiver after v (read off the receiver's mask), else the
+    // receiver's exit
+#pragma unroll 2
+    for (int v = tid; v < N; v += TPB) {
+        const int r = r16[v];
+        if (r == v) continue;
+        Ids<KDT> jds;
+        load_ids<KDT>(c, r, jds);
         int nx = NONE16;
-        if (r != v) {
+        if (KDT <= 8) {
+            const unsigned dm = dmask[r];
+#pragma unroll
+            for (int p = 0; p < KDT; ++p) {
+                const int w = jds.get(p);
+                if (((dm >> p) & 1u) && w > v && w < nx) nx = w;
+            }
+        } else {
 #pragma unroll
             for (int p = 0; p < KDT; ++p) {
                 if (jds.get(p) == NONE16) continue;
@@ -358,13 +381,7 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
                 if (w > v && w < nx && r16[w] == r) nx = w;
             }
         }
-        const unsigned en = (unsigned)((f != NONE16) ? 2 * f : 2 * v + 1);
-        if (r != v) reinterpret_cast<unsigned *>(nxg)[v] = en | ((unsigned)((nx != NONE16) ? 2 * nx : 2 * r + 1) << 16);
-        else {                                              // a root's exit is linked to the next root below
-            nxg[2 * v] = (unsigned short)en;
-            atomicOr(&rootbits[v >> 5], 1u << (v & 31));
-        }
-        if (filled) cnt8[v] = (unsigned char)n;              // donor counts: the breadth-first layout of discharge_c
+        nxg[2 * v + 1] = (unsigned short)((nx != NONE16) ? 2 * nx : 2 * r + 1);
     }
     __syncthreads();
     sub_tick(stl, 28);      // receivers to shared memory + link construction
