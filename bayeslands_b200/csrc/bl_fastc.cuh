@@ -1,21 +1,33 @@
 // bl_fastc.cuh - "compact" shared-memory time step (included by bl_device.cuh after bl_fast.cuh).
 //
 // bl_fast.cuh keeps 17 bytes of shared memory per node, so a 12.7 k-node landscape owns an SM: one CTA, and nothing to
-// hide its barrier waits (38 % of the warp samples, profiles/r02x_stalls_by_line.txt).  The phases below compute the
-// same values in the same fp64 operation order with at most 8 bytes per node (+ bitmaps) in shared memory, so that TWO
-// 512-thread CTAs - two landscapes - are resident per SM and one runs while the other waits:
-//   fill            W fp64 in shared memory, pending set as one BIT per node (woken with red.shared.or), z read from L2
-//   receivers       two passes over the same 8N bytes (W, then z)
-//   stack order     links built against receivers in shared memory (2N), the Euler tour written to global scratch and
-//                   brought back as (next:16 | rank:16) words for the ranking (8N)
-//   basins          root ids (2N), then the stack-ordered volume terms (8N) in the same bytes
+// hide its barrier waits (38 % of the warp samples in round 1).  The phases below compute the same values in the same
+// fp64 operation order with at most 8 bytes per node (+ bitmaps and 4 KB of lists) in shared memory, so that TWO 512-thread
+// CTAs - two landscapes - are resident per SM and one runs while the other waits:
+//   fill            W fp64 in shared memory, pending set as one BIT per node (woken with red.shared.or), z of the evaluated
+//                   node and its id row from L2; every warp sweeps, one batch of 8 bitmap words per warp and level; the
+//                   initial pending set is the ring of nodes next to a ghost node (the rest is woken as the front arrives)
+//   receivers       two passes over the same 8N bytes (W, then z brought in by a TMA bulk copy); they also leave W(d) - W(rcv),
+//                   the receiver distance, z(rcv) and 16-bit copies of both receiver arrays for the later passes
+//   stack order     receivers (2N, bulk copy) for the link construction (donor slots as a bit mask per node, two passes); the
+//                   Euler tour as 2N u16 successors (4N, written to global scratch, bulk copy back), ranked in O(N) work:
+//                   dense splitters, one walk per sublist, pointer jumping over the splitters only, a dense finishing pass;
+//                   the same ranking yields every node's depth in the receiver tree
+//   basins          roots from the stack segments (marks propagated over stack positions, 2N), then the stack-ordered
+//                   volume terms (8N) in the same bytes; long segments summed by a warp that skips the zero terms
+//   drainage        fast::drainage with its two u16 tables staged by bulk copies
 //   discharge / stream power
 //                   node values fp64 indexed by BREADTH-FIRST POSITION: the depth-first stack is stably sorted by depth,
 //                   which puts the donors of a node next to each other (ascending id), so a node sums the contiguous
 //                   run vals[fc .. fc+cnt) backwards - no donor links, no bucket order, no receiver ids in shared memory.
-//                   (first child, donor count, rule) live in one global word per position, fetched one level ahead.
-//   diffusion       z fp64 (8N); the "neighbour is inside" test comes from a per-node bit mask (mesh constant)
-// Selected by bl_ctx_create (DevConst::compact) for non-marine configurations on colour-major meshes.
+//                   One 16-byte global record per position (first child, donor count, rule, node id, fp64 payload) is
+//                   fetched one item ahead; the flow CFL condition rides on the pass that writes Q by node id
+//   diffusion       z fp64 (8N); the "neighbour is an inside node" test comes from a per-node bit mask (mesh constant);
+//                   the ghost update is folded into the same pass
+// Streaming passes over per-proposal arrays issue every load before the first branch, launder the loop index (so that the
+// compiler keeps no per-array running address under the 64-register cap) and request the next batch's lines into L2.
+// Selected by bl_ctx_create (DevConst::compact) for non-marine configurations on colour-major meshes when there are more
+// landscapes than SMs; parity: tests/test_gpu_compact.py.
 
 namespace fastc {
 
@@ -542,7 +554,7 @@ __device__ __noinline__ void basins_c(const DevConst &c, Smem &S, unsigned char 
     unsigned short *queue = (unsigned short *)tail_of(dsm, Nq);   // (lo, hi, root) of the long segments
     constexpr int QCAP = (NWARP / 2) * 256 / 6;
     const double *__restrict__ z = S.P.f[F_Z], *__restrict__ W = S.P.f[F_FILLH];
-    const int *__restrict__ rcv1 = S.P.i[I_RCV1], *__restrict__ pos1 = S.P.i[I_POS1], *__restrict__ ns1 = S.P.i[I_NS];
+    const int *__restrict__ pos1 = S.P.i[I_POS1], *__restrict__ ns1 = S.P.i[I_NS];
     int *__restrict__ pitID = S.P.i[I_PITID];
     double *__restrict__ pitVol = S.P.f[F_PITVOL];
     unsigned short *__restrict__ pid16w = (unsigned short *)S.P.i[I_FC] + np_of(N);
