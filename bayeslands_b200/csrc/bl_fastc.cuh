@@ -1202,8 +1202,9 @@ __device__ __noinline__ void apply_c(const DevConst &c, Smem &S, unsigned char *
         const unsigned char fg = gflags[g];
         const unsigned inm = nbin[g];            // bit p: neighbour slot p is an inside node (borders2)
         const double zg = zs[g];
-        const double sf = sedflux[g];
-        const double c0 = cumdiff[g] + sf, h0 = cumhill[g];
+        // the three per-proposal values are requested here and first used after the gather below (they come from DRAM)
+        const double sf = sedflux[g], cdf0 = cumdiff[g], h0 = cumhill[g];
+        if (g + TPB < N) { pf_l2(sedflux + g + TPB); pf_l2(cumdiff + g + TPB); pf_l2(cumhill + g + TPB); }
         const double dsp = dispA ? dispA[g] * timestep : 0.;
         const double area = areaA[g];
         Ids<KDT> ids;
@@ -1247,6 +1248,7 @@ __device__ __noinline__ void apply_c(const DevConst &c, Smem &S, unsigned char *
         // the node's new elevation is final here (its neighbours read the old one from shared memory); ghost nodes
         // take their parent's new elevation below, so the increments of the parents are kept
         cd[g] = d;
+        const double c0 = cdf0 + sf;
         if (fg & 1) { cumdiff[g] = c0 + d; cumhill[g] = h0 + d; }
         else cumdiff[g] = c0;
         if (g >= nbn || c.btype == 0) {
