@@ -490,7 +490,11 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     unsigned short *depg = (unsigned short *)S.P.i[I_FC];            // depth by stack position (filled surface: discharge_c)
     int mdep = 0;
     if (!S.ibuf[7] && S_tot <= 4096 && !(c.dbg & 256)) {
-        // dense finish: rank of enter(v) = (enter events from its sublist's splitter to the end) - (those before it)
+        // dense finish: rank of enter(v) = (enter events from its sublist's splitter to the end) - (those before it).
+        // The permutation (stack[p] = v, depth by position) is scattered in SHARED memory - the successors are no longer
+        // needed, the splitter table stays where it is - and leaves with coalesced stores.
+        unsigned short *stk_s = (unsigned short *)dsm;                        // [N] node at stack position p   (over nx16)
+        unsigned short *dep_s = (unsigned short *)(dsm + (size_t)2 * Nq);     // [N] depth at stack position p  (over nx16)
 #pragma unroll 4
         for (int v = tid; v < N; v += TPB) {
             const unsigned info = infog[v];
@@ -499,8 +503,14 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
             const int ra = (int)(a >> 32) - (int)(info & 0x3FFu);
             const int p = N - re;
             pos[v] = p;
-            stack[p] = v;
-            if (filled) { const int dep = 2 * p - (M - ra); depg[p] = (unsigned short)dep; mdep = max(mdep, dep); }
+            stk_s[p] = (unsigned short)v;
+            if (filled) { const int dep = 2 * p - (M - ra); dep_s[p] = (unsigned short)dep; mdep = max(mdep, dep); }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int p = tid; p < N; p += TPB) {
+            stack[p] = stk_s[p];
+            if (filled) depg[p] = dep_s[p];
         }
     } else {
         int sp = tid;
