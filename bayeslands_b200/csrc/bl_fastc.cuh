@@ -146,7 +146,7 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
 #define BL_FILLC_ALL 1
 #endif
 #ifndef BL_FILLC_PF
-#define BL_FILLC_PF 1
+#define BL_FILLC_PF 0
 #endif
     // sweeping warps: with BL_FILLC_ALL every warp of a (<= 512-thread) CTA sweeps, so a thin front is spread over twice as
     // many warps; a batch is 8 bitmap words per warp (one batch covers a level of up to NWF * 256 nodes); the slot lists take
@@ -199,13 +199,11 @@ __device__ __noinline__ void fill_c(const DevConst &c, Smem &S, unsigned char *d
                         if (mine) {
                             red_and(a, ~mine);
 #if BL_FILLC_PF
-                            // z and the id rows of these 32 nodes: requested now, needed by the evaluation below
+                            // the elevations of these 32 nodes (two lines): requested now, needed by the evaluation below
+                            // (the id rows - four more lines per word - are not worth their instructions: measured)
                             const char *pz = (const char *)(zg + lo);
                             asm volatile("prefetch.global.L1 [%0];" ::"l"(pz));
                             asm volatile("prefetch.global.L1 [%0];" ::"l"(pz + 128));
-                            const char *pi = (const char *)(ngb16f + (size_t)lo * KDT);
-#pragma unroll
-                            for (int u = 0; u < KDT / 2; ++u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pi + 128 * u));
 #endif
                         }
                     }
