@@ -70,7 +70,9 @@ srcs = {}
 def text(f, l):
     if f not in srcs:
         try:
-            srcs[f] = open("bayeslands_b200/csrc/" + f).read().split("\n")
+            import os
+            here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+            srcs[f] = open(os.path.join(here, "bayeslands_b200", "csrc", f)).read().split("\n")
         except Exception:
             srcs[f] = []
     s = srcs[f]
