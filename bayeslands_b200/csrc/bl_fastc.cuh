@@ -1085,9 +1085,9 @@ __device__ __noinline__ void streampower_c(const DevConst &c, Smem &S, unsigned 
     __syncthreads();
     STICK(12);
     if (nev == 0) return;
-    int over = 0;
+    int over = 0, allaff = 0;      // allaff: an event's pit lies under the sea - the serial replay takes every event
     if (S.ibuf[1])
-        for (int e = tid; e < nev; e += TPB) { const int pit = ev_pit[e]; if (pit != NONE16 && W[pit] < sea) over = 1; }
+        for (int e = tid; e < nev; e += TPB) { const int pit = ev_pit[e]; if (pit != NONE16 && W[pit] < sea) allaff = 1; }
     // one WARP per pit that receives events: the lanes scan the event list 32 entries at a time and the matching events
     // are applied in order (same sums as the serial loop: events of other pits do not touch this pit's deposit)
     int *plist = S.P.i[I_EVENTS];
@@ -1113,18 +1113,39 @@ __device__ __noinline__ void streampower_c(const DevConst &c, Smem &S, unsigned 
                     else { ovf = true; break; }
                 }
             }
-            if (ovf) over = 1;
+            if (ovf) { over = 1; if (lane == 0) has_ev[pit] = 3; }     // bit 1: this pit's events must be replayed in order
             if (lane == 0) S.P.f[F_VAL][pit] = dp;
         }
     }
-    over = __syncthreads_or(over);
+    {
+        const int both = __syncthreads_or(over | (allaff << 1));
+        allaff = (both >> 1) & 1;
+        over = (both & 1) | allaff;
+    }
     STICK(13);
     if (!over) {
         for (int i = tid; i < nbase1; i += TPB) { const int pit = base1[i]; if (has_ev[pit]) depo[pit] = S.P.f[F_VAL][pit]; }
         __syncthreads();
         return;
     }
-    // serial replay, literal (FLOWalgo.f90:967-1034)
+    // Some pit overflows.  A cascade only moves sediment DOWN the drainage chain (FLOWalgo.f90:1002 tmpID = pitDrain), so
+    // the pits whose deposit can differ from the independent sums above are the overflowing pits and everything
+    // downstream of them: those are marked, every other pit commits its sum, and the literal serial replay
+    // (FLOWalgo.f90:967-1034) runs over the events of the marked pits only, in the original order.
+    if (!allaff) {
+        for (int ip = tid; ip < npl; ip += TPB) {
+            int p = base1[plist[ip]];
+            if (!(has_ev[p] & 2)) continue;
+            for (int it = 0; it < nbase1; ++it) {
+                const int q = pitDrain[p];
+                if (q < 0 || q == p) break;
+                has_ev[q] |= 2;
+                p = q;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nbase1; i += TPB) { const int pit = base1[i]; if (has_ev[pit] == 1) depo[pit] = S.P.f[F_VAL][pit]; }
+    }
     for (int k = tid; k < N; k += TPB) pitVol[k] = pitVol1[k];
     if (tid == 0) S.ibuf[0] = 0;
     __syncthreads();
@@ -1132,6 +1153,7 @@ __device__ __noinline__ void streampower_c(const DevConst &c, Smem &S, unsigned 
         unsigned st = 0;
         for (int e = 0; e < nev; ++e) {
             if (ev_pit[e] == NONE16) continue;
+            if (!allaff && !(has_ev[ev_pit[e]] & 2)) continue;
             const int donor = ev_donor[e];
             const int recvr = rcv[donor];
             double pitDep = ev_dep[e];
