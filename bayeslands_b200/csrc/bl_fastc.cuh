@@ -369,7 +369,7 @@ __device__ __noinline__ void links_stack_c(const DevConst &c, Smem &S, unsigned 
     __syncthreads();
     // pass 2: the successor of exit(v) is the next donor of v's receiver after v (read off the receiver's mask), else the
     // receiver's exit
-#pragma unroll 2
+#pragma unroll 4
     for (int v = tid; v < N; v += TPB) {
         const int r = r16[v];
         if (r == v) continue;
@@ -598,7 +598,7 @@ __device__ __noinline__ void basins_c(const DevConst &c, Smem &S, unsigned char 
         for (int p = p0; p < p1; ++p) { const unsigned m = rootpos[p]; if (m != NONE16) cur = m; else rootpos[p] = (unsigned short)cur; }
     }
     __syncthreads();
-#pragma unroll 2
+#pragma unroll 4
     for (int v = tid; v < N; v += TPB) {
         const bool wet = W[v] > z[v];
         if (v + 2 * TPB < N) { pf_l2(W + v + 2 * TPB); pf_l2(z + v + 2 * TPB); pf_l2(pos1 + v + 2 * TPB); }
@@ -609,7 +609,7 @@ __device__ __noinline__ void basins_c(const DevConst &c, Smem &S, unsigned char 
         pitVol[v] = -1.0;
     }
     __syncthreads();
-#pragma unroll 2
+#pragma unroll 4
     for (int v = tid; v < N; v += TPB) {
         const double wv = W[v], zv = z[v];
         if (v + 2 * TPB < N) { pf_l2(W + v + 2 * TPB); pf_l2(z + v + 2 * TPB); pf_l2(pos1 + v + 2 * TPB); }
