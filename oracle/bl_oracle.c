@@ -1,7 +1,8 @@
 /* bl_oracle.c - CPU ORACLE (test infrastructure, see bl_oracle.h).  Pinned: the sfd.c routines (against
  * oracle/_ref/libsfd_ref.so and tests/golden) and, by the hand-derived fixtures of tests/micro.py, fillPD, fstack.build,
- * basinparameters, basindrainage(all), discharge, streampower + pit cascade, the land-pit fill.  "parity unpinned" (no
- * fixture of their own): flowcfl with n != 1, the getid1 re-run, diffmarine, marine_distribution, the marine cascade branch.
+ * basinparameters, basindrainage(all), discharge, streampower + pit cascade, the land-pit fill, marine_distribution (F4a / F4b)
+ * and diffmarine with its sub-step loop (F5).  "parity unpinned" (no fixture of their own): flowcfl with n != 1, the getid1
+ * re-run, the marine branch of the pit cascade (a lake overflowing into the sea).
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared (no -ffast-math), mirroring
  * pyBadlands/libUtils/Makefile:47 (f2py modules: -O3 -ftree-vectorize, no fast-math, no FMA).

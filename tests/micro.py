@@ -198,3 +198,167 @@ F3 = dict(N=8,
           pitVol=[-1.0, 5.0, 3.0, -1.0, -1.0, -1.0, -1.0, -1.0],
           fillH=[0.0, 9.0, 8.0, 7.5, 7.0, 1.0, 2.0, 3.0],
           pitDrain=[-1, 5, 1, -1, -1, -1, -1, -1])
+
+
+# ---------------------------------------------------------------------------------------------------
+# F4  river sediment reaching the sea: marine_distribution (PDalgo.f90:136-269), both ways out of its walk
+# F5  the same step followed by the river-borne marine diffusion sub-steps (buildFlux.py:198-247, FLOWalgo.f90:332-388)
+# positions:    0(g0)   1     2     3    4    5     6    7(g1)       ids: g0 = 0, g1 = 1, position p -> id p + 1
+F4A_Z = [-40.0, -30.0, -20.0, -10.0, 5.0, 20.0, 40.0, 60.0]        # a ramp into the sea (sea level 0): diffnb 5, diffprop 0.9
+F4B_Z = [-40.0, -5.0, -20.0, -10.0, 5.0, 20.0, 40.0, 60.0]         # a sill at position 1: marine pit at positions 2, 3; diffnb 1, diffprop 0.1
+F4_RAIN, F4_EROD, F4_SEA, F4_DT = 1.0, 2.0e-3, 0.0, 204.0
+F5_CDR = 0.5                                                        # CFLms = 0.01 * 100^2 / 0.5 = 200 a: sub-steps of 200 a and 4 a
+
+
+def inputs_marine(diffnb, diffprop, criver=0.0):
+    inp = inputs(fillmax=200.0)
+    inp.seapos, inp.diffnb, inp.diffprop, inp.CDr = F4_SEA, int(diffnb), float(diffprop), float(criver)
+    return inp
+
+
+def _f4_fluvial(Z):
+    """Erosion of the three land nodes (ids 7, 6, 5) and the load that reaches the first marine node (id 4) at dt = 204 a
+    (FLOWalgo.f90:635-714, :875-964): id 5 drains into the sea, its dh is 0.99 (z - sea) (:652)."""
+    import math
+    z = {0: Z[0], 1: Z[7]}
+    for p in range(1, 7):
+        z[p + 1] = Z[p]
+    Q = {7: AREA * F4_RAIN + 0.0}
+    Q[6] = AREA * F4_RAIN + Q[7]
+    Q[5] = AREA * F4_RAIN + Q[6]
+    Q[4] = AREA * F4_RAIN + Q[5]
+    Q[3] = AREA * F4_RAIN + Q[4]
+    Q[2] = AREA * F4_RAIN + Q[3]
+    Q[0] = 0.0 + Q[2]
+    Q[1] = 0.0
+    assert float(math.floor(DX / (F4_EROD * math.sqrt(Q[2])))) == F4_DT          # flowcfl (FLOWalgo.f90:299-330), id 2 has the largest Q
+    ero = {k: 0.0 for k in range(8)}
+    for d, dh in ((7, 0.95 * (z[7] - z[6])), (6, 0.95 * (z[6] - z[5])), (5, 0.99 * (z[5] - F4_SEA))):
+        spl = -F4_EROD * 1.0 * 1.0 * math.sqrt(Q[d]) * (dh / DX)
+        assert -(0.0 + spl) * F4_DT <= dh                                          # no capping (:706-712)
+        ero[d] = 0.0 + spl * F4_DT * AREA
+    load = -ero[5] + (0.0 + (-ero[6] + (0.0 + (-ero[7] + 0.0))))                   # sedfl handed down ids 7 -> 6 -> 5 -> 4
+    return z, Q, ero, load
+
+
+def _finish(z, ero, elev):
+    """deposition = diffsed = elev - elevation (PDalgo.f90:263), sedflux = erosion + deposition (flowNetwork.py:787-791),
+    elevation += sedflux (buildFlux.py:193)."""
+    n = len(z)
+    diffsed = [elev[k] - z[k] for k in range(n)]
+    sedflux = [0.0 if k < 2 else ero[k] / AREA + (0.0 + diffsed[k]) for k in range(n)]
+    znew = [z[k] + sedflux[k] for k in range(n)]
+    return diffsed, sedflux, znew
+
+
+def f4a_derive():
+    """Ramp: 5 rounds of load / 5 start at id 4 (water depth 10 m).  Rounds 1, 2: the share fits under diffprop x the
+    room below sea level and stays.  Rounds 3-5: id 4 keeps diffprop x its room, the rest moves to its lowest neighbour
+    id 3 (:249-253), which has room for it (:201-204)."""
+    z, Q, ero, load = _f4_fluvial(F4A_Z)
+    e = dict(z)
+    share = load / 5.0                                   # seavol / float(diffnbmax) (:160)
+    for rnd in range(5):
+        sd = share
+        maxz = min(max(e[3], e[5]), F4_SEA)              # highest neighbour, clipped to sea level (:171-176)
+        vol = max(0.0, 0.9 * (maxz - e[4]) * AREA)
+        assert sd / AREA >= 1.0e-2
+        if sd < vol:                                     # rounds 1, 2
+            assert rnd < 2
+            e[4] = e[4] + sd / AREA
+            continue
+        assert rnd >= 2
+        sd = sd - vol
+        e[4] = e[4] + vol / AREA
+        assert sd > 0.0 and e[3] < e[4] and e[3] < e[5]  # lowest neighbour is id 3, lower than id 4: pass the rest on
+        sd3 = 0.0 + sd
+        maxz = min(max(e[2], e[4]), F4_SEA)
+        vol3 = max(0.0, 0.9 * (maxz - e[3]) * AREA)
+        assert sd3 / AREA >= 1.0e-2 and sd3 < vol3
+        e[3] = e[3] + sd3 / AREA
+    elev = [e[k] for k in range(8)]
+    ero_l = [ero[k] for k in range(8)]
+    depo = [0.0] * 8
+    depo[4] = 0.0 + load
+    diffsed, sedflux, znew = _finish([z[k] for k in range(8)], ero_l, elev)
+    return dict(Q=[Q[k] for k in range(8)], ero=ero_l, depo=depo, diffsed=diffsed, sedflux=sedflux, z=znew, load=load)
+
+
+def f4b_derive():
+    """Sill: one round with the whole load (diffnb 1), diffprop 0.1.  id 4 keeps 0.1 x 10 m, passes on to id 3 (bottom of
+    the marine pit), which keeps 0.1 x 15 m, has no lower neighbour (:214) and more left than lifts it 0.1 m above its
+    highest neighbour: it is raised by dh (:216-218), the rest goes BACK to the start node id 4 (:219-228), which keeps
+    0.1 x 9 m, has no lower neighbour either and takes the remainder (:231-234)."""
+    z, Q, ero, load = _f4_fluvial(F4B_Z)
+    e = dict(z)
+    sd = load / 1.0
+    vol = max(0.0, 0.1 * (min(max(e[3], e[5]), F4_SEA) - e[4]) * AREA)
+    assert sd / AREA >= 1.0e-2 and sd >= vol
+    sd = sd - vol
+    e[4] = e[4] + vol / AREA
+    assert sd > 0.0 and e[3] < e[4]
+    sd3 = 0.0 + sd                                       # id 3
+    vol3 = max(0.0, 0.1 * (min(max(e[2], e[4]), F4_SEA) - e[3]) * AREA)
+    assert sd3 / AREA >= 1.0e-2 and sd3 >= vol3
+    sd3 = sd3 - vol3
+    e[3] = e[3] + vol3 / AREA
+    assert sd3 > 0.0 and e[2] >= e[3] and e[4] >= e[3]  # no lower neighbour
+    dh = max(e[2], e[4]) - e[3] + 0.1                   # the unclipped highest neighbour (:207-213)
+    assert sd3 > dh * AREA
+    e[3] = e[3] + dh
+    sd3 = sd3 - dh * AREA
+    sd = 0.0 + sd3                                       # back at id 4 (seadep(4) was zeroed when it passed its rest on)
+    vol = max(0.0, 0.1 * (min(max(e[3], e[5]), F4_SEA) - e[4]) * AREA)
+    assert sd / AREA >= 1.0e-2 and sd >= vol
+    sd = sd - vol
+    e[4] = e[4] + vol / AREA
+    assert sd > 0.0 and e[3] >= e[4] and e[5] >= e[4]
+    dh = max(e[3], e[5]) - e[4] + 0.1
+    assert sd <= dh * AREA
+    e[4] = e[4] + sd / AREA
+    elev = [e[k] for k in range(8)]
+    ero_l = [ero[k] for k in range(8)]
+    depo = [0.0] * 8
+    depo[4] = 0.0 + load
+    W = [z[k] for k in range(8)]
+    W[3] = z[2] + EPS                                    # fillPD: the marine pit fills to its sill (PDalgo.f90:58-79)
+    W[4] = W[3] + EPS
+    diffsed, sedflux, znew = _finish([z[k] for k in range(8)], ero_l, elev)
+    return dict(Q=[Q[k] for k in range(8)], ero=ero_l, depo=depo, diffsed=diffsed, sedflux=sedflux, z=znew, load=load, fillH=W)
+
+
+def f5_derive():
+    """F4a followed by the marine diffusion of the river deposits with criver = 0.5: two sub-steps (200 a, 4 a).  coeff is
+    frozen before the loop (buildFlux.py:205): criver / area on ids 2, 3, 4 (below sea level after the fluvial update).
+    A node loses to a lower neighbour when it carries more than 0.1 m of river deposits (FLOWalgo.f90:367), gains from a
+    higher marine neighbour that does (:369); towards a ghost node only the loss exists (:372-377)."""
+    f = f4a_derive()
+    z = list(f["z"])
+    H = list(f["diffsed"])                               # np.sum(deposition, axis=1): the marine deposits of this step
+    cum = list(f["sedflux"])
+    assert z[2] < F4_SEA and z[3] < F4_SEA and z[4] < F4_SEA and z[5] >= F4_SEA
+    c = 1.0 / AREA * F5_CDR
+    left, right = {2: 0, 3: 2, 4: 3}, {2: 3, 3: 4, 4: 5}
+    ghost = {0}
+    trace = []
+    for step in (200.0, 4.0):                            # min(CFLms, diffstep); mindt never binds (checked below)
+        d = {}
+        for g in (2, 3, 4):
+            acc = 0.0
+            for nb in (left[g], right[g]):
+                flx = DX * (z[nb] - z[g]) / DX
+                if nb in ghost:
+                    if H[g] > 0.1 and z[g] > z[nb]:
+                        acc = acc + c * flx
+                        trace.append(("ghost-loss", g, step))
+                elif H[g] > 0.1 and z[g] > z[nb]:
+                    acc = acc + c * flx
+                    trace.append(("loss", g, step))
+                elif H[nb] > 0.1 and z[g] < z[nb] and z[nb] < F4_SEA:
+                    acc = acc + c * flx
+                    trace.append(("gain", g, step))
+            assert not (acc < 0.0 and acc * step < -H[g])
+            d[g] = acc
+        for g in (2, 3, 4):
+            H[g] += d[g] * step; z[g] += d[g] * step; cum[g] += d[g] * step
+    return dict(z=z, cumdiff=cum, trace=trace, ero=f["ero"], depo=f["depo"], sedflux=f["sedflux"])

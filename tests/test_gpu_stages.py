@@ -119,3 +119,24 @@ def test_micro_fixtures_on_the_device(generic):
     eng8 = Engine(m8, micro.inputs(), 1, force_generic=generic)
     d1, d2 = eng8.basindrainage(f["pitID"], f["pitVol"], f["rcv"], f["fillH"], -1000.0)
     assert d1.tolist() == f["pitDrain"] and d2.tolist() == f["pitDrain"]
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_micro_marine_fixtures_on_the_device(generic):
+    """F4a / F4b (marine_distribution: both exits of the walk, restart from the entry node) and F5 (two sub-steps of the
+    river-borne marine diffusion with every branch of diffmarine) through bl_step, against the hand derivation."""
+    import micro
+    from bayeslands_b200.engine import Engine
+    cases = (("F4a", micro.F4A_Z, micro.inputs_marine(5, 0.9), micro.f4a_derive, ("Q", "ero", "depo", "sedflux", "z")),
+             ("F4b", micro.F4B_Z, micro.inputs_marine(1, 0.1), micro.f4b_derive, ("fillH", "Q", "ero", "depo", "sedflux", "z")),
+             ("F5", micro.F4A_Z, micro.inputs_marine(5, 0.9, micro.F5_CDR), micro.f5_derive, ("ero", "depo", "sedflux", "z", "cumdiff")))
+    for name, Z, inp, derive, keys in cases:
+        m = micro.chain_mesh(Z)
+        eng = Engine(m, inp, 1, shuffle_mode=0, force_generic=generic)
+        eng.reset(np.array([micro.F4_RAIN]), np.array([micro.F4_EROD]), np.array([1], dtype=np.int64))
+        eng.step(5000.0)
+        sc = eng.scalars()
+        assert sc["last_dt"][0] == micro.F4_DT and sc["status"][0] == 0, (name, sc)
+        exp = derive()
+        for k in keys:
+            assert np.array_equal(eng.field(k, 0), np.asarray(exp[k])), (name, generic, k)

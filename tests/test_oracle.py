@@ -251,3 +251,46 @@ def test_micro_f3_drainage_dedup_hit():
     f = micro.F3
     d1, d2 = om.basindrainage_routine(f["pitID"], f["pitVol"], f["rcv"], f["fillH"], -1000.0)
     assert d1.tolist() == f["pitDrain"] and d2.tolist() == f["pitDrain"]
+
+
+def _marine_step(Z, inp):
+    import micro
+    from oracle import oracle
+    m = micro.chain_mesh(Z)
+    om = oracle.OracleModel(m, inp, seed=1, shuffle_mode=0)
+    om.reset(micro.F4_RAIN, micro.F4_EROD, seed=1)
+    om.streamflow()
+    fillH = om.fillH.copy()
+    om.sediment_flux(5000.0)
+    assert om.last_dt == micro.F4_DT
+    return om, fillH
+
+
+def test_micro_f4_marine_distribution_both_exits():
+    """PDalgo.f90:136-269: F4a (ramp) - the share stays / the rest moves to the lowest neighbour; F4b (sill) - the walk
+    ends in a marine pit, raises it above its rim and restarts from the entry node."""
+    import micro
+    om, _ = _marine_step(micro.F4A_Z, micro.inputs_marine(5, 0.9))
+    exp = micro.f4a_derive()
+    assert exp["diffsed"][3] > 9.0 and exp["diffsed"][4] > 9.9 and exp["z"][4] < 0.0      # the ramp keeps both under water
+    for k in ("Q", "ero", "depo", "sedflux", "z"):
+        assert np.array_equal(np.asarray(getattr(om, k)), np.asarray(exp[k])), ("F4a", k)
+    assert np.array_equal(om.cumdiff, exp["sedflux"])
+    om, fillH = _marine_step(micro.F4B_Z, micro.inputs_marine(1, 0.1))
+    exp = micro.f4b_derive()
+    assert exp["z"][3] == micro.F4B_Z[1] + 0.1                                            # the pit bottom ends 0.1 m above the sill
+    assert np.array_equal(fillH, exp["fillH"])
+    for k in ("Q", "ero", "depo", "sedflux", "z"):
+        assert np.array_equal(np.asarray(getattr(om, k)), np.asarray(exp[k])), ("F4b", k)
+
+
+def test_micro_f5_marine_diffusion_substeps():
+    """buildFlux.py:198-247 + FLOWalgo.f90:332-388: two sub-steps (200 a, 4 a) that take every branch of diffmarine: loss to
+    a lower neighbour, gain from a higher marine neighbour, loss to a ghost node."""
+    import micro
+    om, _ = _marine_step(micro.F4A_Z, micro.inputs_marine(5, 0.9, micro.F5_CDR))
+    exp = micro.f5_derive()
+    kinds = {(k, s) for k, _, s in exp["trace"]}
+    assert kinds == {("gain", 200.0), ("loss", 200.0), ("gain", 4.0), ("loss", 4.0), ("ghost-loss", 4.0)}
+    for k in ("ero", "depo", "sedflux", "z", "cumdiff"):
+        assert np.array_equal(np.asarray(getattr(om, k)), np.asarray(exp[k])), ("F5", k)
