@@ -10,9 +10,10 @@
  * (likelihood formula, likelihood-surface argmax, MSE at truth, per-cell deviation of the shipped sweeps).
  * Pinned by hand-derived fixtures (tests/micro.py, derivations in tests/golden/README.md): fillPD incl. the capped
  * early stop and its order dependence, fstack.build, basinparameters, basindrainage(all) incl. a de-dup hit, discharge,
- * streampower incl. the two-pit overflow cascade, the land-pit proportional fill, the CFL time step.
- * "parity unpinned" (line-by-line restatements with no fixture of their own): flowcfl's slope exponent branch (n != 1),
- * getid1's newdt re-run, diffmarine, marine_distribution, the marine branch of the pit cascade (FLOWalgo.f90:979-991).
+ * streampower incl. the two-pit overflow cascade and its marine branch (FLOWalgo.f90:979-991), the land-pit proportional fill,
+ * the CFL time step incl. n != 1, getid1's newdt re-run, marine_distribution (every exit of the walk), diffmarine and its
+ * sub-step loop.  No routine of the path is left "parity unpinned"; the fixtures are 1-D chains, so neighbour-order effects on
+ * a real TIN are pinned only where the reference's own sfd.c covers them (receivers, hillslope diffusion).
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  */

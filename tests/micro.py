@@ -362,3 +362,147 @@ def f5_derive():
         for g in (2, 3, 4):
             H[g] += d[g] * step; z[g] += d[g] * step; cum[g] += d[g] * step
     return dict(z=z, cumdiff=cum, trace=trace, ero=f["ero"], depo=f["depo"], sedflux=f["sedflux"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# F6  overfilled closed basin: getid1 and the re-run of the stream power law with the shortened step
+#     (FLOWalgo.f90:1047-1086, flowNetwork.py:662-700)
+# positions:   0(g0)  1     2     3     4    5(g1)      ids: g0 = 0, g1 = 1, position p -> id p + 1;  fill_TH = 5 m
+F6_Z = [0.0, 30.0, 10.0, 30.0, 50.0, 70.0]
+F6_RAIN, F6_EROD, F6_TH = 1.0, 2.0e-3, 5.0
+
+
+def f6_derive():
+    """The lake at id 3 is capped 5 m above its bottom, 15 m below its rim: it is its own receiver on the filled surface and
+    drains to itself (a closed basin).  With the CFL step (353 a) it would receive 6.5 x its volume: getid1 finds it
+    (deposit > pitVol > 0, allDrain = pitID), the step shrinks to floor(353 x pitVol / deposit) = 54 a and stream power
+    runs again."""
+    import math
+    z = {0: 0.0, 1: 70.0, 2: 30.0, 3: 10.0, 4: 30.0, 5: 50.0}
+    W = dict(z)
+    W[3] = z[3] + F6_TH                                   # 30 + eps would stand 20.01 m deep: capped (PDalgo.f90:66-69)
+    Q = {5: AREA * F6_RAIN + 0.0}
+    Q[4] = AREA * F6_RAIN + Q[5]
+    Q[3] = AREA * F6_RAIN + Q[4]
+    Q[2] = AREA * F6_RAIN + 0.0
+    Q[0] = 0.0 + Q[2]
+    Q[1] = 0.0
+    pitVol3 = -1.0 + (W[3] - z[3]) * AREA
+    cfl = float(math.floor(DX / (F6_EROD * math.sqrt(Q[4]))))      # id 4 (Q = 2 A) is the fastest flowing node
+    rcv = {2: 0, 4: 3, 5: 4}
+
+    def spl(d):
+        dh = 0.95 * (z[d] - z[rcv[d]])
+        return -F6_EROD * 1.0 * 1.0 * math.sqrt(Q[d]) * (dh / DX), dh
+
+    def run(dt):
+        ero = {k: 0.0 for k in range(6)}
+        for d in (5, 4, 2):
+            s, dh = spl(d)
+            assert -(0.0 + s) * dt <= dh
+            ero[d] = 0.0 + s * dt * AREA
+        depo3 = 0.0 + (0.0 + (-ero[4] + (0.0 + (-ero[5] + 0.0))))   # everything that enters the closed lake stays (:1003-1008)
+        return ero, depo3
+    ero, depo3 = run(cfl)
+    assert depo3 > pitVol3 > 0.0
+    newdt = cfl * (pitVol3 / (0.0 + (depo3 + 0.0)))                 # flowNetwork.py:683-685
+    newdt = float(round(newdt - 0.5)) if newdt > 1.0 else newdt    # :687-688 (python-2 round)
+    ero, depo3 = run(newdt)
+    assert depo3 <= pitVol3
+    th = (W[3] - z[3]) * 1.0                                        # land-pit fill (flowNetwork.py:750-763)
+    th = th * ((0.0 + depo3) / (th * AREA))
+    sed = [0.0, 0.0] + [ero[k] / AREA + (th if k == 3 else 0.0) for k in range(2, 6)]
+    return dict(cfl=cfl, dt=newdt, fillH=[W[k] for k in range(6)], Q=[Q[k] for k in range(6)],
+                pitVol=[-1.0, -1.0, -1.0, pitVol3, -1.0, -1.0], pitDrain=[-1, -1, -1, 3, -1, -1],
+                ero=[ero[k] for k in range(6)], depo=[0.0, 0.0, 0.0, depo3, 0.0, 0.0], sedflux=sed,
+                z=[z[k] + sed[k] for k in range(6)])
+
+
+# ---------------------------------------------------------------------------------------------------
+# F7  a coastal lake overflowing into the sea: the marine branch of the pit cascade (FLOWalgo.f90:979-991), the drain of a
+#     land pit at the first node below sea level (:207-210), marine_distribution leaving the domain through a ghost node
+# positions:    0(g0)   1    2    3    4     5     6    7(g1)       ids: g0 = 0, g1 = 1, position p -> id p + 1; sea level 0
+F7_Z = [-40.0, -20.0, 8.0, 2.0, 20.0, 40.0, 60.0, 80.0]
+
+
+def f7_derive():
+    """Lake at id 4 (bottom 2 m, rim id 3 at 8 m, fillH = 8 + eps, volume 60 099 m3); id 3 drains into the sea node id 2.
+    basindrainage stops at the first node below sea level: pitDrain[4] = 2, which is no pit.  The lake receives 307 992 m3:
+    it keeps its volume, the cascade moves on to `pitDrain`, finds fillH < sea there and, the donor (id 4) standing above
+    sea level, hands the excess to the donor's RECEIVER's flux (:986-989): id 3 then carries it (plus its own erosion,
+    dh = 0.99 (z - sea)) to id 2, where everything deposits (32 m under 20 m of water).  marine_distribution: rounds 1-3 stay
+    at id 2, rounds 4 and 5 leave 0.9 x the room and pass the rest to the lowest neighbour - the ghost node g0, where it is
+    dropped (border < 1, PDalgo.f90:167-170)."""
+    import math
+    z = {0: F7_Z[0], 1: F7_Z[7]}
+    for p in range(1, 7):
+        z[p + 1] = F7_Z[p]
+    W = dict(z)
+    W[4] = z[3] + EPS
+    Q = {7: AREA * F4_RAIN + 0.0}
+    for k in (6, 5, 4, 3, 2):
+        Q[k] = AREA * F4_RAIN + Q[k + 1]
+    Q[0] = 0.0 + Q[2]
+    Q[1] = 0.0
+    assert float(math.floor(DX / (F4_EROD * math.sqrt(Q[2])))) == F4_DT
+    pitVol4 = -1.0 + (W[4] - z[4]) * AREA
+    ero = {k: 0.0 for k in range(8)}
+    for d, dh in ((7, 0.95 * (z[7] - z[6])), (6, 0.95 * (z[6] - z[5])), (5, 0.95 * (z[5] - z[4])), (3, 0.99 * (z[3] - F4_SEA))):
+        spl = -F4_EROD * 1.0 * 1.0 * math.sqrt(Q[d]) * (dh / DX)
+        assert -(0.0 + spl) * F4_DT <= dh
+        ero[d] = 0.0 + spl * F4_DT * AREA
+    load4 = -ero[5] + (0.0 + (-ero[6] + (0.0 + (-ero[7] + 0.0))))
+    assert load4 > pitVol4
+    depo = {k: 0.0 for k in range(8)}
+    frac = load4 / load4
+    depo[4] = 0.0 + (pitVol4 - 0.0) * frac                          # the lake keeps its volume (:1016-1020)
+    rest = (load4 - (pitVol4 - 0.0)) * frac
+    sedfl3 = 0.0 + rest                                             # fillH(pitDrain) < sea, z(donor) >= sea: to the receiver (:986-989)
+    load2 = -ero[3] + sedfl3
+    depo[2] = 0.0 + (0.0 + load2)
+    # land-pit fill of the lake (flowNetwork.py:750-763)
+    th = (W[4] - z[4]) * (depo[4] / (0.0 + depo[4]))
+    th4 = th * ((0.0 + depo[4]) / (th * AREA))
+    # marine_distribution from id 2 (water depth 20 m): neighbours g0 (-40) and id 3 (8 m -> clipped to sea level)
+    e2 = z[2]
+    share = load2 / 5.0
+    exits = []
+    for rnd in range(5):
+        vol = max(0.0, 0.9 * (min(max(z[0], z[3]), F4_SEA) - e2) * AREA)
+        assert share / AREA >= 1.0e-2
+        if share < vol:
+            e2 = e2 + share / AREA
+            exits.append("stays")
+        else:
+            e2 = e2 + vol / AREA
+            assert share - vol > 0.0 and z[0] < e2                  # the rest goes to g0 and is dropped
+            exits.append("ghost")
+    assert exits == ["stays", "stays", "stays", "ghost", "ghost"]
+    sed = [0.0] * 8
+    sed[2] = 0.0 / AREA + (0.0 + (e2 - z[2]))
+    sed[3] = ero[3] / AREA + 0.0
+    sed[4] = 0.0 / AREA + th4
+    for k in (5, 6, 7):
+        sed[k] = ero[k] / AREA + 0.0
+    return dict(fillH=[W[k] for k in range(8)], Q=[Q[k] for k in range(8)], pitVol=[-1.0] * 4 + [pitVol4] + [-1.0] * 3,
+                pitDrain=[-1, -1, -1, -1, 2, -1, -1, -1], ero=[ero[k] for k in range(8)], depo=[depo[k] for k in range(8)],
+                sedflux=sed, z=[z[k] + sed[k] for k in range(8)])
+
+
+# ---------------------------------------------------------------------------------------------------
+# F8  flowcfl with a slope exponent n != 1 (FLOWalgo.f90:299-330): dt = min over the flowing nodes of
+#     dist / (K Q^m (dz / dist)^(n - 1)), dz taken on the FILLED surface.  F2's staircase with n = 2.
+F8_N = 2.0
+
+
+def f8_cfl_dt():
+    import math
+    e = f2_derive(1.0)
+    W, rcv = e["fillH"], e["rcv"]
+    per_node = {}
+    for d in range(2, 10):
+        dz = W[d] - W[rcv[d]]
+        assert dz > 0.0
+        per_node[d] = DX / (F2_EROD * math.sqrt(e["Q"][d]) * (dz / DX))          # (dz / dist) ** (n - 1), n - 1 = 1
+    assert min(per_node, key=per_node.get) == 2                                    # the outlet node: Q = 8 A, slope 0.1
+    return float(math.floor(min(per_node.values()))), per_node

@@ -124,12 +124,15 @@ def test_micro_fixtures_on_the_device(generic):
 @pytest.mark.parametrize("generic", [False, True])
 def test_micro_marine_fixtures_on_the_device(generic):
     """F4a / F4b (marine_distribution: both exits of the walk, restart from the entry node) and F5 (two sub-steps of the
-    river-borne marine diffusion with every branch of diffmarine) through bl_step, against the hand derivation."""
+    river-borne marine diffusion with every branch of diffmarine) and F7 (a coastal lake overflowing into the sea: marine branch of
+    the pit cascade) through bl_step, against the hand derivation."""
     import micro
     from bayeslands_b200.engine import Engine
     cases = (("F4a", micro.F4A_Z, micro.inputs_marine(5, 0.9), micro.f4a_derive, ("Q", "ero", "depo", "sedflux", "z")),
              ("F4b", micro.F4B_Z, micro.inputs_marine(1, 0.1), micro.f4b_derive, ("fillH", "Q", "ero", "depo", "sedflux", "z")),
-             ("F5", micro.F4A_Z, micro.inputs_marine(5, 0.9, micro.F5_CDR), micro.f5_derive, ("ero", "depo", "sedflux", "z", "cumdiff")))
+             ("F5", micro.F4A_Z, micro.inputs_marine(5, 0.9, micro.F5_CDR), micro.f5_derive, ("ero", "depo", "sedflux", "z", "cumdiff")),
+             ("F7", micro.F7_Z, micro.inputs_marine(5, 0.9), micro.f7_derive,
+              ("fillH", "Q", "pitVol", "pitDrain", "ero", "depo", "sedflux", "z")))
     for name, Z, inp, derive, keys in cases:
         m = micro.chain_mesh(Z)
         eng = Engine(m, inp, 1, shuffle_mode=0, force_generic=generic)
@@ -140,3 +143,41 @@ def test_micro_marine_fixtures_on_the_device(generic):
         exp = derive()
         for k in keys:
             assert np.array_equal(eng.field(k, 0), np.asarray(exp[k])), (name, generic, k)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_micro_overfilled_closed_basin_on_the_device(generic):
+    """F6: getid1 finds the overfilled closed lake, the step shrinks from 353 a to 54 a and stream power runs again."""
+    import micro
+    from bayeslands_b200.engine import Engine
+    m = micro.chain_mesh(micro.F6_Z)
+    eng = Engine(m, micro.inputs(fillmax=micro.F6_TH), 1, shuffle_mode=0, force_generic=generic)
+    eng.reset(np.array([micro.F6_RAIN]), np.array([micro.F6_EROD]), np.array([1], dtype=np.int64))
+    eng.step(5000.0)
+    exp = micro.f6_derive()
+    sc = eng.scalars()
+    assert sc["last_dt"][0] == exp["dt"] == 54.0 and sc["status"][0] == 0, sc
+    for k in ("fillH", "Q", "pitVol", "pitDrain", "ero", "depo", "sedflux", "z"):
+        assert np.array_equal(eng.field(k, 0), np.asarray(exp[k])), (generic, k)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_micro_flow_cfl_slope_exponent_on_the_device(generic):
+    """F8: the CFL step with n = 2 (hand value 1767 a); the step itself against the oracle (pow(slope, 2) is libm on the host
+    and the CUDA math library on the device: 1e-12 relative instead of bit equality for the erosion)."""
+    import micro
+    from bayeslands_b200.engine import Engine
+    from oracle import oracle
+    inp = micro.inputs(fillmax=200.0)
+    inp.SPLn = micro.F8_N
+    m = micro.chain_mesh(micro.F2_Z)
+    eng = Engine(m, inp, 1, shuffle_mode=0, force_generic=generic)
+    eng.reset(np.array([micro.F2_RAIN]), np.array([micro.F2_EROD]), np.array([1], dtype=np.int64))
+    eng.step(5000.0)
+    sc = eng.scalars()
+    assert sc["last_dt"][0] == micro.f8_cfl_dt()[0] == 1767.0 and sc["status"][0] == 0, sc
+    om = oracle.OracleModel(m, inp, seed=1, shuffle_mode=0)
+    om.reset(micro.F2_RAIN, micro.F2_EROD, seed=1)
+    om.streamflow(); om.sediment_flux(5000.0)
+    for k in ("ero", "depo", "z"):
+        np.testing.assert_allclose(eng.field(k, 0), np.asarray(getattr(om, k)), rtol=1e-12, atol=0.0, err_msg=k)

@@ -294,3 +294,44 @@ def test_micro_f5_marine_diffusion_substeps():
     assert kinds == {("gain", 200.0), ("loss", 200.0), ("gain", 4.0), ("loss", 4.0), ("ghost-loss", 4.0)}
     for k in ("ero", "depo", "sedflux", "z", "cumdiff"):
         assert np.array_equal(np.asarray(getattr(om, k)), np.asarray(exp[k])), ("F5", k)
+
+
+def test_micro_f6_overfilled_closed_basin_reruns_the_step():
+    """FLOWalgo.f90:1047-1086 + flowNetwork.py:662-700: a capped lake that drains to itself would receive more than it
+    holds: the step shrinks from 353 a to 54 a and stream power runs a second time."""
+    import micro
+    from oracle import oracle
+    m = micro.chain_mesh(micro.F6_Z)
+    om = oracle.OracleModel(m, micro.inputs(fillmax=micro.F6_TH), seed=1, shuffle_mode=0)
+    om.reset(micro.F6_RAIN, micro.F6_EROD, seed=1)
+    om.streamflow(); om.sediment_flux(5000.0)
+    exp = micro.f6_derive()
+    assert (exp["cfl"], exp["dt"]) == (353.0, 54.0) and om.last_dt == 54.0 and om.reruns == 1
+    for k in ("fillH", "Q", "pitVol", "pitDrain", "ero", "depo", "sedflux", "z"):
+        assert np.array_equal(np.asarray(getattr(om, k)), np.asarray(exp[k])), k
+
+
+def test_micro_f7_coastal_lake_overflows_into_the_sea():
+    """FLOWalgo.f90:979-991 (marine branch of the pit cascade), :207-210 (a land pit drains to the first node below sea
+    level), PDalgo.f90:167-170 (marine_distribution leaves the domain through a ghost node)."""
+    import micro
+    om, fillH = _marine_step(micro.F7_Z, micro.inputs_marine(5, 0.9))
+    exp = micro.f7_derive()
+    assert exp["depo"][4] == exp["pitVol"][4] and exp["depo"][2] > 3.0e5
+    assert np.array_equal(fillH, exp["fillH"])
+    for k in ("Q", "pitVol", "pitDrain", "ero", "depo", "sedflux", "z"):
+        assert np.array_equal(np.asarray(getattr(om, k)), np.asarray(exp[k])), k
+
+
+def test_micro_f8_flow_cfl_with_slope_exponent():
+    """FLOWalgo.f90:299-330 with n = 2: the slope factor (dz / dist)^(n - 1) of the CFL condition, on the filled surface."""
+    import micro
+    from oracle import oracle
+    inp = micro.inputs(fillmax=200.0)
+    inp.SPLn = micro.F8_N
+    om = oracle.OracleModel(micro.chain_mesh(micro.F2_Z), inp, seed=1, shuffle_mode=0)
+    om.reset(micro.F2_RAIN, micro.F2_EROD, seed=1)
+    om.streamflow(); om.sediment_flux(5000.0)
+    dt, per_node = micro.f8_cfl_dt()
+    assert dt == 1767.0 and om.reruns == 0 and om.last_dt == dt
+    assert per_node[3] > 1.0e5 and per_node[6] > 1.0e5          # lake nodes: 1 cm of head on the filled surface
