@@ -45,7 +45,10 @@ B_ALG_CELL = 160.0        # bytes / grid cell / evaluation
 def load_config(name):
     from bayeslands_b200 import config, mesh
     npz, simtime, rl, el, coords, likl_sed = CONFIGS[name]
-    d = np.load(os.path.join(ROOT, "data", npz + ".npz"))
+    # every array read now: a lazily read NpzFile would share one file descriptor (and its offset) between the forked pool
+    # workers of run_reference, and concurrent reads then corrupt each other's zlib streams
+    with np.load(os.path.join(ROOT, "data", npz + ".npz")) as f:
+        d = {k: f[k] for k in f.files}
     inp = config.parse_xml(str(d["xml"]))
     m = mesh.build_from_dem(d["dem_xyz"], inp.btype, inp.Afactor)
     return d, inp, m, simtime, rl, el, np.array(coords), likl_sed
