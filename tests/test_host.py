@@ -116,3 +116,36 @@ def test_lattice_arrays_match_the_mesh_builder():
         lattice.from_mesh(r)
     # the interior uplift rate interpolated by load_tecto_map is the map itself on a lattice = DEM grid
     assert np.allclose(a.disp[1:-1, 1:-1], bump / T, rtol=0, atol=1e-18)
+
+
+def test_fv_arithmetic_on_analytic_cells():
+    """FVclass.f90:605-856 through mesh.build_fv on point sets whose Voronoi cells are known in closed form: a regular
+    triangular lattice (hexagonal cells: area sqrt(3)/2 a^2, six neighbours at distance a across Voronoi edges of
+    a / sqrt(3)) and a square lattice (square cells; the diagonal Delaunay edges Qhull has to invent between co-circular
+    points carry Voronoi edges of length zero).  Values pass through the float32 round trip of FVmethod.py:152."""
+    from bayeslands_b200 import mesh as M
+    a = 100.0
+    f32 = lambda v: float(np.float32(v))
+    # triangular lattice, 9 x 9
+    pts = np.array([[a * (i + 0.5 * (j % 2)), a * np.sqrt(3.0) / 2.0 * j] for j in range(9) for i in range(9)])
+    fv = M.build_fv(pts, res_cap=1.0e9)
+    inner = [j * 9 + i for j in range(2, 7) for i in range(2, 7)]
+    for k in inner:
+        nb = fv.neighbours[k]
+        deg = int((nb >= 0).sum())
+        assert deg == 6 and sorted(np.round(np.hypot(*(pts[nb[:6]] - pts[k]).T), 6)) == [a] * 6
+        assert np.allclose(fv.edge_length[k, :6], a, rtol=1e-6) and np.allclose(fv.vor_edges[k, :6], a / np.sqrt(3.0), rtol=1e-6)
+        assert abs(fv.control_volumes[k] - np.sqrt(3.0) / 2.0 * a * a) <= 1e-6 * a * a
+        assert fv.control_volumes[k] == f32(fv.control_volumes[k])
+    hull = [k for k in range(81) if k // 9 in (0, 8)]            # bottom and top row: on the convex hull
+    assert (fv.control_volumes[hull] == 0.0).all()               # unbounded cells export zero area (FVclass.f90:760)
+    # square lattice, 7 x 7
+    pts = np.array([[a * i, a * j] for j in range(7) for i in range(7)], dtype=np.float64)
+    fv = M.build_fv(pts, res_cap=1.0e9)
+    for k in [j * 7 + i for j in range(2, 5) for i in range(2, 5)]:
+        nb = fv.neighbours[k]; nb = nb[nb >= 0]
+        dist = np.hypot(*(pts[nb] - pts[k]).T)
+        axis = np.isclose(dist, a)
+        assert axis.sum() == 4 and np.isclose(dist[~axis], a * np.sqrt(2.0)).all()
+        assert np.allclose(fv.vor_edges[k, :len(nb)][axis], a, rtol=1e-6) and np.allclose(fv.vor_edges[k, :len(nb)][~axis], 0.0, atol=1e-6 * a)
+        assert abs(fv.control_volumes[k] - a * a) <= 1e-6 * a * a
