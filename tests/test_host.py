@@ -149,3 +149,23 @@ def test_fv_arithmetic_on_analytic_cells():
         assert axis.sum() == 4 and np.isclose(dist[~axis], a * np.sqrt(2.0)).all()
         assert np.allclose(fv.vor_edges[k, :len(nb)][axis], a, rtol=1e-6) and np.allclose(fv.vor_edges[k, :len(nb)][~axis], 0.0, atol=1e-6 * a)
         assert abs(fv.control_volumes[k] - a * a) <= 1e-6 * a * a
+
+
+def test_bench_reference_arm_prints_its_line():
+    """`bench.py --impl reference` (the CPU-oracle arm the driver runs next to the GPU arm) on the host cores: one JSON line
+    with the metric, the arm's own cpu_baseline and a zero-copy e2e block.  Also guards the fork-safety of the config
+    arrays (they are read eagerly: a lazily read NpzFile shared between the pool workers corrupted their zlib streams)."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    import bench
+    d = bench.load_config("crater_fast")[0]
+    assert isinstance(d, dict) and isinstance(d["final_elev"], np.ndarray)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "crater_fast",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "mcmc_forward_model_evals_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
