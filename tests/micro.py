@@ -506,3 +506,41 @@ def f8_cfl_dt():
         per_node[d] = DX / (F2_EROD * math.sqrt(e["Q"][d]) * (dz / DX))          # (dz / dist) ** (n - 1), n - 1 = 1
     assert min(per_node, key=per_node.get) == 2                                    # the outlet node: Q = 8 A, slope 0.1
     return float(math.floor(min(per_node.values()))), per_node
+
+
+# ---------------------------------------------------------------------------------------------------
+# F9  an eps-puddle on the tree of a boundary node (FLOWalgo.f90:150-163, :897-905, :955-967): a node less than eps above its
+#     receiver is "flooded" by fillPD (W = W(rcv) + eps > z).  basinparameters gives it the pit id of the tree's root - the
+#     ghost node, area 0 - so in streampower the load that reaches it is a pit deposit (waterH > 0) whose pit has no area:
+#     neither the routing branch (:955) nor the cascade (:967) fires and the load leaves the model.
+# positions:    0(g0)  1     2        3     4     5    6(g1)         ids: g0 = 0, g1 = 1, position p -> id p + 1
+F9_Z = [0.0, 10.0, 10.0005, 12.0, 50.0, 90.0, 130.0]
+F9_RAIN, F9_EROD = 1.0, 2.0e-3
+
+
+def f9_derive():
+    import math
+    n = 7
+    z = {0: F9_Z[0], 1: F9_Z[6]}
+    for p in range(1, 6):
+        z[p + 1] = F9_Z[p]
+    W = dict(z)
+    W[3] = z[2] + EPS                                             # 10.0005 < 10 + eps: flooded by 9.5 mm
+    Q = {6: AREA * F9_RAIN + 0.0}
+    for k in (5, 4, 3, 2):
+        Q[k] = AREA * F9_RAIN + Q[k + 1]
+    Q[0] = 0.0 + Q[2]
+    Q[1] = 0.0
+    dt = float(math.floor(DX / (F9_EROD * math.sqrt(Q[2]))))     # id 2 carries the largest discharge
+    pitID = [0, -1, -1, 0, -1, -1, -1]                            # id 3 belongs to the "pit" of the boundary node g0
+    pitVol = [-1.0 + (W[3] - z[3]) * AREA] + [-1.0] * 6
+    ero = {k: 0.0 for k in range(n)}
+    for d in (6, 5, 4, 2):                                        # id 3 is under water: no incision (:692)
+        dh = 0.95 * (z[d] - z[0 if d == 2 else d - 1])
+        spl = -F9_EROD * 1.0 * 1.0 * math.sqrt(Q[d]) * (dh / DX)
+        assert -(0.0 + spl) * dt <= dh
+        ero[d] = 0.0 + spl * dt * AREA
+    lost = -ero[4] + (0.0 + (-ero[5] + (0.0 + (-ero[6] + 0.0))))  # reaches id 3 and is dropped
+    sed = [0.0, 0.0] + [ero[k] / AREA + 0.0 for k in range(2, n)]
+    return dict(dt=dt, fillH=[W[k] for k in range(n)], pitID=pitID, pitVol=pitVol, Q=[Q[k] for k in range(n)],
+                ero=[ero[k] for k in range(n)], depo=[0.0] * n, sedflux=sed, z=[z[k] + sed[k] for k in range(n)], lost=lost)

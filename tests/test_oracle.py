@@ -335,3 +335,21 @@ def test_micro_f8_flow_cfl_with_slope_exponent():
     dt, per_node = micro.f8_cfl_dt()
     assert dt == 1767.0 and om.reruns == 0 and om.last_dt == dt
     assert per_node[3] > 1.0e5 and per_node[6] > 1.0e5          # lake nodes: 1 cm of head on the filled surface
+
+
+def test_micro_f9_eps_puddle_on_a_boundary_tree_drops_its_load():
+    """FLOWalgo.f90:150-163 + :897-967: a node flooded by less than eps on the tree of a ghost node carries the ghost's pit
+    id (area 0): the 411 851 m3 that reach it are neither routed on nor deposited."""
+    import micro
+    from oracle import oracle
+    m = micro.chain_mesh(micro.F9_Z)
+    om = oracle.OracleModel(m, micro.inputs(fillmax=200.0), seed=1, shuffle_mode=0)
+    om.reset(micro.F9_RAIN, micro.F9_EROD, seed=1)
+    om.streamflow()
+    exp = micro.f9_derive()
+    for k in ("fillH", "pitID", "pitVol", "Q"):
+        assert np.array_equal(np.asarray(getattr(om, k)), np.asarray(exp[k])), k
+    om.sediment_flux(5000.0)
+    assert om.last_dt == exp["dt"] == 223.0 and om.reruns == 0 and exp["lost"] > 4.1e5
+    for k in ("ero", "depo", "sedflux", "z"):
+        assert np.array_equal(np.asarray(getattr(om, k)), np.asarray(exp[k])), k
