@@ -2,7 +2,7 @@
  * oracle/_ref/libsfd_ref.so and tests/golden) and, by the hand-derived fixtures of tests/micro.py, fillPD, fstack.build,
  * basinparameters, basindrainage(all), discharge, streampower + pit cascade, the land-pit fill, marine_distribution (F4a / F4b)
  * and diffmarine with its sub-step loop (F5), getid1 + the re-run of the step (F6), the marine branch of the pit cascade (F7),
- * flowcfl with n != 1 (F8).  No routine of the path is left "parity unpinned"; the fixtures are 1-D chains, so neighbour-order
+ * flowcfl with n != 1 (F8), the eps-puddle on a boundary tree (F9, oracle level).  No routine of the path is left "parity unpinned"; the fixtures are 1-D chains, so neighbour-order
  * effects on a real TIN are pinned only where the reference's own sfd.c covers them (receivers, diffusion).
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared (no -ffast-math), mirroring
